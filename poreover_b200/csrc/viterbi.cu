@@ -1,0 +1,257 @@
+// Best-path decode of CTC reads (poreover / bonito kinds), fused with collapse, blank removal,
+// warp-level stream compaction and the base -> timestep mapping.
+//
+// Reference semantics:
+//   path[t] = first-index argmax over logical columns (A C G T blank)       transducer.py:27-33
+//   poreover: bases = path[t] != blank, repeats kept                          transducer.py:72-73
+//   bonito  : itertools.groupby collapse, then blanks dropped                 transducer.py:83-89
+//   mapping : timestep of each emitted base                                   pair_decode.py:114-142
+// Compare-only arithmetic, so results are bit-exact by construction.
+//
+// Fast path: one warp per read, float32, 5 states.  A lane owns 4 consecutive rows = 20 floats = five
+// 16-byte loads, so a warp consumes 2560 contiguous bytes per iteration; the next chunk's loads are
+// issued before the current chunk is reduced (2 x 2.5 KB in flight per warp).  HBM-bound: 20 B in per
+// timestep, ~2.4 B out.
+#include "common.cuh"
+
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 4;
+
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
+  int x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  total = __shfl_sync(0xffffffffu, x, 31);
+  return x - v;
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// first-index argmax of one row held in registers; cols are compile-time after inlining
+template <int LAYOUT>
+__device__ __forceinline__ int argmax5(const float* r, bool rc) {
+  // logical k -> physical column
+  float v0, v1, v2, v3, v4;
+  if (LAYOUT == POB_BLANK_LAST) {
+    v0 = rc ? r[3] : r[0];
+    v1 = rc ? r[2] : r[1];
+    v2 = rc ? r[1] : r[2];
+    v3 = rc ? r[0] : r[3];
+    v4 = r[4];
+  } else {
+    v0 = rc ? r[4] : r[1];
+    v1 = rc ? r[3] : r[2];
+    v2 = rc ? r[2] : r[3];
+    v3 = rc ? r[1] : r[4];
+    v4 = r[0];
+  }
+  int b = 0;
+  float m = v0;
+  if (v1 > m) { m = v1; b = 1; }
+  if (v2 > m) { m = v2; b = 2; }
+  if (v3 > m) { m = v3; b = 3; }
+  if (v4 > m) { m = v4; b = 4; }
+  return b;
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+viterbi5_f32_kernel(const float* __restrict__ data, const int64_t* __restrict__ row_off,
+                    const int32_t* __restrict__ row_len, const uint8_t* __restrict__ rcflag, int n, int kind, uint8_t* __restrict__ out_seq,
+                    int32_t* __restrict__ out_s2s, int8_t* __restrict__ out_path, int32_t* __restrict__ out_len,
+                    int32_t* __restrict__ out_status) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const int64_t ro = row_off[r];
+  const int T = pob_read_len(row_off, row_len, r);
+  const bool rc = rcflag ? (rcflag[r] != 0) : false;
+  const float* base = data + ro * 5;
+  const int G = (T + 3) >> 2;
+  const int nch = (G + 31) >> 5;
+  const bool aligned = (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+
+  float cur[20], nxt[20];
+  auto load_group = [&](int c, float* dst) {
+    int gi = (c << 5) + lane;
+    if (gi >= G) return;
+    int g = rc ? (G - 1 - gi) : gi;
+    const float* p = base + (size_t)g * 20;
+    if (aligned && 4 * g + 4 <= T) {
+      const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        float4 v = ldg_stream(q + i);
+        dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+      }
+    } else {
+      int nv = (T - 4 * g) * 5;
+#pragma unroll
+      for (int i = 0; i < 20; ++i) dst[i] = (i < nv) ? __ldg(p + i) : 0.f;
+    }
+  };
+
+  int carry = -1;           // path value at the last timestep of the previous chunk
+  int nout = 0;             // bases emitted so far
+  int pfirst = -1, plast = -1;
+  uint8_t* oseq = out_seq + ro;
+  int32_t* os2s = out_s2s ? out_s2s + ro : nullptr;
+  int8_t* opath = out_path ? out_path + ro : nullptr;
+
+  if (nch > 0) load_group(0, cur);
+  for (int c = 0; c < nch; ++c) {
+    if (c + 1 < nch) load_group(c + 1, nxt);
+    const int gi = (c << 5) + lane;
+    const bool have = gi < G;
+    const int g = rc ? (G - 1 - gi) : gi;
+    int pp[4];  // argmax of the lane's 4 physical rows (compile-time register indexing)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pp[j] = argmax5<LAYOUT>(cur + 5 * j, rc);
+    int p[4], tt[4];
+    bool valid[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int pr = rc ? (4 * g + 3 - j) : (4 * g + j);  // physical row of the lane's j-th logical row
+      valid[j] = have && pr < T;
+      tt[j] = rc ? (T - 1 - pr) : pr;
+      p[j] = rc ? pp[3 - j] : pp[j];
+    }
+    int last = -1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (valid[j]) last = p[j];
+    int prev = __shfl_up_sync(0xffffffffu, last, 1);
+    if (lane == 0) prev = carry;
+    carry = __shfl_sync(0xffffffffu, last, 31);  // chunks before the final one are full
+    unsigned em = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (valid[j]) {
+        bool e = (p[j] != 4) && (kind == POB_KIND_POREOVER || p[j] != prev);
+        em |= (e ? 1u : 0u) << j;
+        prev = p[j];
+        if (tt[j] == 0) pfirst = p[j];
+        if (tt[j] == T - 1) plast = p[j];
+        if (opath) opath[tt[j]] = (int8_t)p[j];
+      }
+    }
+    int cnt = __popc(em), total;
+    int off = nout + warp_excl_scan(cnt, lane, total);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (em & (1u << j)) {
+        oseq[off] = (uint8_t)("ACGT"[p[j]]);
+        if (os2s) os2s[off] = tt[j];
+        ++off;
+      }
+    }
+    nout += total;
+#pragma unroll
+    for (int i = 0; i < 20; ++i) cur[i] = nxt[i];
+  }
+  pfirst = __reduce_max_sync(0xffffffffu, pfirst);
+  plast = __reduce_max_sync(0xffffffffu, plast);
+  if (lane == 0) {
+    out_len[r] = nout;
+    int st = (T == 0) ? POB_ST_EMPTY : 0;
+    // pair_decode.py:136 compares path[0] with path[-1]; equal bases drop the first one
+    if (kind == POB_KIND_BONITO && T > 0 && pfirst != 4 && pfirst == plast) st |= POB_ST_MAPPING_WRAP;
+    if (out_status) out_status[r] = st;
+  }
+}
+
+// Generic path: any dtype, 2 <= S <= 9, one row per lane.
+template <typename TIn>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+viterbi_generic_kernel(const TIn* __restrict__ data, const int64_t* __restrict__ row_off,
+                       const int32_t* __restrict__ row_len, const uint8_t* __restrict__ rcflag, int n, int S, int layout, int kind,
+                       uint8_t* __restrict__ out_seq, int32_t* __restrict__ out_s2s, int8_t* __restrict__ out_path,
+                       int32_t* __restrict__ out_len, int32_t* __restrict__ out_status) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const int64_t ro = row_off[r];
+  const int T = pob_read_len(row_off, row_len, r);
+  const bool rc = rcflag ? (rcflag[r] != 0) : false;
+  const TIn* base = data + ro * S;
+  const int blank = S - 1;
+  int carry = -1, nout = 0, pfirst = -1, plast = -1;
+  uint8_t* oseq = out_seq + ro;
+  int32_t* os2s = out_s2s ? out_s2s + ro : nullptr;
+  int8_t* opath = out_path ? out_path + ro : nullptr;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    int t = t0 + lane;
+    bool valid = t < T;
+    int p = -1;
+    if (valid) {
+      const TIn* row = base + (size_t)(rc ? (T - 1 - t) : t) * S;
+      TIn m = row[pob_col(0, S, layout, rc)];
+      p = 0;
+      for (int k = 1; k < S; ++k) {
+        TIn v = row[pob_col(k, S, layout, rc)];
+        if (v > m) { m = v; p = k; }
+      }
+      if (opath) opath[t] = (int8_t)p;
+      if (t == 0) pfirst = p;
+      if (t == T - 1) plast = p;
+    }
+    int prev = __shfl_up_sync(0xffffffffu, p, 1);
+    if (lane == 0) prev = carry;
+    carry = __shfl_sync(0xffffffffu, p, 31);
+    bool e = valid && p != blank && (kind == POB_KIND_POREOVER || p != prev);
+    unsigned m = __ballot_sync(0xffffffffu, e);
+    if (e) {
+      int off = nout + __popc(m & ((1u << lane) - 1));
+      oseq[off] = (uint8_t)("ACGTNNNN"[p]);
+      if (os2s) os2s[off] = t;
+    }
+    nout += __popc(m);
+  }
+  pfirst = __reduce_max_sync(0xffffffffu, pfirst);
+  plast = __reduce_max_sync(0xffffffffu, plast);
+  if (lane == 0) {
+    out_len[r] = nout;
+    int st = (T == 0) ? POB_ST_EMPTY : 0;
+    if (kind == POB_KIND_BONITO && T > 0 && pfirst != blank && pfirst == plast) st |= POB_ST_MAPPING_WRAP;
+    if (out_status) out_status[r] = st;
+  }
+}
+
+}  // namespace
+
+// Device-side entry used by the host API and by the fused pair pipeline.
+int pob_viterbi_launch(pob_ctx* ctx, const pob_reads& rd, int kind, uint8_t* out_seq, int32_t* out_s2s,
+                       int8_t* out_path, int32_t* out_len, int32_t* out_status) {
+  if (rd.n <= 0) return POB_OK;
+  dim3 block(WARPS_PER_BLOCK * 32);
+  dim3 grid((rd.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  pob_prof_scope ps(ctx, POB_K_VITERBI);
+  if (rd.dtype == POB_F32 && rd.n_states == 5) {
+    if (rd.layout == POB_BLANK_LAST)
+      viterbi5_f32_kernel<POB_BLANK_LAST><<<grid, block, 0, ctx->stream>>>(
+          (const float*)rd.data, rd.row_off, rd.row_len, rd.rc, rd.n, kind, out_seq, out_s2s, out_path, out_len, out_status);
+    else
+      viterbi5_f32_kernel<POB_BLANK_FIRST><<<grid, block, 0, ctx->stream>>>(
+          (const float*)rd.data, rd.row_off, rd.row_len, rd.rc, rd.n, kind, out_seq, out_s2s, out_path, out_len, out_status);
+  } else if (rd.dtype == POB_F32) {
+    viterbi_generic_kernel<float><<<grid, block, 0, ctx->stream>>>((const float*)rd.data, rd.row_off, rd.row_len, rd.rc, rd.n,
+                                                                   rd.n_states, rd.layout, kind, out_seq, out_s2s, out_path,
+                                                                   out_len, out_status);
+  } else {
+    viterbi_generic_kernel<double><<<grid, block, 0, ctx->stream>>>((const double*)rd.data, rd.row_off, rd.row_len, rd.rc, rd.n,
+                                                                    rd.n_states, rd.layout, kind, out_seq, out_s2s, out_path,
+                                                                    out_len, out_status);
+  }
+  POB_CUDA(cudaGetLastError());
+  return POB_OK;
+}
