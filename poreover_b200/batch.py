@@ -68,3 +68,67 @@ def viterbi_batch(arrays, kind, rc=None, layout=_lib.BLANK_LAST, return_path=Fal
     maps = [s2s[o:o + l].astype(np.int64) for o, l in zip(offs, ln[:b.n])]
     paths = [path[o:o + t].astype(np.int64) for o, t in zip(offs, b.lens)] if return_path else None
     return seqs, maps, paths, st[:b.n].copy()
+
+
+def _pack_bytes(strings):
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in strings]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in bs], out=off[1:])
+    buf = np.frombuffer(b"".join(bs) + b"\0", dtype=np.uint8).copy()
+    return buf, off
+
+
+def align_banded_batch(seqs1, seqs2, band_width=500, match=2, mismatch=-1, gap_cost=-1, device=None):
+    """Banded NW for many sequence pairs.  Returns list of (row1, row2, matches) with row strings.
+
+    replaces align.global_pair_banded (align.pyx:100-178)."""
+    n = len(seqs1)
+    for s in seqs1:
+        if len(s) == 0:
+            raise ZeroDivisionError("float division by zero")  # align.pyx:122 with l1 == 0
+    ctx = get_ctx(device)
+    b1, o1 = _pack_bytes(seqs1)
+    b2, o2 = _pack_bytes(seqs2)
+    aln_off = o1 + o2 + 8 * np.arange(n + 1, dtype=np.int64)
+    a1 = np.zeros(int(aln_off[-1]) + 1, dtype=np.uint8)
+    a2 = np.zeros(int(aln_off[-1]) + 1, dtype=np.uint8)
+    alen = np.zeros(max(n, 1), dtype=np.int32)
+    mat = np.zeros(max(n, 1), dtype=np.int32)
+    check(lib().pob_align_banded(ctx.h, _lib.HOST, ptr(b1), ptr(o1), ptr(b2), ptr(o2), n, band_width, match, mismatch,
+                                 gap_cost, ptr(a1), ptr(a2), ptr(alen), ptr(mat)), "pob_align_banded")
+    out = []
+    for p in range(n):
+        o, l = int(aln_off[p]), int(alen[p])
+        out.append((a1[o:o + l].tobytes().decode(), a2[o:o + l].tobytes().decode(), int(mat[p])))
+    return out
+
+
+def build_envelope_batch(alignments, s2s1_list, s2s2_list, U_list, V_list, padding=5, device=None):
+    """alignments: list of (row1, row2) gapped strings.  Returns list of int64 (U,2) envelopes.
+
+    replaces envelope.get_alignment_columns + envelope.build_envelope (envelope.py:26-87)."""
+    n = len(alignments)
+    ctx = get_ctx(device)
+    r1, aoff = _pack_bytes([a[0] for a in alignments])
+    r2, _ = _pack_bytes([a[1] for a in alignments])
+    alen = np.diff(aoff).astype(np.int32)
+
+    def pack_i32(lst):
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum([len(x) for x in lst], out=off[1:])
+        buf = np.zeros(int(off[-1]) + 1, dtype=np.int32)
+        for x, o in zip(lst, off[:-1]):
+            buf[o:o + len(x)] = np.asarray(x, dtype=np.int32)
+        return buf, off, np.diff(off).astype(np.int32)
+
+    m1, so1, l1 = pack_i32(s2s1_list)
+    m2, so2, l2 = pack_i32(s2s2_list)
+    U = np.asarray(U_list, dtype=np.int32)
+    V = np.asarray(V_list, dtype=np.int32)
+    eoff = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(U, out=eoff[1:])
+    env = np.zeros((int(eoff[-1]) + 1, 2), dtype=np.int32)
+    check(lib().pob_build_envelope(ctx.h, _lib.HOST, ptr(r1), ptr(r2), ptr(aoff), ptr(alen), ptr(m1), ptr(so1),
+                                   ptr(l1), ptr(m2), ptr(so2), ptr(l2), ptr(U), ptr(V), ptr(eoff), n, padding,
+                                   ptr(env)), "pob_build_envelope")
+    return [env[eoff[p]:eoff[p + 1]].astype(np.int64) for p in range(n)]

@@ -45,12 +45,6 @@ int check_reads(const pob_reads_t* r, int min_states, int max_states) {
 // total packed rows of a HOST descriptor
 size_t total_rows(const pob_reads_t* r) { return r->n > 0 ? (size_t)r->row_off[r->n] : 0; }
 
-size_t reads_bytes(const pob_reads_t* r) {
-  size_t rows = total_rows(r);
-  return pob_align_up(rows * r->n_states * elt_size(r->dtype) + 64, 256) + pob_align_up(((size_t)r->n + 1) * 8, 256) +
-         2 * pob_align_up((size_t)r->n * 4 + 4, 256) + 1024;
-}
-
 // copy a host descriptor's arrays into the arena, produce the device descriptor
 int stage_reads(pob_ctx* ctx, const pob_reads_t* h, pob_reads_t* d) {
   *d = *h;
@@ -62,6 +56,32 @@ int stage_reads(pob_ctx* ctx, const pob_reads_t* h, pob_reads_t* d) {
   POB_TRY(stage_in(ctx, h->row_len, (size_t)h->n, &d->row_len));
   POB_TRY(stage_in(ctx, h->rc, (size_t)h->n, &d->rc));
   return POB_OK;
+}
+
+// fetch an int64 offsets array (n+1) to the host regardless of where it lives
+int fetch_i64(pob_ctx* ctx, int where, const int64_t* p, size_t count, std::vector<int64_t>& out) {
+  out.resize(count);
+  if (where == POB_HOST) {
+    memcpy(out.data(), p, count * 8);
+  } else {
+    POB_CUDA(cudaMemcpyAsync(out.data(), p, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    POB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return POB_OK;
+}
+int fetch_i32(pob_ctx* ctx, int where, const int32_t* p, size_t count, std::vector<int32_t>& out) {
+  out.resize(count);
+  if (where == POB_HOST) {
+    memcpy(out.data(), p, count * 4);
+  } else {
+    POB_CUDA(cudaMemcpyAsync(out.data(), p, count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    POB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return POB_OK;
+}
+template <typename T>
+int upload(pob_ctx* ctx, const std::vector<T>& h, const T** dev) {
+  return stage_in(ctx, h.data(), h.size(), dev);
 }
 
 }  // namespace
@@ -81,9 +101,7 @@ int pob_viterbi(pob_ctx* ctx, int where, const pob_reads_t* reads, int kind, uin
   if (where == POB_DEVICE)
     return pob_viterbi_launch(ctx, *reads, kind, out_seq, out_s2s, out_path, out_len, out_status);
   const size_t rows = total_rows(reads);
-  pob_arena_plan pl;
-  pl.add(reads_bytes(reads)); pl.add(rows + 4); pl.add(rows * 4 + 4); pl.add(rows + 4); pl.add(n * 4); pl.add(n * 4);
-  POB_TRY(pob_arena_reserve(ctx, pl.total));
+  POB_TRY(pob_arena_reset(ctx));
   pob_reads_t d;
   POB_TRY(stage_reads(ctx, reads, &d));
   uint8_t* d_seq; int32_t* d_s2s; int8_t* d_path; int32_t *d_len, *d_st;
@@ -106,14 +124,99 @@ int pob_viterbi(pob_ctx* ctx, int where, const pob_reads_t* reads, int kind, uin
 int pob_viterbi_flipflop(pob_ctx*, int, const pob_reads_t*, const double*, uint8_t*, int32_t*, int8_t*, int32_t*) {
   return POB_EUNSUPPORTED;
 }
-int pob_align_banded(pob_ctx*, int, const uint8_t*, const int64_t*, const uint8_t*, const int64_t*, int, int, int, int,
-                     int, uint8_t*, uint8_t*, int32_t*, int32_t*) {
-  return POB_EUNSUPPORTED;
+int pob_align_banded(pob_ctx* ctx, int where, const uint8_t* seq1, const int64_t* off1, const uint8_t* seq2,
+                     const int64_t* off2, int n, int band, int match, int mismatch, int gap, uint8_t* out_a1,
+                     uint8_t* out_a2, int32_t* out_alen, int32_t* out_matches) {
+  if (!ctx || n < 0 || band < 0) return POB_EINVAL;
+  if (n == 0) return POB_OK;
+  if (!seq1 || !seq2 || !off1 || !off2 || !out_a1 || !out_a2 || !out_alen) return POB_EINVAL;
+  POB_CUDA(cudaSetDevice(ctx->device));
+  POB_TRY(pob_arena_reset(ctx));
+  std::vector<int64_t> o1, o2;
+  POB_TRY(fetch_i64(ctx, where, off1, (size_t)n + 1, o1));
+  POB_TRY(fetch_i64(ctx, where, off2, (size_t)n + 1, o2));
+  const int SZ = pob_nw_slots(band);
+  std::vector<int64_t> m_off(n + 1), rb_off(n + 1), aln_off(n + 1);
+  m_off[0] = rb_off[0] = 0;
+  for (int p = 0; p < n; ++p) {
+    int64_t l1 = o1[p + 1] - o1[p], l2 = o2[p + 1] - o2[p];
+    int64_t D = (l1 > 0 && l2 > 0) ? l1 + l2 - 1 : 0;
+    m_off[p + 1] = m_off[p] + D * SZ;
+    rb_off[p + 1] = rb_off[p] + 2 * l1;
+    aln_off[p] = o1[p] + o2[p] + 8 * (int64_t)p;
+  }
+  aln_off[n] = o1[n] + o2[n] + 8 * (int64_t)n;
+  const uint8_t *d_s1 = seq1, *d_s2 = seq2;
+  const int64_t *d_o1 = off1, *d_o2 = off2;
+  uint8_t *d_a1 = out_a1, *d_a2 = out_a2;
+  int32_t *d_alen = out_alen, *d_match = out_matches;
+  if (where == POB_HOST) {
+    POB_TRY(stage_in(ctx, seq1, (size_t)o1[n], &d_s1));
+    POB_TRY(stage_in(ctx, seq2, (size_t)o2[n], &d_s2));
+    POB_TRY(stage_in(ctx, off1, (size_t)n + 1, &d_o1));
+    POB_TRY(stage_in(ctx, off2, (size_t)n + 1, &d_o2));
+    POB_TRY(stage_out(ctx, out_a1, (size_t)aln_off[n], &d_a1));
+    POB_TRY(stage_out(ctx, out_a2, (size_t)aln_off[n], &d_a2));
+    POB_TRY(stage_out(ctx, out_alen, (size_t)n, &d_alen));
+    POB_TRY(stage_out(ctx, out_matches, (size_t)n, &d_match));
+  }
+  const int64_t *d_moff, *d_rboff, *d_alnoff;
+  POB_TRY(upload(ctx, m_off, &d_moff));
+  POB_TRY(upload(ctx, rb_off, &d_rboff));
+  POB_TRY(upload(ctx, aln_off, &d_alnoff));
+  int32_t *M, *rowband;
+  POB_TRY(pob_take(ctx, (size_t)m_off[n] + 1, &M));
+  POB_TRY(pob_take(ctx, (size_t)rb_off[n] + 1, &rowband));
+  POB_TRY(pob_nw_launch(ctx, d_s1, d_o1, nullptr, d_s2, d_o2, nullptr, nullptr, n, band, match, mismatch, gap, SZ,
+                        d_moff, M, d_rboff, rowband, d_alnoff, d_a1, d_a2, d_alen, d_match));
+  if (where == POB_HOST) {
+    POB_TRY(copy_back(ctx, out_a1, d_a1, (size_t)aln_off[n]));
+    POB_TRY(copy_back(ctx, out_a2, d_a2, (size_t)aln_off[n]));
+    POB_TRY(copy_back(ctx, out_alen, d_alen, (size_t)n));
+    POB_TRY(copy_back(ctx, out_matches, d_match, (size_t)n));
+  }
+  // scratch sizes came from host-side offsets, so the stream is drained before the arena can be reused
+  POB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return POB_OK;
 }
-int pob_build_envelope(pob_ctx*, int, const uint8_t*, const uint8_t*, const int64_t*, const int32_t*, const int32_t*,
-                       const int64_t*, const int32_t*, const int32_t*, const int64_t*, const int32_t*, const int32_t*,
-                       const int32_t*, const int64_t*, int, int, int32_t*) {
-  return POB_EUNSUPPORTED;
+
+int pob_build_envelope(pob_ctx* ctx, int where, const uint8_t* a1, const uint8_t* a2, const int64_t* aln_off,
+                       const int32_t* alen, const int32_t* s2s1, const int64_t* soff1, const int32_t* slen1,
+                       const int32_t* s2s2, const int64_t* soff2, const int32_t* slen2, const int32_t* U,
+                       const int32_t* V, const int64_t* env_off, int n, int padding, int32_t* out_env) {
+  if (!ctx || n < 0) return POB_EINVAL;
+  if (n == 0) return POB_OK;
+  if (!a1 || !a2 || !aln_off || !alen || !s2s1 || !soff1 || !slen1 || !s2s2 || !soff2 || !slen2 || !U || !V ||
+      !env_off || !out_env)
+    return POB_EINVAL;
+  POB_CUDA(cudaSetDevice(ctx->device));
+  if (where == POB_DEVICE)
+    return pob_envelope_launch(ctx, a1, a2, aln_off, alen, s2s1, soff1, slen1, s2s2, soff2, slen2, U, V, env_off,
+                               nullptr, n, padding, out_env);
+  POB_TRY(pob_arena_reset(ctx));
+  const uint8_t *d_a1, *d_a2;
+  const int64_t *d_aoff, *d_so1, *d_so2, *d_eoff;
+  const int32_t *d_alen, *d_m1, *d_m2, *d_l1, *d_l2, *d_U, *d_V;
+  int32_t* d_env;
+  POB_TRY(stage_in(ctx, a1, (size_t)aln_off[n], &d_a1));
+  POB_TRY(stage_in(ctx, a2, (size_t)aln_off[n], &d_a2));
+  POB_TRY(stage_in(ctx, aln_off, (size_t)n + 1, &d_aoff));
+  POB_TRY(stage_in(ctx, alen, (size_t)n, &d_alen));
+  POB_TRY(stage_in(ctx, s2s1, (size_t)soff1[n], &d_m1));
+  POB_TRY(stage_in(ctx, soff1, (size_t)n + 1, &d_so1));
+  POB_TRY(stage_in(ctx, slen1, (size_t)n, &d_l1));
+  POB_TRY(stage_in(ctx, s2s2, (size_t)soff2[n], &d_m2));
+  POB_TRY(stage_in(ctx, soff2, (size_t)n + 1, &d_so2));
+  POB_TRY(stage_in(ctx, slen2, (size_t)n, &d_l2));
+  POB_TRY(stage_in(ctx, U, (size_t)n, &d_U));
+  POB_TRY(stage_in(ctx, V, (size_t)n, &d_V));
+  POB_TRY(stage_in(ctx, env_off, (size_t)n + 1, &d_eoff));
+  POB_TRY(stage_out(ctx, out_env, (size_t)env_off[n] * 2, &d_env));
+  POB_TRY(pob_envelope_launch(ctx, d_a1, d_a2, d_aoff, d_alen, d_m1, d_so1, d_l1, d_m2, d_so2, d_l2, d_U, d_V,
+                              d_eoff, nullptr, n, padding, d_env));
+  POB_TRY(copy_back(ctx, out_env, d_env, (size_t)env_off[n] * 2));
+  POB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return POB_OK;
 }
 int pob_beam_search(pob_ctx*, int, const pob_reads_t*, int, int, uint8_t*, int32_t*, double*, int32_t*) {
   return POB_EUNSUPPORTED;

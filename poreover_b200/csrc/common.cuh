@@ -32,13 +32,17 @@ struct pob_prof_rec {
   cudaEvent_t a, b;
 };
 
+struct pob_arena_block {
+  char* ptr;
+  size_t size, used;
+};
+
 struct pob_ctx {
   int device;
   int sm_count;
   cudaStream_t stream;
-  // bump arena for per-call device scratch; grown (never shrunk) between calls
-  char* arena;
-  size_t arena_size, arena_used;
+  // bump arena for per-call device scratch: a list of blocks, consolidated into one between calls
+  std::vector<pob_arena_block> blocks;
   // pinned staging for small host<->device metadata
   char* pinned;
   size_t pinned_size;
@@ -53,21 +57,17 @@ struct pob_ctx {
   unsigned long long* d_counters;  // device side (2 x u64)
 };
 
-// Reserve `bytes` (256-B aligned) from the arena.  All reservations of one API call are made through a
-// two-pass plan: first with ctx->arena == NULL semantics to size it (arena_plan), then for real.
 static inline size_t pob_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int pob_arena_reserve(pob_ctx* ctx, size_t total_bytes);  // ensure capacity, resets the bump pointer
-void* pob_arena_take(pob_ctx* ctx, size_t bytes);         // bump allocate (after reserve)
-
-struct pob_arena_plan {
-  size_t total = 0;
-  size_t add(size_t bytes) {
-    size_t off = total;
-    total += pob_align_up(bytes ? bytes : 1, 256);
-    return off;
-  }
-};
+// Start a new API call: every block becomes free again; several blocks are merged into one.
+int pob_arena_reset(pob_ctx* ctx);
+// Bump-allocate 256-B aligned device scratch; grows by adding a block. nullptr on out-of-memory.
+void* pob_arena_take(pob_ctx* ctx, size_t bytes);
+template <typename T>
+static inline int pob_take(pob_ctx* ctx, size_t count, T** out) {
+  *out = (T*)pob_arena_take(ctx, count * sizeof(T));
+  return *out ? POB_OK : POB_ENOMEM;
+}
 
 // profiling scope: records events around a kernel launch when enabled
 struct pob_prof_scope {

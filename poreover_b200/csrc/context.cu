@@ -42,8 +42,6 @@ int pob_ctx_create(int device, pob_ctx** out) {
   POB_CUDA(cudaSetDevice(device));
   pob_ctx* c = new pob_ctx();
   c->device = device;
-  c->arena = nullptr;
-  c->arena_size = c->arena_used = 0;
   c->pinned = nullptr;
   c->pinned_size = 0;
   c->prof_on = 0;
@@ -70,7 +68,7 @@ int pob_ctx_destroy(pob_ctx* c) {
     cudaEventDestroy(r.b);
   }
   for (auto e : c->prof_pool) cudaEventDestroy(e);
-  if (c->arena) cudaFree(c->arena);
+  for (auto& b : c->blocks) cudaFree(b.ptr);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->d_counters) cudaFree(c->d_counters);
   cudaStreamDestroy(c->stream);
@@ -196,34 +194,47 @@ pob_prof_scope::~pob_prof_scope() {
   if (idx >= 0) cudaEventRecord(ctx->prof_pending[idx].b, ctx->stream);
 }
 
-int pob_arena_reserve(pob_ctx* c, size_t total) {
-  total = pob_align_up(total + 256, 1 << 20);
-  if (total > c->arena_size) {
+int pob_arena_reset(pob_ctx* c) {
+  if (c->blocks.size() > 1) {
+    // steady state is one block: merge what the previous call needed
+    size_t total = 0;
+    for (auto& b : c->blocks) total += b.size;
     POB_CUDA(cudaStreamSynchronize(c->stream));
-    if (c->arena) POB_CUDA(cudaFree(c->arena));
-    c->arena = nullptr;
-    c->arena_size = 0;
-    size_t want = total + total / 4;
-    cudaError_t e = cudaMalloc(&c->arena, want);
-    if (e != cudaSuccess) {
+    for (auto& b : c->blocks) cudaFree(b.ptr);
+    c->blocks.clear();
+    char* p = nullptr;
+    if (cudaMalloc(&p, total) == cudaSuccess) {
+      c->blocks.push_back({p, total, 0});
+    } else {
       cudaGetLastError();
-      want = total;
-      e = cudaMalloc(&c->arena, want);
     }
-    if (e != cudaSuccess) {
-      snprintf(g_pob_cuda_err, sizeof(g_pob_cuda_err), "arena cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
-      cudaGetLastError();
-      return POB_ENOMEM;
-    }
-    c->arena_size = want;
   }
-  c->arena_used = 0;
+  for (auto& b : c->blocks) b.used = 0;
   return POB_OK;
 }
 
 void* pob_arena_take(pob_ctx* c, size_t bytes) {
-  size_t off = c->arena_used;
-  c->arena_used += pob_align_up(bytes ? bytes : 1, 256);
-  if (c->arena_used > c->arena_size) return nullptr;
-  return c->arena + off;
+  bytes = pob_align_up(bytes ? bytes : 1, 256);
+  for (auto& b : c->blocks) {
+    if (b.used + bytes <= b.size) {
+      void* p = b.ptr + b.used;
+      b.used += bytes;
+      return p;
+    }
+  }
+  size_t want = pob_align_up(bytes + bytes / 8, (size_t)8 << 20);
+  char* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&p, want);
+  }
+  if (e != cudaSuccess) {
+    snprintf(g_pob_cuda_err, sizeof(g_pob_cuda_err), "arena cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+    cudaGetLastError();
+    return nullptr;
+  }
+  c->blocks.push_back({p, want, bytes});
+  return p;
 }
