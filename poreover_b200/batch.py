@@ -132,3 +132,103 @@ def build_envelope_batch(alignments, s2s1_list, s2s2_list, U_list, V_list, paddi
                                    ptr(l1), ptr(m2), ptr(so2), ptr(l2), ptr(U), ptr(V), ptr(eoff), n, padding,
                                    ptr(env)), "pob_build_envelope")
     return [env[eoff[p]:eoff[p + 1]].astype(np.int64) for p in range(n)]
+
+
+def _as_batch(arrays, rc=None, layout=_lib.BLANK_LAST):
+    return arrays if isinstance(arrays, ReadBatch) else ReadBatch(arrays, rc=rc, layout=layout)
+
+
+def beam_search_batch(arrays, beam_width=25, model="ctc", rc=None, layout=_lib.BLANK_LAST, device=None):
+    """CTC prefix beam search over many single reads.  Returns (sequences, scores, status).
+
+    replaces decoding_cpp.cpp_beam_search (decoding_cpp.pyx:88-103)."""
+    if model not in _lib.MODEL:
+        raise ValueError("unknown model %r (the reference falls off the end of beam_search, BeamSearch.h:400-408)" % model)
+    b = _as_batch(arrays, rc, layout)
+    ctx = get_ctx(device)
+    n = b.n
+    seq = np.zeros(max(b.total_rows, 1) + 4, dtype=np.uint8)
+    ln = np.zeros(max(n, 1), dtype=np.int32)
+    sc = np.zeros(max(n, 1), dtype=np.float64)
+    st = np.zeros(max(n, 1), dtype=np.int32)
+    rs = b.struct()
+    check(lib().pob_beam_search(ctx.h, _lib.HOST, C.byref(rs), int(beam_width), _lib.MODEL[model], ptr(seq), ptr(ln),
+                                ptr(sc), ptr(st)), "pob_beam_search")
+    seqs = [seq[o:o + l].tobytes().decode() for o, l in zip(b.row_off[:-1], ln[:n])]
+    return seqs, sc[:n].copy(), st[:n].copy()
+
+
+def beam_search_2d_batch(arrays1, arrays2, envelopes=None, beam_width=25, model="ctc", method="row", rc1=None,
+                         rc2=None, layout=_lib.BLANK_LAST, device=None):
+    """Joint two-read prefix beam search.  envelopes: list of (U,2) int arrays or None.
+
+    replaces decoding_cpp.cpp_beam_search_2d (decoding_cpp.pyx:107-139).  Returns (sequences, scores, status)."""
+    if model not in _lib.MODEL:
+        raise ValueError("unknown model %r" % model)
+    if method not in _lib.METHOD:
+        raise ValueError("unknown method %r (only 'row' and 'row_col' are built; 'grid' is out of scope)" % method)
+    b1 = _as_batch(arrays1, rc1, layout)
+    b2 = _as_batch(arrays2, rc2, layout)
+    n = b1.n
+    if envelopes is None and method == "row_col":
+        raise ValueError("method 'row_col' needs an envelope (the reference dereferences a null envelope)")
+    ctx = get_ctx(device)
+    env = env_off = None
+    if envelopes is not None:
+        env_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(b1.lens, out=env_off[1:])
+        env = np.zeros((int(env_off[-1]) + 1, 2), dtype=np.int32)
+        for p, e in enumerate(envelopes):
+            e = np.asarray(e, dtype=np.int32).reshape(-1, 2)  # decoding_cpp.pyx:121: np.intc
+            if e.shape[0] < b1.lens[p]:
+                raise ValueError("envelope of pair %d has %d rows, read 1 has %d timesteps" % (p, e.shape[0], b1.lens[p]))
+            env[env_off[p]:env_off[p + 1]] = e[:b1.lens[p]]
+    out_off = (b1.row_off + b2.row_off).astype(np.int64)
+    seq = np.zeros(int(out_off[-1]) + 8, dtype=np.uint8)
+    ln = np.zeros(max(n, 1), dtype=np.int32)
+    sc = np.zeros(max(n, 1), dtype=np.float64)
+    st = np.zeros(max(n, 1), dtype=np.int32)
+    s1, s2 = b1.struct(), b2.struct()
+    check(lib().pob_beam_search_2d(ctx.h, _lib.HOST, C.byref(s1), C.byref(s2), ptr(env), ptr(env_off), int(beam_width),
+                                   _lib.MODEL[model], _lib.METHOD[method], ptr(out_off), ptr(seq), ptr(ln), ptr(sc),
+                                   ptr(st)), "pob_beam_search_2d")
+    seqs = [seq[o:o + l].tobytes().decode() for o, l in zip(out_off[:-1], ln[:n])]
+    return seqs, sc[:n].copy(), st[:n].copy()
+
+
+def pair_decode_batch(arrays1, arrays2, kind="bonito", beam_width=25, padding=5, band_width=500, method="row_col",
+                      rc2=True, rc1=False, layout=_lib.BLANK_LAST, device=None):
+    """The whole pair-decode hot path for many pairs in one call (pair_decode.py:361-398, :495-511).
+
+    arrays: log-probabilities as the loader produced them; rc2=True is --reverse_complement.
+    Returns one dict per pair: basecall1, basecall2, consensus, score, identity, skipped, status."""
+    b1 = _as_batch(arrays1, rc1 if rc1 is not None else None, layout)
+    b2 = _as_batch(arrays2, rc2 if rc2 is not None else None, layout)
+    n = b1.n
+    ctx = get_ctx(device)
+    seq1 = np.zeros(max(b1.total_rows, 1) + 4, dtype=np.uint8)
+    seq2 = np.zeros(max(b2.total_rows, 1) + 4, dtype=np.uint8)
+    cons = np.zeros(b1.total_rows + b2.total_rows + 8, dtype=np.uint8)
+    l1 = np.zeros(max(n, 1), dtype=np.int32)
+    l2 = np.zeros(max(n, 1), dtype=np.int32)
+    lc = np.zeros(max(n, 1), dtype=np.int32)
+    sc = np.zeros(max(n, 1), dtype=np.float64)
+    stats = np.zeros((max(n, 1), 4), dtype=np.int32)
+    st = np.zeros(max(n, 1), dtype=np.int32)
+    s1, s2 = b1.struct(), b2.struct()
+    check(lib().pob_pair_decode(ctx.h, _lib.HOST, C.byref(s1), C.byref(s2), _lib.KIND[kind], int(beam_width),
+                                int(padding), int(band_width), _lib.METHOD[method], ptr(seq1), ptr(l1), ptr(seq2),
+                                ptr(l2), ptr(cons), ptr(lc), ptr(sc), ptr(stats), ptr(st)), "pob_pair_decode")
+    out = []
+    skip_mask = _lib.ST_SKIPPED_LENGTH | _lib.ST_SKIPPED_IDENTITY | _lib.ST_MAPPING_WRAP | _lib.ST_EMPTY
+    for p in range(n):
+        o1, o2 = int(b1.row_off[p]), int(b2.row_off[p])
+        r = {"basecall1": seq1[o1:o1 + l1[p]].tobytes().decode(), "basecall2": seq2[o2:o2 + l2[p]].tobytes().decode(),
+             "status": int(st[p]), "skipped": 1 if (st[p] & skip_mask) else 0, "length1": int(l1[p]), "length2": int(l2[p])}
+        if stats[p, 3] > 0:
+            r["identity"] = stats[p, 2] / stats[p, 3]  # np.sum(a0 == a1) / len(a0)  (pair_decode.py:391)
+        if not r["skipped"]:
+            r["consensus"] = cons[o1 + o2:o1 + o2 + lc[p]].tobytes().decode()
+            r["score"] = float(sc[p])
+        out.append(r)
+    return out

@@ -19,3 +19,11 @@ int pob_envelope_launch(pob_ctx* ctx, const uint8_t* a1, const uint8_t* a2, cons
 int pob_envelope_transpose_launch(pob_ctx* ctx, const int32_t* env, const int64_t* env_off, const int32_t* U,
                                   const int32_t* V, const int64_t* envt_off, const int32_t* skip, int n,
                                   int32_t* envt, int32_t* span);
+
+enum { POB_MODE_1D = 0, POB_MODE_ROW = 1, POB_MODE_ROWCOL = 2 };
+int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, const int32_t* env,
+                    const int64_t* env_off, const int32_t* envt, const int64_t* envt_off, const int32_t* order,
+                    const int32_t* skip, int n_items, int n_total, int W, int model, int mode, int max_span0,
+                    int max_span1, int Umax, int Vmax, const int64_t* trace_off, uint32_t* trace, int32_t* top,
+                    const int64_t* out_off, uint8_t* out_seq, int32_t* out_len, double* out_score,
+                    int32_t* out_status);

@@ -1,1 +1,3 @@
 from . import transducer  # noqa: F401
+from . import decoding_cpp  # noqa: F401
+from . import envelope  # noqa: F401

@@ -1,0 +1,47 @@
+"""Drop-in for the reference's Cython module poreover/decoding/decoding_cpp.pyx: same function names,
+arguments, defaults and return values; the searches run on the GPU (poreover_b200/csrc/beam.cu)."""
+import numpy as np
+
+from .. import batch
+
+
+def _prep(y_):
+    y = np.asarray(y_)
+    if y.dtype != np.float32:
+        y = np.asarray(y, dtype=np.float64)  # decoding_cpp.pyx:96: coerced to float64
+    return np.ascontiguousarray(y)
+
+
+def _check_alphabet(alphabet_, y):
+    if len(alphabet_) != 4 or y.shape[1] != 5:
+        raise NotImplementedError(
+            "the GPU searches are built for the 4-letter alphabet (5 states); got alphabet %r, %d states"
+            % (alphabet_, y.shape[1]))
+
+
+def _spell(seq, alphabet_):
+    return seq if alphabet_ == "ACGT" else seq.translate(str.maketrans("ACGT", alphabet_))
+
+
+def cpp_beam_search(y_, beam_width_=25, alphabet_="ACGT", model_="ctc"):
+    """decoding_cpp.pyx:88-103 -> beam_search (BeamSearch.h:400) -> beam_search_ (:18-58)."""
+    y = _prep(y_)
+    _check_alphabet(alphabet_, y)
+    seqs, _, _ = batch.beam_search_batch([y], beam_width_, model_)
+    return _spell(seqs[0], alphabet_)
+
+
+def cpp_beam_search_2d(y1_, y2_, envelope_ranges_=None, beam_width_=25, alphabet_="ACGT", model_="ctc", method_="row"):
+    """decoding_cpp.pyx:107-139 -> beam_search (BeamSearch.h:411 / :440)."""
+    y1, y2 = _prep(y1_), _prep(y2_)
+    _check_alphabet(alphabet_, y1)
+    if y1.dtype != y2.dtype:
+        y1, y2 = y1.astype(np.float64), y2.astype(np.float64)
+    env = None if envelope_ranges_ is None else [np.asarray(envelope_ranges_, dtype=np.intc)]
+    seqs, _, _ = batch.beam_search_2d_batch([y1], [y2], env, beam_width_, model_, method_)
+    return _spell(seqs[0], alphabet_)
+
+
+def cpp_forward(y_, label_, alphabet_="ACGT", model_="ctc"):
+    """decoding_cpp.pyx:49-65 -> forward (PrefixTree.h:710-759)."""
+    raise NotImplementedError("cpp_forward is not built on the GPU backend yet (SURVEY.md section 8(f) rank 4)")
