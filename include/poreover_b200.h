@@ -109,6 +109,9 @@ enum {
   POB_K_VITERBI = 0, POB_K_FLIPFLOP = 1, POB_K_NW_FILL = 2, POB_K_NW_TRACE = 3, POB_K_ENVELOPE = 4,
   POB_K_BEAM_2D = 5, POB_K_BEAM_1D = 6, POB_K_BACKTRACE = 7, POB_K_FORWARD = 8, POB_K_COUNT = 9
 };
+/* whole-region device timing: CUDA events recorded on the context's stream */
+int pob_timer_start(pob_ctx* ctx);
+int pob_timer_stop(pob_ctx* ctx, double* ms); /* records the stop event, synchronises, returns elapsed ms */
 int pob_profile_enable(pob_ctx* ctx, int on);
 int pob_profile_reset(pob_ctx* ctx);
 /* synchronises, then returns accumulated device milliseconds and launch count of kernel `id` */

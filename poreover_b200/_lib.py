@@ -44,6 +44,8 @@ SIGNATURES = {
     "pob_free_host": (i32, [vp]),
     "pob_memcpy_h2d": (i32, [vp, vp, vp, C.c_size_t]),
     "pob_memcpy_d2h": (i32, [vp, vp, vp, C.c_size_t]),
+    "pob_timer_start": (i32, [vp]),
+    "pob_timer_stop": (i32, [vp, C.POINTER(dbl)]),
     "pob_profile_enable": (i32, [vp, i32]),
     "pob_profile_reset": (i32, [vp]),
     "pob_profile_get": (i32, [vp, i32, C.POINTER(dbl), C.POINTER(i64)]),
@@ -147,6 +149,14 @@ class Context:
         check(lib().pob_memcpy_d2h(self.h, out.ctypes.data_as(vp), vp(ptr), out.nbytes), "d2h")
         self.sync()
         return out
+
+    def timer_start(self):
+        check(lib().pob_timer_start(self.h), "pob_timer_start")
+
+    def timer_stop(self):
+        ms = dbl(0)
+        check(lib().pob_timer_stop(self.h, C.byref(ms)), "pob_timer_stop")
+        return ms.value
 
     # profiling ---------------------------------------------------------------
     def profile(self, on=True):

@@ -55,6 +55,7 @@ struct pob_ctx {
   // counters
   int64_t counters[3];
   unsigned long long* d_counters;  // device side (2 x u64)
+  cudaEvent_t t0, t1;              // pob_timer_*
 };
 
 static inline size_t pob_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -49,6 +49,7 @@ int pob_ctx_create(int device, pob_ctx** out) {
   memset(c->prof_n, 0, sizeof(c->prof_n));
   memset(c->counters, 0, sizeof(c->counters));
   c->d_counters = nullptr;
+  c->t0 = c->t1 = nullptr;
   cudaDeviceProp p;
   POB_CUDA(cudaGetDeviceProperties(&p, device));
   c->sm_count = p.multiProcessorCount;
@@ -117,6 +118,25 @@ int pob_memcpy_h2d(pob_ctx* c, void* dst, const void* src, size_t bytes) {
 int pob_memcpy_d2h(pob_ctx* c, void* dst, const void* src, size_t bytes) {
   if (!c) return POB_EINVAL;
   POB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return POB_OK;
+}
+
+int pob_timer_start(pob_ctx* c) {
+  if (!c) return POB_EINVAL;
+  if (!c->t0) {
+    POB_CUDA(cudaEventCreate(&c->t0));
+    POB_CUDA(cudaEventCreate(&c->t1));
+  }
+  POB_CUDA(cudaEventRecord(c->t0, c->stream));
+  return POB_OK;
+}
+int pob_timer_stop(pob_ctx* c, double* ms) {
+  if (!c || !ms || !c->t0) return POB_EINVAL;
+  POB_CUDA(cudaEventRecord(c->t1, c->stream));
+  POB_CUDA(cudaEventSynchronize(c->t1));
+  float f = 0;
+  POB_CUDA(cudaEventElapsedTime(&f, c->t0, c->t1));
+  *ms = f;
   return POB_OK;
 }
 

@@ -1,0 +1,83 @@
+"""Multi-GPU sharding of pair-decode: one process per GPU, a host work queue, results gathered on the host.
+
+Read pairs are independent (the reference treats them so: pair_decode.py:292-297), so there is NO data-path
+collective.  Ranks pull chunks of pairs from a shared counter (torch.distributed's TCPStore `add`, i.e. an
+atomic fetch-and-add on the host), longest pairs first so the tail is short, and rank 0 collects the
+per-pair records with gather_object over the host (gloo) group.  Single process: plain loop.
+"""
+import os
+
+
+def dist_info():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+class WorkQueue:
+    """Chunked dynamic queue over range(n_items) shared by all ranks of a torch.distributed job."""
+
+    def __init__(self, n_items, chunk, store=None, key="poreover_b200_queue"):
+        self.n, self.chunk, self.store, self.key = n_items, max(1, chunk), store, key
+        self._local = 0
+
+    def next(self):
+        if self.store is None:
+            k = self._local
+            self._local += 1
+        else:
+            k = self.store.add(self.key, 1) - 1  # atomic on the store's host
+        lo = k * self.chunk
+        if lo >= self.n:
+            return None
+        return lo, min(self.n, lo + self.chunk)
+
+
+def run_sharded(items, cost, process_chunk, chunk=256, group=None, store=None):
+    """Process `items` across all ranks.  cost[i] orders the queue (descending).  process_chunk(list) ->
+    list of results.  Returns the full result list in input order on rank 0, None elsewhere."""
+    rank, world, _ = dist_info()
+    order = sorted(range(len(items)), key=lambda i: -cost[i])
+    q = WorkQueue(len(order), chunk, store if world > 1 else None)
+    mine = {}
+    while True:
+        c = q.next()
+        if c is None:
+            break
+        idx = order[c[0]:c[1]]
+        for i, r in zip(idx, process_chunk([items[i] for i in idx])):
+            mine[i] = r
+    if world == 1:
+        return [mine.get(i) for i in range(len(items))]
+    import torch.distributed as dist
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0, group=group)
+    if rank != 0:
+        return None
+    out = [None] * len(items)
+    for part in gathered:
+        for i, r in part.items():
+            out[i] = r
+    return out
+
+
+def decode_pairs_all_gpus(args, pair_list, chunk=256):
+    """CLI path: every rank decodes the chunks it pulls on its own GPU (LOCAL_RANK)."""
+    from .decoding import pair_decode as pd
+    rank, world, local = dist_info()
+    store = group = None
+    if world > 1:
+        import datetime
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("gloo", timeout=datetime.timedelta(hours=4))
+        group = dist.group.WORLD
+        store = dist.distributed_c10d._get_default_store()
+
+    def cost_of(p):
+        try:
+            path1, _ = pd._paths(args, p)
+            return os.path.getsize(os.path.join(args.dir, path1))
+        except OSError:
+            return 0
+
+    cost = [cost_of(p) for p in pair_list]
+    return run_sharded(pair_list, cost, lambda sub: pd.decode_pairs(args, sub, device=local), chunk, group, store)
