@@ -22,6 +22,8 @@
 // nothing here is a contraction.  Per step the dependent chain is the time-major band sweep: threads
 // own (node, read) items, carry their own t-1 values in registers and exchange parent values through
 // double-buffered shared memory, one barrier per time sub-step.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "launch.cuh"
 
@@ -66,6 +68,8 @@ struct BeamParams {
   const int32_t* order;     // item processing order or NULL
   const int32_t* skip;      // per item != 0 -> not searched
   int n_items, W, mode, NP, CAP0, CAP1, RQ, EMAX;
+  int dbg_noreclaim, dbg_step;
+  double* dbg_trace;  // optional: [step][2] = (top score, sum of beam scores) after each prune of item 0
   char* ws;                 // workspace, one stride per resident CTA
   size_t ws_stride;
   uint32_t* trace;
@@ -116,13 +120,16 @@ __device__ __forceinline__ ReadView make_view(const pob_reads& r, int item) {
 template <int MODEL>
 struct Engine {
   typedef Entry<MODEL> Ent;
-  const BeamParams& P;
+  // copied launch parameters (the engine object lives in shared memory: one copy per CTA)
+  struct { int W, NP, RQ, EMAX, mode, noreclaim; } P;
   // workspace views
   NodeHdr* hdr;
   Ent* win[2];
   int32_t* freelist;
   int2* retq;
   double* cum[2];  // ctc: blank prefix sums of each read (root node values, PrefixTree.h:508-514)
+  int32_t* sufmin; // ROW: min over rows >= u of the envelope's band start (band starts are NOT monotone:
+                   // build_envelope's repair pass clamps some rows far back, envelope.py:82-85)
   int cap[2], mask[2];
   ReadView rv[2];
   uint32_t* trace;
@@ -142,9 +149,6 @@ struct Engine {
   int32_t* sh;       // scalars: see SH_*
   enum { SH_NB = 0, SH_NE, SH_NFREE, SH_ORDER, SH_TID, SH_STAMP, SH_RQH, SH_RQT, SH_STATUS, SH_FIRSTALIVE,
          SH_FREED, SH_NEOLD, SH_TOTALLOC, SH_TOTFIRST, SH_DMIN, SH_REPUSH, SH_COUNT };
-  unsigned long long n_updates;
-
-  __device__ Engine(const BeamParams& p) : P(p) {}
 
   __device__ __forceinline__ Ent* wptr(int slot, int r, int t) const {
     return win[r] + (size_t)slot * cap[r] + ((t + 1) & mask[r]);
@@ -158,46 +162,58 @@ struct Engine {
   }
 
   // ---- one update_prob(n, r, t) with every input read from the stored windows -------------------
-  __device__ void update_one(int slot, int r, int t) {
-    NodeHdr& h = hdr[slot];
+  // Split in two halves with a block barrier in between (update_all): when a node and its parent are
+  // updated at the same t by different threads, the child must see the parent's window bounds and t-1
+  // entry as they were BEFORE this phase (the reference reads t-1, writes t).  Reading lo/hi while the
+  // parent's thread rewrites them can otherwise pair a new hi with an old lo and admit a stale entry.
+  struct UpdIn {
+    double p_prev, ng_prev, pv, ylast, yblank;
+    int lo, hi;
+  };
+
+  __device__ __forceinline__ void update_gather(int slot, int r, int t, UpdIn& in) const {
+    const NodeHdr& h = hdr[slot];
     const int last = h.last;
-    int lo = h.lo[r], hi = h.hi[r];
-    const bool self_ok = (t - 1 >= lo && t - 1 < hi);
+    in.lo = h.lo[r]; in.hi = h.hi[r];
+    const bool self_ok = (t - 1 >= in.lo && t - 1 < in.hi);
     const Ent* se = wptr(slot, r, t - 1);
-    const double p_prev = self_ok ? se->prob : ninf();
-    const double ylast = rv[r].at(t, rv[r].pcol(last));
-    const double yblank = rv[r].at(t, rv[r].cblank);
-    // parent value at t-1
-    double pv;
+    in.p_prev = self_ok ? se->prob : ninf();
+    in.ng_prev = ninf();
+    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.ng_prev = self_ok ? se->nogap : ninf();
+    in.ylast = rv[r].at(t, rv[r].pcol(last));
+    in.yblank = rv[r].at(t, rv[r].cblank);
     const int ps = h.parent_slot;
-    bool same = false;
     if (ps < 0) {
-      pv = root_prob(r, t - 1);
+      in.pv = root_prob(r, t - 1);
     } else {
       const NodeHdr& ph = hdr[ps];
-      same = (ph.last == last);
-      if (ph.order == h.parent_order && t - 1 >= ph.lo[r] && t - 1 < ph.hi[r]) {
+      const bool same = (ph.last == last);
+      const int plo = ph.lo[r], phi = ph.hi[r];
+      if (ph.order == h.parent_order && t - 1 >= plo && t - 1 < phi) {
         const Ent* pe = wptr(ps, r, t - 1);
-        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pv = same ? pe->gap : pe->prob;
-        else pv = pe->prob;
+        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.pv = same ? pe->gap : pe->prob;
+        else in.pv = pe->prob;
       } else {
-        pv = ninf();
+        in.pv = ninf();
       }
     }
+  }
+
+  __device__ __forceinline__ void update_commit(int slot, int r, int t, const UpdIn& in) {
+    NodeHdr& h = hdr[slot];
     Ent out;
     double prob;
     if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
-      const double ng_prev = self_ok ? ((const Entry<POB_MODEL_CTC_MERGE_REPEATS>*)se)->nogap : ninf();
-      const double gp = p_prev + yblank;
-      const double ng = lae(pv + ylast, ng_prev + ylast);
+      const double gp = in.p_prev + in.yblank;
+      const double ng = lae(in.pv + in.ylast, in.ng_prev + in.ylast);
       prob = lae(gp, ng);
-      Entry<POB_MODEL_CTC_MERGE_REPEATS>* o = (Entry<POB_MODEL_CTC_MERGE_REPEATS>*)&out;
-      o->prob = prob; o->gap = gp; o->nogap = ng; o->pad = 0;
+      out.prob = prob; out.gap = gp; out.nogap = ng; out.pad = 0;
     } else {
-      prob = lae(pv + ylast, p_prev + yblank);
+      prob = lae(in.pv + in.ylast, in.p_prev + in.yblank);
       out.prob = prob;
     }
     *wptr(slot, r, t) = out;
+    int lo = in.lo, hi = in.hi;
     if (t >= hi) { if (t > hi) lo = t; hi = t + 1; }
     else if (t < lo) { lo = t; hi = t + 1; }
     if (hi - lo > cap[r]) lo = hi - cap[r];
@@ -205,32 +221,64 @@ struct Engine {
     if (prob > h.maxp[r]) h.maxp[r] = prob;
   }
 
+  // all threads call this; `mine` selects the threads that own a node (slot) this phase
+  __device__ void update_all(bool mine, int slot, int r, int t) {
+    UpdIn in;
+    if (mine) update_gather(slot, r, t, in);
+    __syncthreads();
+    if (mine) update_commit(slot, r, t, in);
+    __syncthreads();
+  }
+
   // ---- time-major band sweep over the expanded beam (BeamSearch.h:361-375, :146-156) ----------------
   // reads_mask bit r: read r swept over [t0[r], t1[r]).  Resets max_prob of the swept reads first.
-  __device__ void sweep(int nE, int reads_mask, const int* t0, const int* t1, bool reset_other) {
+  __device__ void sweep(int nE, int reads_mask, const int* t0, const int* t1, bool reset_other,
+                        unsigned long long& n_updates) {
     const int tid = threadIdx.x;
+    const int EMAX = P.EMAX;
     const int nItems = nE * 2;
     const int len0 = (reads_mask & 1) ? t1[0] - t0[0] : 0, len1 = (reads_mask & 2) ? t1[1] - t0[1] : 0;
     const int maxlen = max(len0, len1);
-    // NOTE: written for one item per thread (launcher guarantees blockDim >= 2*EMAX)
+    // one item per thread (launcher guarantees blockDim >= 2*EMAX)
     const int item = tid;
     const bool have = item < nItems;
     const int e = item >> 1, r = item & 1;
-    bool on = have && act[e] && ((reads_mask >> r) & 1);
-    int slot = 0, last = 0, pe = -1, lo = 0, hi = 0, ps = -1, plo = 0, phi = 0;
+    const bool live = have && act[e];
+    const bool on = live && ((reads_mask >> r) & 1);
+    int slot = 0, pe = -1, lo = 0, hi = 0, ps = -1, plo = 0, phi = 0;
     bool same = false, proot = false, pfrozen = false;
     double p_prev = ninf(), ng_prev = ninf(), maxv = ninf();
-    int ts = 0, te = 0, pcl = 0;
-    if (have && act[e]) slot = E[e];
+    int ts = 0, te = 0;
+    // hoisted addressing: own window, parent window, the two probability columns of this read
+    Ent* wbase = nullptr;
+    const Ent* pwbase = nullptr;
+    int wmask = 0;
+    const char* ylast_p = nullptr;
+    const char* yblank_p = nullptr;
+    long ystep = 0;
+    bool f64 = false;
+    if (live) slot = E[e];
     if (on) {
       NodeHdr& h = hdr[slot];
-      last = h.last; lo = h.lo[r]; hi = h.hi[r];
+      const int last = h.last;
+      lo = h.lo[r]; hi = h.hi[r];
       ts = t0[r]; te = t1[r];
-      pcl = rv[r].pcol(last);
+      wmask = mask[r];
+      wbase = win[r] + (size_t)slot * cap[r];
+      {
+        const ReadView v = rv[r];
+        f64 = v.f64;
+        const long es = f64 ? 8 : 4;
+        const long rowb = (long)v.S * es;
+        const char* row0 = (const char*)v.base + (long)v.prow(ts) * rowb;
+        ystep = v.rc ? -rowb : rowb;
+        ylast_p = row0 + (long)v.pcol(last) * es;
+        yblank_p = row0 + (long)v.cblank * es;
+      }
       if (ts - 1 >= lo && ts - 1 < hi) {
-        const Ent* se = wptr(slot, r, ts - 1);
+        const Ent* se = wbase + (ts & wmask);
         p_prev = se->prob;
-        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_prev = ((const Entry<POB_MODEL_CTC_MERGE_REPEATS>*)se)->nogap;
+        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_prev = se->nogap;
       }
       ps = h.parent_slot;
       if (ps < 0) proot = true;
@@ -240,17 +288,20 @@ struct Engine {
         if (ph.order != h.parent_order) { ps = -2; }  // recycled parent: every read is -inf
         else {
           pe = slot2e[ps];
-          if (pe < 0) { pfrozen = true; plo = ph.lo[r]; phi = ph.hi[r]; }
+          if (pe < 0) { pfrozen = true; plo = ph.lo[r]; phi = ph.hi[r]; pwbase = win[r] + (size_t)ps * cap[r]; }
         }
       }
       // publish the stored values at ts-1 for children whose parent is swept too
       double2 pb; pb.x = p_prev; pb.y = ninf();
       if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
-        if (ts - 1 >= lo && ts - 1 < hi) pb.y = ((const Entry<POB_MODEL_CTC_MERGE_REPEATS>*)wptr(slot, r, ts - 1))->gap;
+        if (ts - 1 >= lo && ts - 1 < hi) pb.y = (wbase + (ts & wmask))->gap;
       }
-      pub[(0 * P.EMAX + e) * 2 + r] = pb;
+      pub[(0 * EMAX + e) * 2 + r] = pb;
     }
     __syncthreads();
+    const double2* pub_rd = pub + (size_t)(pe < 0 ? 0 : pe) * 2 + r;
+    double2* pub_wr = pub + (size_t)e * 2 + r;
+    const int pstride = EMAX * 2;
     for (int it = 0; it < maxlen; ++it) {
       const int t = ts + it;
       const bool go = on && t < te;
@@ -259,34 +310,36 @@ struct Engine {
         if (proot) pv = root_prob(r, t - 1);
         else if (ps == -2) pv = ninf();
         else if (!pfrozen) {
-          const double2 pb = pub[((it & 1) * P.EMAX + pe) * 2 + r];
+          const double2 pb = pub_rd[(it & 1) * pstride];
           pv = (MODEL == POB_MODEL_CTC_MERGE_REPEATS && same) ? pb.y : pb.x;
         } else if (t - 1 >= plo && t - 1 < phi) {
-          const Ent* q = wptr(ps, r, t - 1);
+          const Ent* q = pwbase + (t & wmask);
           if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pv = same ? q->gap : q->prob;
           else pv = q->prob;
         } else pv = ninf();
-        const double ylast = rv[r].at(t, pcl);
-        const double yblank = rv[r].at(t, rv[r].cblank);
+        double ylast, yblank;
+        if (f64) { ylast = __ldg((const double*)ylast_p); yblank = __ldg((const double*)yblank_p); }
+        else { ylast = (double)__ldg((const float*)ylast_p); yblank = (double)__ldg((const float*)yblank_p); }
+        ylast_p += ystep; yblank_p += ystep;
         double prob;
         double2 pb;
+        Ent* o = wbase + ((t + 1) & wmask);
         if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
           const double gp = p_prev + yblank;
           const double ng = lae(pv + ylast, ng_prev + ylast);
           prob = lae(gp, ng);
-          Entry<POB_MODEL_CTC_MERGE_REPEATS>* o = (Entry<POB_MODEL_CTC_MERGE_REPEATS>*)wptr(slot, r, t);
           double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
           *reinterpret_cast<double4*>(o) = v4;
           ng_prev = ng;
           pb.x = prob; pb.y = gp;
         } else {
           prob = lae(pv + ylast, p_prev + yblank);
-          wptr(slot, r, t)->prob = prob;
+          o->prob = prob;
           pb.x = prob; pb.y = ninf();
         }
         p_prev = prob;
         if (prob > maxv) maxv = prob;
-        pub[(((it + 1) & 1) * P.EMAX + e) * 2 + r] = pb;
+        pub_wr[((it + 1) & 1) * pstride] = pb;
       }
       __syncthreads();
     }
@@ -304,8 +357,7 @@ struct Engine {
         smax[e * 2 + r] = h.maxp[r];  // empty band: max_prob left stale (A.6b)
       }
       n_updates += (unsigned long long)(te - ts);
-    } else if (have && act[e] && reset_other) {
-      // read not swept in this call keeps its stored max
+    } else if (live && reset_other) {
       smax[e * 2 + r] = hdr[slot].maxp[r];
     }
     __syncthreads();
@@ -480,7 +532,7 @@ struct Engine {
     if (tid == 0) { sh[SH_FIRSTALIVE] = 0x7fffffff; sh[SH_FREED] = 0; sh[SH_REPUSH] = 0; }
     __syncthreads();
     const int head = sh[SH_RQH], tail = sh[SH_RQT];
-    const int navail = min(tail - head, (int)blockDim.x);
+    const int navail = P.noreclaim ? 0 : min(tail - head, (int)blockDim.x);
     const int dmin = sh[SH_DMIN];
     int st = 0;  // 1 stale, 2 dead+freeable, 3 dead but must be kept, 4 alive
     int slot = -1, stamp = 0;
@@ -525,6 +577,23 @@ struct Engine {
     __syncthreads();
   }
 
+  __device__ void dbg_record(const BeamParams& G, long step) {
+    if (!G.dbg_trace) return;
+    __syncthreads();
+    if (threadIdx.x == 0 && step < 100000) {
+      double sum = 0;
+      for (int b = 0; b < sh[SH_NB]; ++b) {
+        const NodeHdr& h = hdr[beam[b]];
+        double sc = (P.mode == MODE_1D) ? wptr(beam[b], 0, h.hi[0] - 1)->prob
+                  : (P.mode == MODE_ROW) ? wptr(beam[b], 0, h.hi[0] - 1)->prob + h.maxp[1] : h.maxp[0] + h.maxp[1];
+        if (b == 0) G.dbg_trace[2 * step] = sc;
+        if (sc > -1e300) sum += sc;
+      }
+      G.dbg_trace[2 * step + 1] = sum;
+    }
+    __syncthreads();
+  }
+
   __device__ void save_old(int nE) {
     const int tid = threadIdx.x;
     if (tid < nE) {
@@ -535,17 +604,19 @@ struct Engine {
     __syncthreads();
   }
 
-  __device__ void run_item(int item, char* ws, char* smem);
+  __device__ void run_item(const BeamParams& G, int item, char* ws, char* smem);
 };
 
 template <int MODEL>
-__device__ void Engine<MODEL>::run_item(int item, char* ws, char* smem) {
+__device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws, char* smem) {
   const int tid = threadIdx.x, NT = blockDim.x;
-  const int W = P.W, NP = P.NP, EMAX = P.EMAX;
-  const int mode = P.mode;
-  // ---- carve shared memory
-  {
-    char* p = smem;
+  const int W = G.W, NP = G.NP, EMAX = G.EMAX;
+  const int mode = G.mode;
+  unsigned long long n_updates = 0;
+  // ---- carve shared memory (the engine object itself sits at the front)
+  if (tid == 0) {
+    P.W = W; P.NP = NP; P.RQ = G.RQ; P.EMAX = EMAX; P.mode = mode; P.noreclaim = G.dbg_noreclaim;
+    char* p = smem + ((sizeof(Engine<MODEL>) + 15) & ~(size_t)15);
     pub = (double2*)p; p += sizeof(double2) * 2 * EMAX * 2;
     score = (double*)p; p += sizeof(double) * EMAX;
     smax = (double*)p; p += sizeof(double) * EMAX * 2;
@@ -561,23 +632,26 @@ __device__ void Engine<MODEL>::run_item(int item, char* ws, char* smem) {
     actold = (uint8_t*)p; p += (EMAX + 15) & ~15;
   }
   // ---- carve the global workspace
-  cap[0] = P.CAP0; cap[1] = P.CAP1; mask[0] = P.CAP0 - 1; mask[1] = P.CAP1 - 1;
-  rv[0] = make_view(P.r[0], item);
-  if (mode != MODE_1D) rv[1] = make_view(P.r[1], item); else { rv[1] = rv[0]; rv[1].T = 0; }
-  const int U = rv[0].T, V = rv[1].T;
+  if (tid == 0) {
+  cap[0] = G.CAP0; cap[1] = G.CAP1; mask[0] = G.CAP0 - 1; mask[1] = G.CAP1 - 1;
+  rv[0] = make_view(G.r[0], item);
+  if (mode != MODE_1D) rv[1] = make_view(G.r[1], item); else { rv[1] = rv[0]; rv[1].T = 0; }
   {
     char* p = ws;
     hdr = (NodeHdr*)p; p += sizeof(NodeHdr) * (size_t)NP;
     win[0] = (Ent*)p; p += sizeof(Ent) * (size_t)NP * cap[0];
     win[1] = (Ent*)p; p += sizeof(Ent) * (size_t)NP * cap[1];
     freelist = (int32_t*)p; p += 4 * (size_t)NP;
-    retq = (int2*)p; p += 8 * (size_t)P.RQ;
-    cum[0] = (double*)p; p += 8 * (size_t)(MODEL == POB_MODEL_CTC ? U : 0);
-    cum[1] = (double*)p;
+    retq = (int2*)p; p += 8 * (size_t)G.RQ;
+    cum[0] = (double*)p; p += 8 * (size_t)(MODEL == POB_MODEL_CTC ? rv[0].T : 0);
+    cum[1] = (double*)p; p += 8 * (size_t)(MODEL == POB_MODEL_CTC ? rv[1].T : 0);
+    sufmin = (int32_t*)p;
   }
-  trace = P.trace + P.trace_off[item];
-  n_updates = 0;
-  int32_t* otop = P.out_top + 4 * (size_t)item;
+  trace = G.trace + G.trace_off[item];
+  }
+  __syncthreads();
+  const int U = rv[0].T, V = rv[1].T;
+  int32_t* otop = G.out_top + 4 * (size_t)item;
 
   // ---- init pool
   for (int s = tid; s < NP; s += NT) {
@@ -597,7 +671,7 @@ __device__ void Engine<MODEL>::run_item(int item, char* ws, char* smem) {
   }
   __syncthreads();
   if (U <= 0 || (mode != MODE_1D && V <= 0)) {
-    if (tid == 0) { otop[0] = 0; otop[1] = -1; otop[2] = 0; otop[3] = POB_ST_EMPTY; P.out_score[item] = 0; }
+    if (tid == 0) { otop[0] = 0; otop[1] = -1; otop[2] = 0; otop[3] = POB_ST_EMPTY; G.out_score[item] = 0; }
     return;
   }
   // ---- seed: the 4 children of the root, updated at t = 0 (BeamSearch.h:24-30, :287-293)
@@ -611,24 +685,42 @@ __device__ void Engine<MODEL>::run_item(int item, char* ws, char* smem) {
     n.lo[0] = n.lo[1] = 0; n.hi[0] = n.hi[1] = 0; n.maxp[0] = n.maxp[1] = ninf(); n.pad[0] = n.pad[1] = 0;
     hdr[slot] = n;
     beam[tid] = slot;
-    update_one(slot, 0, 0);
-    if (mode != MODE_1D) update_one(slot, 1, 0);
     n_updates += (mode != MODE_1D) ? 2 : 1;
   }
+  __syncthreads();
+  update_all(tid < nbase, tid < nbase ? beam[tid] : 0, 0, 0);
+  if (mode != MODE_1D) update_all(tid < nbase, tid < nbase ? beam[tid] : 0, 1, 0);
   if (tid == 0) { sh[SH_NFREE] = NP - nbase; sh[SH_ORDER] = 1 + nbase; sh[SH_NB] = nbase; }
   __syncthreads();
 
-  const int32_t* env = P.env ? P.env + 2 * P.env_off[item] : nullptr;
-  const int32_t* envt = P.envt ? P.envt + 2 * P.envt_off[item] : nullptr;
+  const int32_t* env = G.env ? G.env + 2 * G.env_off[item] : nullptr;
+  const int32_t* envt = G.envt ? G.envt + 2 * G.envt_off[item] : nullptr;
   long nsteps = 0;
+  if (mode == MODE_ROW && env && tid < 32) {
+    // suffix minimum of the band starts, warp-chunked from the end
+    int carry = 0x7fffffff;
+    for (int base = ((U - 1) / 32) * 32; base >= 0; base -= 32) {
+      const int i = base + tid;
+      int v = (i < U) ? max(env[2 * i], 0) : 0x7fffffff;
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_down_sync(0xffffffffu, v, d);
+        if (tid + d < 32) v = min(v, o);
+      }
+      v = min(v, carry);
+      if (i < U) sufmin[i] = v;
+      carry = __shfl_sync(0xffffffffu, v, 0);
+    }
+  }
+  __syncthreads();
 
   if (mode == MODE_1D) {
     // BeamSearch.h:33-53
     build_expanded(item, false);
     for (int t = 1; t < U; ++t) {
       const int nE = sh[SH_NE];
-      if (tid < nE && act[tid]) {
-        update_one(E[tid], 0, t);
+      const bool mine = tid < nE && act[tid];
+      update_all(mine, mine ? E[tid] : 0, 0, t);
+      if (mine) {
         n_updates++;
         score[tid] = wptr(E[tid], 0, t)->prob;  // last_probability(): value at the last written t
         eorder[tid] = hdr[E[tid]].order;
@@ -647,20 +739,33 @@ __device__ void Engine<MODEL>::run_item(int item, char* ws, char* smem) {
       int rs = env ? env[2 * u] : 0, re = env ? env[2 * u + 1] : V;
       rs = max(rs, 0); re = min(re, V);
       const int nE = sh[SH_NE];
-      if (tid < nE && act[tid]) { update_one(E[tid], 0, u); n_updates++; }
-      __syncthreads();
+      {
+        const bool mine = tid < nE && act[tid];
+        update_all(mine, mine ? E[tid] : 0, 0, u);
+        if (mine) n_updates++;
+      }
       int t0[2] = {u, rs}, t1[2] = {u + 1, re};
-      sweep(nE, 2, t0, t1, false);
+      sweep(nE, 2, t0, t1, false, n_updates);
       if (tid < nE && act[tid]) {
         score[tid] = wptr(E[tid], 0, u)->prob + smax[tid * 2 + 1];  // max_probability() (PrefixTree.h:107, :393)
         eorder[tid] = hdr[E[tid]].order;
       }
       __syncthreads();
+      if (G.dbg_trace && nsteps >= G.dbg_step - 2 && nsteps <= G.dbg_step + 1 && tid < nE) {
+        // rows of 10 doubles at offset 4000 + ((step - (dbg_step-2)) * 160 + tid) * 10
+        double* o = G.dbg_trace + 4000 + ((nsteps - (G.dbg_step - 2)) * 160 + tid) * 10;
+        const NodeHdr& h = hdr[E[tid]];
+        o[0] = act[tid] ? (double)h.order : -1.0; o[1] = h.depth; o[2] = h.last; o[3] = h.parent_order;
+        o[4] = act[tid] ? score[tid] : 0; o[5] = wptr(E[tid], 0, u)->prob; o[6] = smax[tid * 2 + 1];
+        o[7] = h.lo[1]; o[8] = h.hi[1]; o[9] = E[tid];
+        if (h.parent_slot >= 0) { const NodeHdr& ph = hdr[h.parent_slot]; o[2] = ph.order; o[6] = ph.hi[0]; o[7] = ph.state; o[8] = slot2e[h.parent_slot]; o[1] = h.parent_slot; }
+      }
       save_old(nE);
       prune(nE);
+      dbg_record(G, nsteps);
       build_expanded(item, sh[SH_NB] < W);
-      // read 0 is next read at index u; read 1 at >= (next row's band start) - 1
-      const int nrs = (u + 1 < U) ? (env ? max(env[2 * (u + 1)], 0) : 0) : 0x7ffffffe;
+      // read 0 is next read at index u; read 1 at >= (smallest band start of any later row) - 1
+      const int nrs = (u + 1 < U) ? (env ? sufmin[u + 1] : 0) : 0x7ffffffe;
       retire_and_reclaim(nE, u, nrs - 1);
       ++nsteps;
     }
@@ -676,8 +781,8 @@ __device__ void Engine<MODEL>::run_item(int item, char* ws, char* smem) {
       else if (v < ers) {
         const int nb = sh[SH_NB];
         if (nb < W && tid == 0) sh[SH_STATUS] |= POB_ST_SHORT_BEAM_SKIP;
-        if (tid < nb) { update_one(beam[tid], 1, v); n_updates++; }
-        __syncthreads();
+        update_all(tid < nb, tid < nb ? beam[tid] : 0, 1, v);
+        if (tid < nb) n_updates++;
         ++v; ++nsteps;
         continue;
       }
@@ -685,8 +790,8 @@ __device__ void Engine<MODEL>::run_item(int item, char* ws, char* smem) {
       else if (u < ecs) {
         const int nb = sh[SH_NB];
         if (nb < W && tid == 0) sh[SH_STATUS] |= POB_ST_SHORT_BEAM_SKIP;
-        if (tid < nb) { update_one(beam[tid], 0, u); n_updates++; }
-        __syncthreads();
+        update_all(tid < nb, tid < nb ? beam[tid] : 0, 0, u);
+        if (tid < nb) n_updates++;
         ++u; ++nsteps;
         continue;
       }
@@ -695,7 +800,7 @@ __device__ void Engine<MODEL>::run_item(int item, char* ws, char* smem) {
       if (!have_E) { build_expanded(item, false); have_E = true; }
       const int nE = sh[SH_NE];
       int t0[2] = {col_start, row_start}, t1[2] = {col_end, row_end};
-      sweep(nE, 3, t0, t1, false);
+      sweep(nE, 3, t0, t1, false, n_updates);
       if (tid < nE && act[tid]) {
         score[tid] = smax[tid * 2] + smax[tid * 2 + 1];  // max_probability_sym() (PrefixTree.h:111, :397)
         eorder[tid] = hdr[E[tid]].order;
@@ -703,6 +808,7 @@ __device__ void Engine<MODEL>::run_item(int item, char* ws, char* smem) {
       __syncthreads();
       save_old(nE);
       prune(nE);
+      dbg_record(G, nsteps);
       build_expanded(item, false);  // next step's expansion, done eagerly so retirement knows who stays
       retire_and_reclaim(nE, u, v);  // later reads are at t-1 >= u (read 0) and >= v (read 1)
       ++u; ++v; ++nsteps;
@@ -715,7 +821,7 @@ __device__ void Engine<MODEL>::run_item(int item, char* ws, char* smem) {
     if (mode == MODE_1D) sc = wptr(beam[0], 0, top.hi[0] - 1)->prob;
     else if (mode == MODE_ROW) sc = wptr(beam[0], 0, top.hi[0] - 1)->prob + top.maxp[1];
     else sc = top.maxp[0] + top.maxp[1];
-    P.out_score[item] = sc;
+    G.out_score[item] = sc;
     if (top.tid >= 0) { otop[0] = top.tid; otop[1] = -1; }
     else { otop[0] = top.parent_tid; otop[1] = top.last; }
     otop[2] = top.depth;
@@ -723,17 +829,17 @@ __device__ void Engine<MODEL>::run_item(int item, char* ws, char* smem) {
   }
   // per-item counters
   for (int o = 16; o > 0; o >>= 1) n_updates += __shfl_down_sync(0xffffffffu, n_updates, o);
-  if ((tid & 31) == 0 && n_updates) atomicAdd(&P.counters[0], n_updates);
-  if (tid == 0) atomicAdd(&P.counters[1], (unsigned long long)nsteps);
+  if ((tid & 31) == 0 && n_updates) atomicAdd(&G.counters[0], n_updates);
+  if (tid == 0) atomicAdd(&G.counters[1], (unsigned long long)nsteps);
   __syncthreads();
 }
 
-template <int MODEL, int MAXT>
-__global__ void __launch_bounds__(MAXT) beam_kernel(BeamParams P) {
+template <int MODEL, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) beam_kernel(BeamParams P) {
   extern __shared__ __align__(16) char smem[];
   __shared__ int s_item;
   char* ws = P.ws + (size_t)blockIdx.x * P.ws_stride;
-  Engine<MODEL> eng(P);
+  Engine<MODEL>& eng = *reinterpret_cast<Engine<MODEL>*>(smem);
   for (;;) {
     if (threadIdx.x == 0) s_item = atomicAdd(P.work_counter, 1);
     __syncthreads();
@@ -749,7 +855,7 @@ __global__ void __launch_bounds__(MAXT) beam_kernel(BeamParams P) {
       }
       continue;
     }
-    eng.run_item(item, ws, smem);
+    eng.run_item(P, item, ws, smem);
   }
 }
 
@@ -774,15 +880,25 @@ __global__ void backtrace_kernel(const uint32_t* __restrict__ trace, const int64
   if (out_status) out_status[i] |= top[4 * i + 3];
 }
 
+}  // namespace
+double* g_pob_dbg_trace = nullptr;
+extern "C" int pob_debug_trace(pob_ctx* ctx, double* out, int n) {
+  if (!g_pob_dbg_trace) return POB_EINVAL;
+  POB_CUDA(cudaMemcpy(out, g_pob_dbg_trace, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  return POB_OK;
+}
+namespace {
+
 size_t ws_bytes(int model, int NP, int CAP0, int CAP1, int RQ, int Umax, int Vmax) {
   const size_t es = model == POB_MODEL_CTC ? 8 : 32;
   size_t b = sizeof(NodeHdr) * (size_t)NP + es * (size_t)NP * ((size_t)CAP0 + CAP1) + 4 * (size_t)NP + 8 * (size_t)RQ;
   if (model == POB_MODEL_CTC) b += 8 * ((size_t)Umax + Vmax + 2);
+  b += 4 * ((size_t)Umax + 2);
   return pob_align_up(b, 256);
 }
 
 size_t smem_bytes(int W, int NP, int EMAX) {
-  size_t b = sizeof(double2) * 2 * EMAX * 2 + 8 * EMAX + 16 * EMAX + 4 * EMAX * 5 + 4 * ((W + 3) & ~3) + 4 * 32 +
+  size_t b = 512 + sizeof(double2) * 2 * EMAX * 2 + 8 * EMAX + 16 * EMAX + 4 * EMAX * 5 + 4 * ((W + 3) & ~3) + 4 * 32 +
              2 * (size_t)NP + 2 * ((EMAX + 15) & ~15);
   return pob_align_up(b, 16);
 }
@@ -816,6 +932,17 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   P.NP = pow2_at_least(64 * W);
   if (P.NP < 1024) P.NP = 1024;
   if (P.NP > 16384) P.NP = 16384;
+  if (const char* e = getenv("POB_DEBUG_NP")) P.NP = atoi(e);
+  if (const char* e = getenv("POB_DEBUG_NORECLAIM")) P.dbg_noreclaim = atoi(e);
+  P.dbg_step = -1000;
+  if (const char* e = getenv("POB_DEBUG_STEP")) P.dbg_step = atoi(e);
+  if (getenv("POB_DEBUG_TRACE")) {
+    static double* dbg = nullptr;
+    if (!dbg) cudaMalloc(&dbg, 200000 * sizeof(double));
+    cudaMemsetAsync(dbg, 0, 200000 * sizeof(double), ctx->stream);
+    P.dbg_trace = dbg;
+    g_pob_dbg_trace = dbg;
+  }
   P.CAP0 = pow2_at_least(max_span0 + 3);
   P.CAP1 = pow2_at_least(max_span1 + 3);
   P.RQ = P.NP * 2;
@@ -826,11 +953,23 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   const size_t smem = smem_bytes(W, P.NP, P.EMAX);
   if (smem > 200 * 1024) return POB_EUNSUPPORTED;
   void (*kern)(BeamParams);
-  if (threads <= 512)
-    kern = model == POB_MODEL_CTC ? beam_kernel<POB_MODEL_CTC, 512> : beam_kernel<POB_MODEL_CTC_MERGE_REPEATS, 512>;
-  else
-    kern = model == POB_MODEL_CTC ? beam_kernel<POB_MODEL_CTC, 1024> : beam_kernel<POB_MODEL_CTC_MERGE_REPEATS, 1024>;
+  const bool ctc = model == POB_MODEL_CTC;
+  constexpr int M0 = POB_MODEL_CTC, M1 = POB_MODEL_CTC_MERGE_REPEATS;
+  if (threads <= 64) { threads = 64; kern = ctc ? beam_kernel<M0, 64, 12> : beam_kernel<M1, 64, 12>; }
+  else if (threads <= 128) { kern = ctc ? beam_kernel<M0, 128, 6> : beam_kernel<M1, 128, 6>; }
+  else if (threads <= 288) { kern = ctc ? beam_kernel<M0, 288, 3> : beam_kernel<M1, 288, 3>; }
+  else if (threads <= 512) { kern = ctc ? beam_kernel<M0, 512, 1> : beam_kernel<M1, 512, 1>; }
+  else { kern = ctc ? beam_kernel<M0, 1024, 1> : beam_kernel<M1, 1024, 1>; }
   POB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // leave most of the unified L1/shared array to L1 (node headers and windows are served from it) but make
+  // sure the shared-memory carve-out does not cap residency
+  {
+    int want_blocks = 2048 / threads;
+    if (want_blocks > 12) want_blocks = 12;
+    int pct = (int)((want_blocks * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    POB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+  }
   int per_sm = 0;
   POB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) return POB_EUNSUPPORTED;
