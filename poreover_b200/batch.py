@@ -232,3 +232,42 @@ def pair_decode_batch(arrays1, arrays2, kind="bonito", beam_width=25, padding=5,
             r["score"] = float(sc[p])
         out.append(r)
     return out
+
+
+FLIPFLOP_LUT = None
+
+
+def flipflop_lut():
+    """log((x + 1e-7) / (255 + 1e-7)) for x = 0..255, computed by numpy exactly as decode.py:92-93 does."""
+    global FLIPFLOP_LUT
+    if FLIPFLOP_LUT is None:
+        eps = 0.0000001
+        FLIPFLOP_LUT = np.log((np.arange(256, dtype=np.uint8) + eps) / (255 + eps))
+    return FLIPFLOP_LUT
+
+
+def flipflop_viterbi_batch(arrays, rc=None, return_path=False, device=None):
+    """Flip-flop Viterbi over many reads.  arrays: T x 8 float64 log-probabilities, or T x 8 uint8 traces
+    (decoded through the host-computed table).  Returns (sequences, s2s lists, paths or None).
+
+    replaces transducer.viterbi_decode for kind 'flipflop' (transducer.py:35-59, :94-103)."""
+    arrays = [np.asarray(a) for a in arrays]
+    u8 = all(a.dtype == np.uint8 for a in arrays) and len(arrays) > 0
+    b = ReadBatch(arrays, rc=rc, dtype=np.uint8 if u8 else np.float64)
+    if b.n and b.n_states != 8:
+        raise ValueError("flip-flop traces have 8 states")
+    ctx = get_ctx(device)
+    rows = max(b.total_rows, 1)
+    seq = np.zeros(rows + 4, dtype=np.uint8)
+    s2s = np.zeros(rows + 4, dtype=np.int32)
+    path = np.zeros(rows + 4, dtype=np.int8)
+    ln = np.zeros(max(b.n, 1), dtype=np.int32)
+    lut = flipflop_lut() if u8 else None
+    rs = b.struct()
+    check(lib().pob_viterbi_flipflop(ctx.h, _lib.HOST, C.byref(rs), ptr(lut), ptr(seq), ptr(s2s), ptr(path), ptr(ln)),
+          "pob_viterbi_flipflop")
+    offs = b.row_off[:-1]
+    seqs = [seq[o:o + l].tobytes().decode() for o, l in zip(offs, ln[:b.n])]
+    maps = [s2s[o:o + l].astype(np.int64) for o, l in zip(offs, ln[:b.n])]
+    paths = [path[o:o + t].astype(np.int64) for o, t in zip(offs, b.lens)] if return_path else None
+    return seqs, maps, paths

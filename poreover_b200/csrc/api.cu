@@ -36,8 +36,43 @@ int pob_viterbi(pob_ctx* ctx, int where, const pob_reads_t* reads, int kind, uin
 }
 
 // ---- not yet built in this revision: every symbol of the header exists and fails loudly ----
-int pob_viterbi_flipflop(pob_ctx*, int, const pob_reads_t*, const double*, uint8_t*, int32_t*, int8_t*, int32_t*) {
-  return POB_EUNSUPPORTED;
+int pob_viterbi_flipflop(pob_ctx* ctx, int where, const pob_reads_t* reads, const double* lut, uint8_t* out_seq,
+                         int32_t* out_s2s, int8_t* out_path, int32_t* out_len) {
+  if (!ctx) return POB_EINVAL;
+  POB_TRY(check_reads(reads, 8, 8));
+  if (reads->dtype != POB_F64 && reads->dtype != POB_U8_TRACE) return POB_EINVAL;
+  if (reads->dtype == POB_U8_TRACE && !lut) return POB_EINVAL;
+  const int n = reads->n;
+  if (n == 0) return POB_OK;
+  if (!out_seq || !out_len) return POB_EINVAL;
+  POB_CUDA(cudaSetDevice(ctx->device));
+  POB_TRY(pob_arena_reset(ctx));
+  std::vector<int64_t> off;
+  POB_TRY(fetch_i64(ctx, where, reads->row_off, (size_t)n + 1, off));
+  const size_t rows = (size_t)off[n];
+  pob_reads_t d = *reads;
+  const double* d_lut = lut;
+  uint8_t* d_seq = out_seq; int32_t* d_s2s = out_s2s; int8_t* d_path = out_path; int32_t* d_len = out_len;
+  if (where == POB_HOST) {
+    POB_TRY(stage_reads(ctx, reads, &d));
+    POB_TRY(stage_in(ctx, lut, (size_t)(lut ? 256 : 0), &d_lut));
+    POB_TRY(stage_out(ctx, out_seq, rows + 4, &d_seq));
+    POB_TRY(stage_out(ctx, out_s2s, rows + 4, &d_s2s));
+    POB_TRY(stage_out(ctx, out_path, rows + 4, &d_path));
+    POB_TRY(stage_out(ctx, out_len, (size_t)n, &d_len));
+  }
+  uint32_t* bp;
+  POB_TRY(pob_take(ctx, rows + 4, &bp));
+  if (!d_path) POB_TRY(pob_take(ctx, rows + 4, &d_path));
+  POB_TRY(pob_flipflop_launch(ctx, d, d_lut, bp, d_path, d_seq, d_s2s, d_len));
+  if (where == POB_HOST) {
+    POB_TRY(copy_back(ctx, out_seq, d_seq, rows));
+    POB_TRY(copy_back(ctx, out_s2s, d_s2s, rows));
+    POB_TRY(copy_back(ctx, out_path, d_path, rows));
+    POB_TRY(copy_back(ctx, out_len, d_len, (size_t)n));
+  }
+  POB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return POB_OK;
 }
 int pob_align_banded(pob_ctx* ctx, int where, const uint8_t* seq1, const int64_t* off1, const uint8_t* seq2,
                      const int64_t* off2, int n, int band, int match, int mismatch, int gap, uint8_t* out_a1,

@@ -27,3 +27,6 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
                     int max_span1, int Umax, int Vmax, const int64_t* trace_off, uint32_t* trace, int32_t* top,
                     const int64_t* out_off, uint8_t* out_seq, int32_t* out_len, double* out_score,
                     int32_t* out_status);
+
+int pob_flipflop_launch(pob_ctx* ctx, const pob_reads& rd, const double* lut, uint32_t* bp, int8_t* path,
+                        uint8_t* out_seq, int32_t* out_s2s, int32_t* out_len);
