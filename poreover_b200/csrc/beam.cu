@@ -929,9 +929,18 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   P.env = env; P.env_off = env_off; P.envt = envt; P.envt_off = envt_off; P.order = order; P.skip = skip;
   P.n_items = n_items; P.W = W; P.mode = mode;
   P.EMAX = 5 * W + 4;
-  P.NP = pow2_at_least(64 * W);
-  if (P.NP < 1024) P.NP = 1024;
-  if (P.NP > 16384) P.NP = 16384;
+  // Node pool: the expanded beam (5W) plus retired nodes whose windows can still be read.  About W nodes
+  // retire per step and stay readable for one band width, so the pool scales with W x widest band; an
+  // overflow is flagged per item (POB_ST_POOL_OVERFLOW), never silent.
+  {
+    const int span = (mode == MODE_1D) ? 1 : (max_span0 > max_span1 ? max_span0 : max_span1);
+    long want = 64L * W;
+    const long by_span = 3L * W * (span + 8) + 16L * W;
+    if (by_span > want) want = by_span;
+    if (want > 65536) want = 65536;
+    P.NP = pow2_at_least((int)want);
+    if (P.NP < 1024) P.NP = 1024;
+  }
   if (const char* e = getenv("POB_DEBUG_NP")) P.NP = atoi(e);
   if (const char* e = getenv("POB_DEBUG_NORECLAIM")) P.dbg_noreclaim = atoi(e);
   P.dbg_step = -1000;
@@ -945,6 +954,9 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   }
   P.CAP0 = pow2_at_least(max_span0 + 3);
   P.CAP1 = pow2_at_least(max_span1 + 3);
+  // keep one CTA's workspace under ~160 MB so that a full wave of CTAs fits in HBM (wide-band batches then
+  // run with a smaller pool and rely on the overflow flag)
+  while (P.NP > 1024 && ws_bytes(model, P.NP, P.CAP0, P.CAP1, 2 * P.NP, Umax, Vmax) > ((size_t)160 << 20)) P.NP >>= 1;
   P.RQ = P.NP * 2;
   // the band sweep wants one thread per (node, read); the single-read search one per node
   int threads = (((mode == MODE_1D ? 1 : 2) * P.EMAX + 31) / 32) * 32;
