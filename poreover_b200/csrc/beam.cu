@@ -10,18 +10,22 @@
 //
 // The reference keeps every node's forward values in per-node hash maps keyed by time, never frees a
 // node, and relies on "missing key reads as -inf" plus stale entries.  Here one CTA owns one item
-// (read or pair).  Nodes live in a pool in global memory (L2 resident); each (node, read) has a
-// time-indexed ring window [lo, hi) of FP64 values -- exactly the entries the reference could still
-// read, because every read is at t-1 >= (current u)-1.  Nodes that leave the expanded beam are retired,
-// not dropped: a later revival (parent re-enters the beam) or a child reading its frozen parent sees the
-// same stale values the reference's hash maps would return.  A retired node is recycled only once its
-// windows are dead (or the pool overflows, which is flagged per item).
+// (read or pair).  Every node has a home slot in a global-memory pool: a 128-byte header and, per read,
+// a time-indexed ring window [lo, hi) of FP64 values -- exactly the entries the reference could still
+// read, because every read is at t-1 >= (current u)-1.  The nodes of the *expanded beam* (beam + children,
+// <= 5W) additionally hold their header in shared memory in a stable "active slot" for as long as they stay
+// in the expanded beam, so a search step touches global memory only for window entries and for nodes that
+// enter or leave.  Nodes that leave are retired, not dropped: a later revival (parent re-enters the beam) or
+// a child reading its frozen parent sees the same stale values the reference's hash maps would return.  A
+// retired node is recycled only once its windows are dead and it cannot hand retained children to a revival
+// (or the pool overflows, which is flagged per item).
 //
-// Arithmetic: forward values are accumulated in FP64 (the reference is all double and scores reach
+// Arithmetic: forward values accumulate in FP64 (the reference is all double and scores reach
 // -2.5e3..-5e4); only the bounded log1p(exp(d)) term, d <= 0, is evaluated in FP32.  No tensor cores:
-// nothing here is a contraction.  Per step the dependent chain is the time-major band sweep: threads
-// own (node, read) items, carry their own t-1 values in registers and exchange parent values through
-// double-buffered shared memory, one barrier per time sub-step.
+// nothing here is a contraction.  Per step the dependent chain is the time-major band sweep: threads own
+// (node, read) items, carry their own t-1 values in registers and exchange parent values through
+// double-buffered shared memory, one block barrier per time sub-step; five more barriers per step cover
+// ranking, expansion, retirement and allocation.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -30,8 +34,10 @@
 namespace {
 
 enum { MODE_1D = 0, MODE_ROW = 1, MODE_ROWCOL = 2 };
+enum { PS_ROOT = 0, PS_INE = 1, PS_FROZEN = 2, PS_DEAD = 3 };  // where a node's parent values come from
+enum { KID_ACTIVE = 0, KID_REVIVE = 1, KID_FRESH = 2 };
 
-struct __align__(16) NodeHdr {  // 128 bytes
+struct __align__(16) NodeHdr {  // 128 bytes, home record of a node in the global pool
   uint32_t order;               // creation order (>= 1); 0 = slot is free / link invalid
   int32_t state;                // 0 active (in the expanded beam), > 0 retire stamp, -1 free
   int32_t parent_slot;          // -1: parent is the root
@@ -46,7 +52,6 @@ struct __align__(16) NodeHdr {  // 128 bytes
   double maxp[2];               // max_prob[] of the reference nodes
   int32_t pad[2];
 };
-static_assert(sizeof(NodeHdr) == 112 || sizeof(NodeHdr) == 128, "hdr size");
 
 template <int MODEL>
 struct Entry;
@@ -68,8 +73,8 @@ struct BeamParams {
   const int32_t* order;     // item processing order or NULL
   const int32_t* skip;      // per item != 0 -> not searched
   int n_items, W, mode, NP, CAP0, CAP1, RQ, EMAX;
-  int dbg_noreclaim, dbg_step;
-  double* dbg_trace;  // optional: [step][2] = (top score, sum of beam scores) after each prune of item 0
+  int dbg_noreclaim;
+  double* dbg_trace;        // optional: [step][2] = (top score, sum of beam scores) after each prune
   char* ws;                 // workspace, one stride per resident CTA
   size_t ws_stride;
   uint32_t* trace;
@@ -81,6 +86,7 @@ struct BeamParams {
 };
 
 __device__ __forceinline__ double ninf() { return __longlong_as_double(0xfff0000000000000LL); }
+__device__ __forceinline__ double no_nan(double x) { return (x == x) ? x : ninf(); }  // NaN cannot be ranked
 
 // Log.h:27-33 with the bounded term in FP32: max + log1p(exp(min - max))
 __device__ __forceinline__ double lae(double a, double b) {
@@ -117,42 +123,58 @@ __device__ __forceinline__ ReadView make_view(const pob_reads& r, int item) {
   return v;
 }
 
+enum { SH_NB = 0, SH_NUSED, SH_FQH, SH_FQT, SH_AFREE, SH_ORDER, SH_TID, SH_STAMP, SH_RQH, SH_RQT, SH_STATUS, SH_FIRSTALIVE,
+       SH_TOTALLOC, SH_TOTFIRST, SH_DMIN, SH_COUNT };
+
+// The engine object lives in shared memory (one per CTA).
 template <int MODEL>
 struct Engine {
   typedef Entry<MODEL> Ent;
-  // copied launch parameters (the engine object lives in shared memory: one copy per CTA)
-  struct { int W, NP, RQ, EMAX, mode, noreclaim; } P;
-  // workspace views
+  int W, NP, RQ, EMAX, mode, noreclaim;
+  // global workspace views
   NodeHdr* hdr;
   Ent* win[2];
   int32_t* freelist;
   int2* retq;
-  double* cum[2];  // ctc: blank prefix sums of each read (root node values, PrefixTree.h:508-514)
-  int32_t* sufmin; // ROW: min over rows >= u of the envelope's band start (band starts are NOT monotone:
-                   // build_envelope's repair pass clamps some rows far back, envelope.py:82-85)
+  double* cum[2];   // ctc: blank prefix sums of each read (root node values, PrefixTree.h:508-514)
+  int32_t* sufmin;  // ROW: min over rows >= u of the envelope's band start (band starts are NOT monotone:
+                    // build_envelope's repair pass clamps some rows far back, envelope.py:82-85)
   int cap[2], mask[2];
   ReadView rv[2];
   uint32_t* trace;
-  // shared state
-  int16_t* slot2e;   // [NP]
-  int32_t* E;        // [EMAX] pool slots of the expanded beam
-  int32_t* Eold;     // [EMAX]
-  uint8_t* act;      // [EMAX] active (not a duplicate)
-  uint8_t* actold;
-  int32_t* beam;     // [W]
-  double* score;     // [EMAX]
-  uint32_t* eorder;  // [EMAX]
-  double2* pub;      // [2][EMAX][2]
-  double* smax;      // [EMAX][2]
-  int32_t* tmpa;     // [EMAX] scratch ints
+  // shared-memory state of the active slots (index a in [0, EMAX)); a_slot[a] < 0 = unused
+  int16_t* slot2e;     // [NP] pool slot -> active slot or -1
+  int32_t* a_slot;     // pool slot
+  uint32_t* a_order;
+  int32_t* a_par;      // active slot of the parent when a_pstat == PS_INE
+  int32_t* a_pslot;    // pool slot of the parent (window base when frozen)
+  uint32_t* a_porder;
+  int32_t* a_depth;
+  int32_t* a_tid;
+  int32_t* a_ptid;
+  int32_t* a_kid;      // [EMAX*4] pool slots of the children, -1 = never created
+  uint32_t* a_kido;    // [EMAX*4]
+  int32_t* a_lo;       // [EMAX*2]
+  int32_t* a_hi;
+  int32_t* a_plo;      // [EMAX*2] window bounds of a frozen parent
+  int32_t* a_phi;
+  double* a_maxp;      // [EMAX*2]
+  double* a_last0;     // [EMAX] value of read 0 at its last written t
+  double2* key;        // [EMAX] (ranking score, creation order)
+  double2* pub;        // [2][EMAX][2] (prob, gap) exchanged between parents and children in a sweep
+  uint8_t* a_last;
+  uint8_t* a_pstat;
+  uint8_t* a_same;     // parent's last base == own last base (merge-repeats reads the parent's gap value)
+  uint8_t* a_inbeam;
+  uint8_t* a_needed;
+  int32_t* beam;       // [W] active slots in rank order
+  int32_t* a_free;     // [EMAX] stack of unused active slots
+  int32_t* tmpa;       // [EMAX] scratch
   int32_t* tmpb;
-  int32_t* sh;       // scalars: see SH_*
-  enum { SH_NB = 0, SH_NE, SH_NFREE, SH_ORDER, SH_TID, SH_STAMP, SH_RQH, SH_RQT, SH_STATUS, SH_FIRSTALIVE,
-         SH_FREED, SH_NEOLD, SH_TOTALLOC, SH_TOTFIRST, SH_DMIN, SH_REPUSH, SH_COUNT };
+  int32_t* tmpc;
+  int32_t* sh;         // scalars SH_*
 
-  __device__ __forceinline__ Ent* wptr(int slot, int r, int t) const {
-    return win[r] + (size_t)slot * cap[r] + ((t + 1) & mask[r]);
-  }
+  __device__ __forceinline__ Ent* wbase(int slot, int r) const { return win[r] + (size_t)slot * cap[r]; }
 
   // value of the root at time t (parent of depth-1 nodes)
   __device__ __forceinline__ double root_prob(int r, int t) const {
@@ -161,37 +183,48 @@ struct Engine {
     return ninf();
   }
 
-  // ---- one update_prob(n, r, t) with every input read from the stored windows -------------------
-  // Split in two halves with a block barrier in between (update_all): when a node and its parent are
-  // updated at the same t by different threads, the child must see the parent's window bounds and t-1
-  // entry as they were BEFORE this phase (the reference reads t-1, writes t).  Reading lo/hi while the
-  // parent's thread rewrites them can otherwise pair a new hi with an old lo and admit a stale entry.
+  // bookkeeping that must not race with the phase that produced it: run by thread 0 at the start of a
+  // compute phase (separated by barriers from every reader)
+  __device__ __forceinline__ void deferred_finalize() {
+    if (threadIdx.x == 0) {
+      sh[SH_ORDER] += sh[SH_TOTALLOC]; sh[SH_TOTALLOC] = 0;
+      sh[SH_TID] += sh[SH_TOTFIRST]; sh[SH_TOTFIRST] = 0;
+      sh[SH_FIRSTALIVE] = 0x7fffffff;
+    }
+  }
+
+  // ---- one update_prob(n, r, t) for a set of nodes at the same t (1D steps, ROW's read 0, skip steps) ----
+  // Gather and commit are separated by a block barrier: when a node and its parent are updated at the same
+  // t by different threads, the child must see the parent's window bounds and t-1 entry as they were before
+  // this phase (the reference reads t-1, writes t).
   struct UpdIn {
     double p_prev, ng_prev, pv, ylast, yblank;
     int lo, hi;
   };
 
-  __device__ __forceinline__ void update_gather(int slot, int r, int t, UpdIn& in) const {
-    const NodeHdr& h = hdr[slot];
-    const int last = h.last;
-    in.lo = h.lo[r]; in.hi = h.hi[r];
+  __device__ __forceinline__ void update_gather(int a, int r, int t, UpdIn& in) const {
+    const int slot = a_slot[a];
+    const int last = a_last[a];
+    in.lo = a_lo[2 * a + r]; in.hi = a_hi[2 * a + r];
     const bool self_ok = (t - 1 >= in.lo && t - 1 < in.hi);
-    const Ent* se = wptr(slot, r, t - 1);
+    const Ent* se = wbase(slot, r) + (t & mask[r]);
     in.p_prev = self_ok ? se->prob : ninf();
     in.ng_prev = ninf();
     if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.ng_prev = self_ok ? se->nogap : ninf();
     in.ylast = rv[r].at(t, rv[r].pcol(last));
     in.yblank = rv[r].at(t, rv[r].cblank);
-    const int ps = h.parent_slot;
-    if (ps < 0) {
+    const int ps = a_pstat[a];
+    if (ps == PS_ROOT) {
       in.pv = root_prob(r, t - 1);
+    } else if (ps == PS_DEAD) {
+      in.pv = ninf();
     } else {
-      const NodeHdr& ph = hdr[ps];
-      const bool same = (ph.last == last);
-      const int plo = ph.lo[r], phi = ph.hi[r];
-      if (ph.order == h.parent_order && t - 1 >= plo && t - 1 < phi) {
-        const Ent* pe = wptr(ps, r, t - 1);
-        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.pv = same ? pe->gap : pe->prob;
+      int plo, phi;
+      if (ps == PS_INE) { const int pa = a_par[a]; plo = a_lo[2 * pa + r]; phi = a_hi[2 * pa + r]; }
+      else { plo = a_plo[2 * a + r]; phi = a_phi[2 * a + r]; }
+      if (t - 1 >= plo && t - 1 < phi) {
+        const Ent* pe = wbase(a_pslot[a], r) + (t & mask[r]);
+        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.pv = a_same[a] ? pe->gap : pe->prob;
         else in.pv = pe->prob;
       } else {
         in.pv = ninf();
@@ -199,8 +232,7 @@ struct Engine {
     }
   }
 
-  __device__ __forceinline__ void update_commit(int slot, int r, int t, const UpdIn& in) {
-    NodeHdr& h = hdr[slot];
+  __device__ __forceinline__ double update_commit(int a, int r, int t, const UpdIn& in) {
     Ent out;
     double prob;
     if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
@@ -212,59 +244,59 @@ struct Engine {
       prob = lae(in.pv + in.ylast, in.p_prev + in.yblank);
       out.prob = prob;
     }
-    *wptr(slot, r, t) = out;
+    *(wbase(a_slot[a], r) + ((t + 1) & mask[r])) = out;
     int lo = in.lo, hi = in.hi;
     if (t >= hi) { if (t > hi) lo = t; hi = t + 1; }
     else if (t < lo) { lo = t; hi = t + 1; }
     if (hi - lo > cap[r]) lo = hi - cap[r];
-    h.lo[r] = lo; h.hi[r] = hi;
-    if (prob > h.maxp[r]) h.maxp[r] = prob;
+    a_lo[2 * a + r] = lo; a_hi[2 * a + r] = hi;
+    if (prob > a_maxp[2 * a + r]) a_maxp[2 * a + r] = prob;
+    if (r == 0) a_last0[a] = prob;
+    return prob;
   }
 
-  // all threads call this; `mine` selects the threads that own a node (slot) this phase
-  __device__ void update_all(bool mine, int slot, int r, int t) {
+  // all threads call this; `mine` selects the threads that own an active slot this phase
+  __device__ double update_all(bool mine, int a, int r, int t) {
     UpdIn in;
-    if (mine) update_gather(slot, r, t, in);
+    double p = 0;
+    deferred_finalize();
+    if (mine) update_gather(a, r, t, in);
     __syncthreads();
-    if (mine) update_commit(slot, r, t, in);
+    if (mine) p = update_commit(a, r, t, in);
     __syncthreads();
+    return p;
   }
 
   // ---- time-major band sweep over the expanded beam (BeamSearch.h:361-375, :146-156) ----------------
-  // reads_mask bit r: read r swept over [t0[r], t1[r]).  Resets max_prob of the swept reads first.
-  __device__ void sweep(int nE, int reads_mask, const int* t0, const int* t1, bool reset_other,
-                        unsigned long long& n_updates) {
+  // reads_mask bit r: read r swept over [t0[r], t1[r]).  Resets max_prob of the swept reads, writes the
+  // ranking keys.  Thread (2a + r) owns (active slot a, read r).
+  __device__ void sweep(int reads_mask, const int* t0, const int* t1, unsigned long long& n_updates) {
     const int tid = threadIdx.x;
-    const int EMAX = P.EMAX;
-    const int nItems = nE * 2;
     const int len0 = (reads_mask & 1) ? t1[0] - t0[0] : 0, len1 = (reads_mask & 2) ? t1[1] - t0[1] : 0;
     const int maxlen = max(len0, len1);
-    // one item per thread (launcher guarantees blockDim >= 2*EMAX)
-    const int item = tid;
-    const bool have = item < nItems;
-    const int e = item >> 1, r = item & 1;
-    const bool live = have && act[e];
-    const bool on = live && ((reads_mask >> r) & 1);
-    int slot = 0, pe = -1, lo = 0, hi = 0, ps = -1, plo = 0, phi = 0;
-    bool same = false, proot = false, pfrozen = false;
+    const int a = tid >> 1, r = tid & 1;
+    const bool used = a < EMAX && a_slot[a] >= 0;
+    const bool on = used && ((reads_mask >> r) & 1);
+    int lo = 0, hi = 0, plo = 0, phi = 0, pstat = PS_DEAD, pa = 0;
+    bool same = false;
     double p_prev = ninf(), ng_prev = ninf(), maxv = ninf();
     int ts = 0, te = 0;
-    // hoisted addressing: own window, parent window, the two probability columns of this read
-    Ent* wbase = nullptr;
-    const Ent* pwbase = nullptr;
+    Ent* wb = nullptr;
+    const Ent* pwb = nullptr;
     int wmask = 0;
     const char* ylast_p = nullptr;
     const char* yblank_p = nullptr;
     long ystep = 0;
     bool f64 = false;
-    if (live) slot = E[e];
+    double ylast = 0, yblank = 0;
+    deferred_finalize();
     if (on) {
-      NodeHdr& h = hdr[slot];
-      const int last = h.last;
-      lo = h.lo[r]; hi = h.hi[r];
+      const int slot = a_slot[a];
+      const int last = a_last[a];
+      lo = a_lo[2 * a + r]; hi = a_hi[2 * a + r];
       ts = t0[r]; te = t1[r];
       wmask = mask[r];
-      wbase = win[r] + (size_t)slot * cap[r];
+      wb = wbase(slot, r);
       {
         const ReadView v = rv[r];
         f64 = v.f64;
@@ -275,65 +307,64 @@ struct Engine {
         ylast_p = row0 + (long)v.pcol(last) * es;
         yblank_p = row0 + (long)v.cblank * es;
       }
+      double g_prev = ninf();
       if (ts - 1 >= lo && ts - 1 < hi) {
-        const Ent* se = wbase + (ts & wmask);
+        const Ent* se = wb + (ts & wmask);
         p_prev = se->prob;
-        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_prev = se->nogap;
+        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { ng_prev = se->nogap; g_prev = se->gap; }
       }
-      ps = h.parent_slot;
-      if (ps < 0) proot = true;
-      else {
-        const NodeHdr& ph = hdr[ps];
-        same = (ph.last == last);
-        if (ph.order != h.parent_order) { ps = -2; }  // recycled parent: every read is -inf
-        else {
-          pe = slot2e[ps];
-          if (pe < 0) { pfrozen = true; plo = ph.lo[r]; phi = ph.hi[r]; pwbase = win[r] + (size_t)ps * cap[r]; }
-        }
-      }
+      pstat = a_pstat[a];
+      same = a_same[a] != 0;
+      if (pstat == PS_INE) pa = a_par[a];
+      else if (pstat == PS_FROZEN) { plo = a_plo[2 * a + r]; phi = a_phi[2 * a + r]; pwb = wbase(a_pslot[a], r); }
       // publish the stored values at ts-1 for children whose parent is swept too
-      double2 pb; pb.x = p_prev; pb.y = ninf();
-      if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
-        if (ts - 1 >= lo && ts - 1 < hi) pb.y = (wbase + (ts & wmask))->gap;
+      double2 pb; pb.x = p_prev; pb.y = g_prev;
+      pub[a * 2 + r] = pb;
+      if (ts < te) {
+        if (f64) { ylast = __ldg((const double*)ylast_p); yblank = __ldg((const double*)yblank_p); }
+        else { ylast = (double)__ldg((const float*)ylast_p); yblank = (double)__ldg((const float*)yblank_p); }
       }
-      pub[(0 * EMAX + e) * 2 + r] = pb;
     }
     __syncthreads();
-    const double2* pub_rd = pub + (size_t)(pe < 0 ? 0 : pe) * 2 + r;
-    double2* pub_wr = pub + (size_t)e * 2 + r;
+    const double2* pub_rd = pub + (size_t)pa * 2 + r;
+    double2* pub_wr = pub + (size_t)(a < EMAX ? a : 0) * 2 + r;
     const int pstride = EMAX * 2;
     for (int it = 0; it < maxlen; ++it) {
       const int t = ts + it;
       const bool go = on && t < te;
       if (go) {
         double pv;
-        if (proot) pv = root_prob(r, t - 1);
-        else if (ps == -2) pv = ninf();
-        else if (!pfrozen) {
+        if (pstat == PS_INE) {
           const double2 pb = pub_rd[(it & 1) * pstride];
           pv = (MODEL == POB_MODEL_CTC_MERGE_REPEATS && same) ? pb.y : pb.x;
-        } else if (t - 1 >= plo && t - 1 < phi) {
-          const Ent* q = pwbase + (t & wmask);
-          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pv = same ? q->gap : q->prob;
-          else pv = q->prob;
-        } else pv = ninf();
-        double ylast, yblank;
-        if (f64) { ylast = __ldg((const double*)ylast_p); yblank = __ldg((const double*)yblank_p); }
-        else { ylast = (double)__ldg((const float*)ylast_p); yblank = (double)__ldg((const float*)yblank_p); }
+        } else if (pstat == PS_FROZEN) {
+          if (t - 1 >= plo && t - 1 < phi) {
+            const Ent* q = pwb + (t & wmask);
+            if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pv = same ? q->gap : q->prob;
+            else pv = q->prob;
+          } else pv = ninf();
+        } else if (pstat == PS_ROOT) pv = root_prob(r, t - 1);
+        else pv = ninf();
+        const double yl = ylast, yb = yblank;
+        // next timestep's probabilities: issued now, consumed after the barrier
         ylast_p += ystep; yblank_p += ystep;
+        if (t + 1 < te) {
+          if (f64) { ylast = __ldg((const double*)ylast_p); yblank = __ldg((const double*)yblank_p); }
+          else { ylast = (double)__ldg((const float*)ylast_p); yblank = (double)__ldg((const float*)yblank_p); }
+        }
         double prob;
         double2 pb;
-        Ent* o = wbase + ((t + 1) & wmask);
+        Ent* o = wb + ((t + 1) & wmask);
         if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
-          const double gp = p_prev + yblank;
-          const double ng = lae(pv + ylast, ng_prev + ylast);
+          const double gp = p_prev + yb;
+          const double ng = lae(pv + yl, ng_prev + yl);
           prob = lae(gp, ng);
           double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
           *reinterpret_cast<double4*>(o) = v4;
           ng_prev = ng;
           pb.x = prob; pb.y = gp;
         } else {
-          prob = lae(pv + ylast, p_prev + yblank);
+          prob = lae(pv + yl, p_prev + yb);
           o->prob = prob;
           pb.x = prob; pb.y = ninf();
         }
@@ -344,203 +375,173 @@ struct Engine {
       __syncthreads();
     }
     if (on) {
-      NodeHdr& h = hdr[slot];
       if (te > ts) {
-        // window bookkeeping for the contiguous write [ts, te)
-        if (ts > hi || ts < lo) { lo = ts; hi = te; }
+        if (ts > hi || ts < lo) { lo = ts; hi = te; }  // window bookkeeping for the contiguous write [ts, te)
         else hi = max(hi, te);
         if (hi - lo > cap[r]) lo = hi - cap[r];
-        h.lo[r] = lo; h.hi[r] = hi;
-        h.maxp[r] = maxv;  // reset + max over the band
-        smax[e * 2 + r] = maxv;
+        a_lo[2 * a + r] = lo; a_hi[2 * a + r] = hi;
+        a_maxp[2 * a + r] = maxv;  // reset + max over the band
       } else {
-        smax[e * 2 + r] = h.maxp[r];  // empty band: max_prob left stale (A.6b)
+        maxv = a_maxp[2 * a + r];  // empty band: max_prob left stale (A.6b)
       }
-      n_updates += (unsigned long long)(te - ts);
-    } else if (live && reset_other) {
-      smax[e * 2 + r] = hdr[slot].maxp[r];
+      n_updates += (unsigned long long)max(te - ts, 0);
     }
-    __syncthreads();
-  }
-
-  // ---- expansion: E = beam + children(beam) (PrefixTree.h:439-446), children created / revived ----
-  // bfs_first_row: ROW traversal while the beam is shorter than W
-  __device__ void build_expanded(int item, bool bfs) {
-    const int tid = threadIdx.x;
-    const int nb = sh[SH_NB];
-    const int W = P.W;
-    int nexp = bfs ? W : nb;  // number of nodes expanded this step
-    // In BFS mode element k >= nb is child (k-nb)%4 of element (k-nb)/4, all freshly created (first row).
-    if (tid < nb) { E[tid] = beam[tid]; act[tid] = 1; }
-    __syncthreads();
-    if (!bfs) {
-      // per beam node: which children are missing, is this its first expansion
-      int miss = 0, first = 0;
-      if (tid < nb) {
-        NodeHdr& h = hdr[beam[tid]];
-        first = h.tid < 0;
-        for (int c = 0; c < 4; ++c) {
-          const int ks = h.kid_slot[c];
-          const bool ok = !first && ks >= 0 && hdr[ks].order == h.kid_order[c];
-          if (!ok) miss |= 1 << c;
-        }
-        tmpa[tid] = __popc(miss);
-        tmpb[tid] = first;
+    // ranking keys: row_col = max0 + max1 (PrefixTree.h:111, :397); row = value(0, u) + max1 (:107, :393)
+    const double other = __shfl_xor_sync(0xffffffffu, maxv, 1);
+    if (used) {
+      if (mode == MODE_ROWCOL) {
+        if (r == 0) key[a] = make_double2(no_nan(maxv + other), (double)a_order[a]);
+      } else if (r == 1) {
+        key[a] = make_double2(no_nan(a_last0[a] + maxv), (double)a_order[a]);
       }
-      __syncthreads();
-      if (tid < nb) {
-        int abase = 0, fbase = 0;
-        for (int b = 0; b < tid; ++b) { abase += tmpa[b]; fbase += tmpb[b]; }
-        if (tid == nb - 1) { sh[SH_TOTALLOC] = abase + tmpa[tid]; sh[SH_TOTFIRST] = fbase + tmpb[tid]; }
-        const int slot = beam[tid];
-        NodeHdr& h = hdr[slot];
-        if (first) {
-          h.tid = sh[SH_TID] + fbase;
-          trace[h.tid] = ((uint32_t)h.parent_tid << 2) | (uint32_t)h.last;
-        }
-        int k = 0;
-        for (int c = 0; c < 4; ++c) {
-          int ks;
-          if (miss & (1 << c)) {
-            const int fi = sh[SH_NFREE] - 1 - (abase + k);
-            ks = (fi >= 0) ? freelist[fi] : -1;
-            if (ks >= 0) {
-              NodeHdr n;
-              n.order = (uint32_t)(sh[SH_ORDER] + abase + k);
-              n.state = 0; n.parent_slot = slot; n.parent_order = h.order; n.parent_tid = h.tid; n.tid = -1;
-              n.depth = h.depth + 1; n.last = c;
-              for (int q = 0; q < 4; ++q) { n.kid_slot[q] = -1; n.kid_order[q] = 0; }
-              n.lo[0] = n.lo[1] = 0; n.hi[0] = n.hi[1] = 0;
-              n.maxp[0] = n.maxp[1] = ninf(); n.pad[0] = n.pad[1] = 0;
-              hdr[ks] = n;
-              h.kid_slot[c] = ks; h.kid_order[c] = n.order;
-            }
-            ++k;
-          } else {
-            ks = h.kid_slot[c];
-            if (hdr[ks].state != 0) hdr[ks].state = 0;  // revived with its retained windows
-          }
-          E[nb + 4 * tid + c] = ks;
-          act[nb + 4 * tid + c] = ks >= 0;
-        }
-      }
-      __syncthreads();
-      if (tid == 0) {
-        if (sh[SH_TOTALLOC] > sh[SH_NFREE]) sh[SH_STATUS] |= POB_ST_POOL_OVERFLOW;
-        sh[SH_NFREE] = max(0, sh[SH_NFREE] - sh[SH_TOTALLOC]);
-        sh[SH_ORDER] += sh[SH_TOTALLOC];
-        sh[SH_TID] += sh[SH_TOTFIRST];
-        sh[SH_NE] = 5 * nb;
-      }
-      __syncthreads();
-      // children that are themselves beam members are duplicates (Beam.h:96-99)
-      const int nE = 5 * nb;
-      if (tid >= nb && tid < nE && act[tid]) {
-        const int s = E[tid];
-        for (int b = 0; b < nb; ++b) if (beam[b] == s) { act[tid] = 0; break; }
-      }
-    } else {
-      // first-row BFS: sequential dependency only through indices, so do it level by level on thread 0..:
-      // element k expanded for k < W; all expansions are first expansions with fresh children.
-      if (tid == 0) {
-        int ne = nb;
-        for (int k = 0; k < nexp && k < ne; ++k) {
-          const int slot = E[k];
-          NodeHdr& h = hdr[slot];
-          if (h.tid < 0) {
-            h.tid = sh[SH_TID]++;
-            trace[h.tid] = ((uint32_t)h.parent_tid << 2) | (uint32_t)h.last;
-          }
-          for (int c = 0; c < 4; ++c) {
-            int ks = h.kid_slot[c];
-            if (!(ks >= 0 && hdr[ks].order == h.kid_order[c])) {
-              const int fi = --sh[SH_NFREE];
-              ks = freelist[fi];
-              NodeHdr n;
-              n.order = (uint32_t)(sh[SH_ORDER]++);
-              n.state = 0; n.parent_slot = slot; n.parent_order = h.order; n.parent_tid = h.tid; n.tid = -1;
-              n.depth = h.depth + 1; n.last = c;
-              for (int q = 0; q < 4; ++q) { n.kid_slot[q] = -1; n.kid_order[q] = 0; }
-              n.lo[0] = n.lo[1] = 0; n.hi[0] = n.hi[1] = 0;
-              n.maxp[0] = n.maxp[1] = ninf(); n.pad[0] = n.pad[1] = 0;
-              hdr[ks] = n;
-              h.kid_slot[c] = ks; h.kid_order[c] = n.order;
-            } else if (hdr[ks].state != 0) hdr[ks].state = 0;
-            bool dupl = false;
-            for (int q = 0; q < ne; ++q) if (E[q] == ks) { dupl = true; break; }
-            E[ne] = ks; act[ne] = !dupl; ++ne;
-          }
-        }
-        sh[SH_NE] = ne;
-      }
-      __syncthreads();
     }
-    __syncthreads();
-    const int nE = sh[SH_NE];
-    if (tid < nE && act[tid]) slot2e[E[tid]] = (int16_t)tid;
     __syncthreads();
   }
 
   // ---- Beam::prune (Beam.h:93-108): rank by score desc, exact ties by creation order ----------
-  __device__ void prune(int nE) {
+  // one barrier at the end; also clears the per-step flags
+  __device__ void prune() {
     const int tid = threadIdx.x;
+    const bool two = (int)blockDim.x >= 2 * EMAX;
+    const int a = two ? (tid >> 1) : tid;
+    const int half = two ? (tid & 1) : 0;
+    const bool cand = a < EMAX && a_slot[a] >= 0;
     int rank = 0;
-    bool a = tid < nE && act[tid];
-    if (a && !(score[tid] == score[tid])) score[tid] = ninf();  // NaN cannot be ranked
-    if (tid == 0) sh[SH_DMIN] = 0x7fffffff;
-    __syncthreads();
-    if (a) {
-      const double s = score[tid];
-      const uint32_t o = eorder[tid];
-      for (int j = 0; j < nE; ++j) {
-        if (!act[j]) continue;
-        const double sj = score[j];
-        rank += (sj > s) || (sj == s && eorder[j] < o);
+    if (tid == 0) { sh[SH_NB] = min(sh[SH_NUSED], W); sh[SH_DMIN] = 0x7fffffff; }
+    if (cand) {
+      const double2 k = key[a];
+      const int mid = two ? (EMAX >> 1) : EMAX;
+      const int j0 = half ? mid : 0, j1 = half ? EMAX : mid;
+      for (int j = j0; j < j1; ++j) {
+        const double2 kj = key[j];
+        rank += (kj.x > k.x) || (kj.x == k.x && kj.y < k.y);
       }
     }
-    __syncthreads();
-    if (a && rank < P.W) {
-      beam[rank] = E[tid];
-      atomicMin(&sh[SH_DMIN], hdr[E[tid]].depth);
-    }
-    if (tid == 0) {
-      int n = 0;
-      for (int j = 0; j < nE; ++j) n += act[j];
-      sh[SH_NB] = min(n, P.W);
+    if (two) rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+    __syncthreads();  // SH_DMIN reset is visible before the atomicMin below
+    if (a < EMAX && half == 0) {
+      a_needed[a] = 0;
+      const bool inb = cand && rank < W;
+      a_inbeam[a] = inb;
+      if (inb) {
+        beam[rank] = a;
+        atomicMin(&sh[SH_DMIN], a_depth[a]);
+      }
     }
     __syncthreads();
   }
 
-  // ---- retire nodes that left the expanded beam; recycle retired nodes that can never matter again ----
-  // A retired node is freed when both windows are dead (every later read is at an index >= dead_r, so
-  // hi <= dead_r means all reads miss) AND it can no longer hand retained children to a revival: either
-  // all its child links are already invalid, or it is unreachable.  The beam's minimum depth never
-  // decreases (the next beam is drawn from beam + children), so a non-active node of depth <= that minimum
-  // has no ancestor that can ever be expanded again: unreachable.
-  __device__ void retire_and_reclaim(int nEold, int dead0, int dead1) {
-    const int tid = threadIdx.x;
-    int myslot = -1;
-    if (tid < nEold && actold[tid]) {
-      myslot = Eold[tid];
-      if (slot2e[myslot] < 0) {
-        const int pos = atomicAdd(&sh[SH_RQT], 1);
-        const int stamp = atomicAdd(&sh[SH_STAMP], 1) + 1;
-        hdr[myslot].state = stamp;
-        retq[pos % P.RQ] = make_int2(myslot, stamp);
+  // ---- retire an active slot: write the header home, queue the node for reclamation ----
+  __device__ void retire(int a) {
+    const int slot = a_slot[a];
+    NodeHdr& h = hdr[slot];
+    h.tid = a_tid[a];
+    for (int c = 0; c < 4; ++c) { h.kid_slot[c] = a_kid[4 * a + c]; h.kid_order[c] = a_kido[4 * a + c]; }
+    h.lo[0] = a_lo[2 * a]; h.lo[1] = a_lo[2 * a + 1]; h.hi[0] = a_hi[2 * a]; h.hi[1] = a_hi[2 * a + 1];
+    h.maxp[0] = a_maxp[2 * a]; h.maxp[1] = a_maxp[2 * a + 1];
+    const int stamp = atomicAdd(&sh[SH_STAMP], 1) + 1;
+    h.state = stamp;
+    const int pos = atomicAdd(&sh[SH_RQT], 1);
+    retq[pos % RQ] = make_int2(slot, stamp);
+    slot2e[slot] = -1;
+    a_slot[a] = -1;
+    key[a] = make_double2(ninf(), 4.5e9);
+    a_free[atomicAdd(&sh[SH_AFREE], 1)] = a;
+    atomicSub(&sh[SH_NUSED], 1);
+  }
+
+  // fill an active slot for a node that did not exist (fresh) or comes back from retirement (revive)
+  __device__ void activate_fresh(int a, int slot, uint32_t order, int pa, int last) {
+    NodeHdr n;
+    n.order = order; n.state = 0; n.parent_slot = a_slot[pa]; n.parent_order = a_order[pa];
+    n.parent_tid = a_tid[pa]; n.tid = -1; n.depth = a_depth[pa] + 1; n.last = last;
+    for (int q = 0; q < 4; ++q) { n.kid_slot[q] = -1; n.kid_order[q] = 0; }
+    n.lo[0] = n.lo[1] = 0; n.hi[0] = n.hi[1] = 0; n.maxp[0] = n.maxp[1] = ninf(); n.pad[0] = n.pad[1] = 0;
+    hdr[slot] = n;
+    a_slot[a] = slot; a_order[a] = order; a_par[a] = pa; a_pslot[a] = n.parent_slot; a_porder[a] = n.parent_order;
+    a_depth[a] = n.depth; a_tid[a] = -1; a_ptid[a] = n.parent_tid;
+    for (int q = 0; q < 4; ++q) { a_kid[4 * a + q] = -1; a_kido[4 * a + q] = 0; }
+    a_lo[2 * a] = a_lo[2 * a + 1] = 0; a_hi[2 * a] = a_hi[2 * a + 1] = 0;
+    a_maxp[2 * a] = a_maxp[2 * a + 1] = ninf(); a_last0[a] = ninf();
+    a_last[a] = (uint8_t)last; a_pstat[a] = PS_INE; a_same[a] = (a_last[pa] == last);
+    a_inbeam[a] = 0; a_needed[a] = 1;
+    key[a] = make_double2(ninf(), 4.5e9);
+    slot2e[slot] = (int16_t)a;
+  }
+
+  __device__ void activate_revived(int a, int slot, int pa) {
+    NodeHdr& h = hdr[slot];
+    h.state = 0;
+    a_slot[a] = slot; a_order[a] = h.order; a_par[a] = pa; a_pslot[a] = h.parent_slot; a_porder[a] = h.parent_order;
+    a_depth[a] = h.depth; a_tid[a] = h.tid; a_ptid[a] = h.parent_tid;
+    for (int q = 0; q < 4; ++q) {
+      const int ks = h.kid_slot[q];
+      a_kid[4 * a + q] = ks; a_kido[4 * a + q] = h.kid_order[q];
+      if (ks >= 0) {
+        // a child that stayed in the expanded beam (it is a beam member) reads this node live again
+        const int ka = slot2e[ks];
+        if (ka >= 0 && a_order[ka] == h.kid_order[q]) { a_par[ka] = a; a_pstat[ka] = PS_INE; }
       }
     }
-    if (tid == 0) { sh[SH_FIRSTALIVE] = 0x7fffffff; sh[SH_FREED] = 0; sh[SH_REPUSH] = 0; }
-    __syncthreads();
+    a_lo[2 * a] = h.lo[0]; a_lo[2 * a + 1] = h.lo[1]; a_hi[2 * a] = h.hi[0]; a_hi[2 * a + 1] = h.hi[1];
+    a_maxp[2 * a] = h.maxp[0]; a_maxp[2 * a + 1] = h.maxp[1]; a_last0[a] = ninf();
+    a_last[a] = (uint8_t)h.last; a_pstat[a] = PS_INE; a_same[a] = (a_last[pa] == h.last);
+    a_inbeam[a] = 0; a_needed[a] = 1;
+    key[a] = make_double2(ninf(), 4.5e9);
+    slot2e[slot] = (int16_t)a;
+  }
+
+  // ---- expansion of the new beam + retirement + reclamation: three phases, three barriers ----------
+  // dead0/dead1: every later read of read r is at an index >= dead_r.  The pool's free slots form a FIFO ring
+  // (pops at SH_FQH, pushes at SH_FQT), so recycling and allocation can share a phase.
+  __device__ void expand_and_retire(int dead0, int dead1) {
+    const int tid = threadIdx.x;
+    const int nb = sh[SH_NB];
+    // -- phase X1: beam threads classify their children.  A retired child that comes back is marked active
+    //    right away so that the queue inspection of the next phase sees its queue entry as stale.
+    int kinds = 0, nfresh = 0, nact = 0, first = 0, a = -1;
+    if (tid < nb) {
+      a = beam[tid];
+      a_needed[a] = 1;
+      first = a_tid[a] < 0;
+      for (int c = 0; c < 4; ++c) {
+        int kind = KID_FRESH;
+        const int ks = a_kid[4 * a + c];
+        if (ks >= 0) {
+          const int ka = slot2e[ks];
+          if (ka >= 0 && a_order[ka] == a_kido[4 * a + c]) { kind = KID_ACTIVE; a_needed[ka] = 1; }
+          else if (hdr[ks].order == a_kido[4 * a + c]) { kind = KID_REVIVE; hdr[ks].state = 0; }
+        }
+        kinds |= kind << (2 * c);
+        nfresh += kind == KID_FRESH;
+        nact += kind != KID_ACTIVE;
+      }
+      tmpa[tid] = nfresh; tmpc[tid] = first;
+    }
     const int head = sh[SH_RQH], tail = sh[SH_RQT];
-    const int navail = P.noreclaim ? 0 : min(tail - head, (int)blockDim.x);
+    const int navail = noreclaim ? 0 : min(tail - head, (int)blockDim.x);
     const int dmin = sh[SH_DMIN];
-    int st = 0;  // 1 stale, 2 dead+freeable, 3 dead but must be kept, 4 alive
-    int slot = -1, stamp = 0;
+    const int fq_head = sh[SH_FQH], fq_tail = sh[SH_FQT];
+    // pool pressure: recycle live retirees too (flagged; the reference never frees anything)
+    const bool force = (fq_tail - fq_head) < 8 * W + 16 && navail > 0;
+    __syncthreads();
+    // -- phase X2: retire what the next expanded beam does not contain, freeze orphaned children, inspect the
+    //    retire queue (entries queued in earlier steps only: a node retired now is still readable)
+    if (tid < EMAX && a_slot[tid] >= 0) {
+      if (!a_needed[tid]) retire(tid);
+      else if (a_pstat[tid] == PS_INE && !a_needed[a_par[tid]]) {
+        const int pa = a_par[tid];
+        a_plo[2 * tid] = a_lo[2 * pa]; a_plo[2 * tid + 1] = a_lo[2 * pa + 1];
+        a_phi[2 * tid] = a_hi[2 * pa]; a_phi[2 * tid + 1] = a_hi[2 * pa + 1];
+        a_pstat[tid] = PS_FROZEN;
+      }
+    }
+    int st = 0, rslot = -1, rstamp = 0;  // 1 stale, 2 dead + freeable, 3 dead but kept, 4 alive
     if (tid < navail) {
-      const int2 q = retq[(head + tid) % P.RQ];
-      slot = q.x; stamp = q.y;
-      const NodeHdr& h = hdr[slot];
-      if (h.state != stamp) st = 1;
+      const int2 q = retq[(head + tid) % RQ];
+      rslot = q.x; rstamp = q.y;
+      const NodeHdr& h = hdr[rslot];
+      if (h.state != rstamp) st = 1;
       else if (!(h.hi[0] <= dead0 && h.hi[1] <= dead1)) st = 4;
       else if (h.depth <= dmin) st = 2;
       else {
@@ -554,54 +555,106 @@ struct Engine {
       if (st == 4) atomicMin(&sh[SH_FIRSTALIVE], tid);
     }
     __syncthreads();
-    int fa = min(sh[SH_FIRSTALIVE], navail);  // entries before the first live one are consumed
-    bool force = false;
-    if (sh[SH_NFREE] + fa < 4 * P.W + 8 && navail > 0) {
-      // pool pressure: recycle live retirees too (flagged; the reference never frees anything)
-      fa = navail; force = true;
-      if (tid == 0) sh[SH_STATUS] |= POB_ST_POOL_OVERFLOW;
+    // -- phase X3: consume the inspected queue entries (strictly from the head, up to the first live one);
+    //    beam threads create / revive the missing children
+    {
+      int fa = min(sh[SH_FIRSTALIVE], navail);
+      if (force) { fa = navail; if (tid == 0) sh[SH_STATUS] |= POB_ST_POOL_OVERFLOW; }
+      if (tid < fa) {
+        if (st == 2 || (force && st >= 2)) {
+          NodeHdr& h = hdr[rslot];
+          h.order = 0; h.state = -1;
+          freelist[atomicAdd(&sh[SH_FQT], 1) % NP] = rslot;
+        } else if (st == 3 || st == 4) {
+          retq[atomicAdd(&sh[SH_RQT], 1) % RQ] = make_int2(rslot, rstamp);  // look again one queue cycle later
+        }
+      }
+      if (tid == 0) sh[SH_RQH] = head + fa;
     }
-    if (tid < fa) {
-      if (st == 2 || (force && st >= 2)) {
-        NodeHdr& h = hdr[slot];
-        h.order = 0; h.state = -1;
-        const int pos = atomicAdd(&sh[SH_FREED], 1);
-        freelist[sh[SH_NFREE] + pos] = slot;
-      } else if (st == 3 || st == 4) {
-        const int pos = atomicAdd(&sh[SH_REPUSH], 1);
-        retq[(tail + pos) % P.RQ] = make_int2(slot, stamp);  // look again one queue cycle later
+    if (tid < nb) {
+      int obase = 0, fbase = 0;
+      for (int b = 0; b < tid; ++b) { obase += tmpa[b]; fbase += tmpc[b]; }
+      if (tid == nb - 1) { sh[SH_TOTALLOC] = obase + nfresh; sh[SH_TOTFIRST] = fbase + first; }
+      if (first) {
+        a_tid[a] = sh[SH_TID] + fbase;
+        trace[a_tid[a]] = ((uint32_t)a_ptid[a] << 2) | (uint32_t)a_last[a];
+      }
+      const int abase = (nact > 0) ? atomicSub(&sh[SH_AFREE], nact) : 0;   // active slots [abase-nact, abase)
+      const int pbase = (nfresh > 0) ? atomicAdd(&sh[SH_FQH], nfresh) : 0;  // ring entries [pbase, pbase+nfresh)
+      if ((nfresh > 0 && pbase + nfresh > fq_tail) || (nact > 0 && abase - nact < 0)) {
+        // cannot happen while the reclamation keeps its margin; refuse to corrupt memory if it does
+        atomicOr(&sh[SH_STATUS], POB_ST_POOL_OVERFLOW);
+        if (nact > 0) atomicAdd(&sh[SH_AFREE], nact);
+        if (nfresh > 0) atomicSub(&sh[SH_FQH], nfresh);
+      } else {
+        int k = 0, ai = 0, pi = 0;
+        for (int c = 0; c < 4; ++c) {
+          const int kind = (kinds >> (2 * c)) & 3;
+          if (kind == KID_ACTIVE) continue;
+          const int na = a_free[abase - 1 - ai]; ++ai;
+          if (kind == KID_FRESH) {
+            const int slot = freelist[(pbase + pi) % NP]; ++pi;
+            const uint32_t order = (uint32_t)(sh[SH_ORDER] + obase + k); ++k;
+            activate_fresh(na, slot, order, a, c);
+            a_kid[4 * a + c] = slot; a_kido[4 * a + c] = order;
+          } else {
+            activate_revived(na, a_kid[4 * a + c], a);
+          }
+        }
+        if (nact > 0) atomicAdd(&sh[SH_NUSED], nact);
       }
     }
     __syncthreads();
-    if (tid == 0) { sh[SH_NFREE] += sh[SH_FREED]; sh[SH_RQH] = head + fa; sh[SH_RQT] = tail + sh[SH_REPUSH]; }
+  }
+
+  // ROW traversal while the beam is shorter than W (first row): the reference walks b < beam_width over a
+  // list that grows as children are pushed (BeamSearch.h:132-144), i.e. a breadth-first closure.  Sequential,
+  // runs once per item.
+  __device__ void expand_bfs() {
+    if (threadIdx.x == 0) {
+      int* list = tmpa;  // EMAX >= 4 + 4W entries
+      int n = 0;
+      const int nb = sh[SH_NB];
+      for (int b = 0; b < nb; ++b) list[n++] = beam[b];
+      for (int k = 0; k < W && k < n; ++k) {
+        const int a = list[k];
+        if (a_tid[a] < 0) {
+          a_tid[a] = sh[SH_TID]++;
+          trace[a_tid[a]] = ((uint32_t)a_ptid[a] << 2) | (uint32_t)a_last[a];
+        }
+        for (int c = 0; c < 4; ++c) {
+          const int ks = a_kid[4 * a + c];
+          int ka = -1;
+          if (ks >= 0) { const int x = slot2e[ks]; if (x >= 0 && a_order[x] == a_kido[4 * a + c]) ka = x; }
+          if (ka < 0 && sh[SH_AFREE] > 0 && sh[SH_FQT] - sh[SH_FQH] > 0) {
+            ka = a_free[--sh[SH_AFREE]];
+            if (ks >= 0 && hdr[ks].order == a_kido[4 * a + c]) activate_revived(ka, ks, a);
+            else {
+              const int slot = freelist[(sh[SH_FQH]++) % NP];
+              const uint32_t order = (uint32_t)sh[SH_ORDER]++;
+              activate_fresh(ka, slot, order, a, c);
+              a_kid[4 * a + c] = slot; a_kido[4 * a + c] = order;
+            }
+            sh[SH_NUSED]++;
+          }
+          if (ka >= 0 && n < EMAX) list[n++] = ka;
+        }
+      }
+    }
     __syncthreads();
   }
 
   __device__ void dbg_record(const BeamParams& G, long step) {
     if (!G.dbg_trace) return;
-    __syncthreads();
-    if (threadIdx.x == 0 && step < 100000) {
+    if (threadIdx.x == 0 && step < 50000) {
       double sum = 0;
       for (int b = 0; b < sh[SH_NB]; ++b) {
-        const NodeHdr& h = hdr[beam[b]];
-        double sc = (P.mode == MODE_1D) ? wptr(beam[b], 0, h.hi[0] - 1)->prob
-                  : (P.mode == MODE_ROW) ? wptr(beam[b], 0, h.hi[0] - 1)->prob + h.maxp[1] : h.maxp[0] + h.maxp[1];
+        const double sc = key[beam[b]].x;
         if (b == 0) G.dbg_trace[2 * step] = sc;
         if (sc > -1e300) sum += sc;
       }
       G.dbg_trace[2 * step + 1] = sum;
     }
-    __syncthreads();
-  }
-
-  __device__ void save_old(int nE) {
-    const int tid = threadIdx.x;
-    if (tid < nE) {
-      Eold[tid] = E[tid]; actold[tid] = act[tid];
-      if (act[tid]) slot2e[E[tid]] = -1;
-    }
-    if (tid == 0) sh[SH_NEOLD] = nE;
-    __syncthreads();
   }
 
   __device__ void run_item(const BeamParams& G, int item, char* ws, char* smem);
@@ -610,58 +663,74 @@ struct Engine {
 template <int MODEL>
 __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws, char* smem) {
   const int tid = threadIdx.x, NT = blockDim.x;
-  const int W = G.W, NP = G.NP, EMAX = G.EMAX;
-  const int mode = G.mode;
   unsigned long long n_updates = 0;
-  // ---- carve shared memory (the engine object itself sits at the front)
+  // ---- carve shared memory (the engine object itself sits at the front) and the global workspace
   if (tid == 0) {
-    P.W = W; P.NP = NP; P.RQ = G.RQ; P.EMAX = EMAX; P.mode = mode; P.noreclaim = G.dbg_noreclaim;
+    W = G.W; NP = G.NP; RQ = G.RQ; EMAX = G.EMAX; mode = G.mode; noreclaim = G.dbg_noreclaim;
     char* p = smem + ((sizeof(Engine<MODEL>) + 15) & ~(size_t)15);
     pub = (double2*)p; p += sizeof(double2) * 2 * EMAX * 2;
-    score = (double*)p; p += sizeof(double) * EMAX;
-    smax = (double*)p; p += sizeof(double) * EMAX * 2;
-    E = (int32_t*)p; p += 4 * EMAX;
-    Eold = (int32_t*)p; p += 4 * EMAX;
-    eorder = (uint32_t*)p; p += 4 * EMAX;
+    key = (double2*)p; p += sizeof(double2) * EMAX;
+    a_maxp = (double*)p; p += 8 * EMAX * 2;
+    a_last0 = (double*)p; p += 8 * EMAX;
+    a_slot = (int32_t*)p; p += 4 * EMAX;
+    a_order = (uint32_t*)p; p += 4 * EMAX;
+    a_par = (int32_t*)p; p += 4 * EMAX;
+    a_pslot = (int32_t*)p; p += 4 * EMAX;
+    a_porder = (uint32_t*)p; p += 4 * EMAX;
+    a_depth = (int32_t*)p; p += 4 * EMAX;
+    a_tid = (int32_t*)p; p += 4 * EMAX;
+    a_ptid = (int32_t*)p; p += 4 * EMAX;
+    a_kid = (int32_t*)p; p += 16 * EMAX;
+    a_kido = (uint32_t*)p; p += 16 * EMAX;
+    a_lo = (int32_t*)p; p += 8 * EMAX;
+    a_hi = (int32_t*)p; p += 8 * EMAX;
+    a_plo = (int32_t*)p; p += 8 * EMAX;
+    a_phi = (int32_t*)p; p += 8 * EMAX;
+    a_free = (int32_t*)p; p += 4 * EMAX;
     tmpa = (int32_t*)p; p += 4 * EMAX;
     tmpb = (int32_t*)p; p += 4 * EMAX;
+    tmpc = (int32_t*)p; p += 4 * EMAX;
     beam = (int32_t*)p; p += 4 * ((W + 3) & ~3);
     sh = (int32_t*)p; p += 4 * 32;
-    slot2e = (int16_t*)p; p += 2 * NP;
-    act = (uint8_t*)p; p += (EMAX + 15) & ~15;
-    actold = (uint8_t*)p; p += (EMAX + 15) & ~15;
-  }
-  // ---- carve the global workspace
-  if (tid == 0) {
-  cap[0] = G.CAP0; cap[1] = G.CAP1; mask[0] = G.CAP0 - 1; mask[1] = G.CAP1 - 1;
-  rv[0] = make_view(G.r[0], item);
-  if (mode != MODE_1D) rv[1] = make_view(G.r[1], item); else { rv[1] = rv[0]; rv[1].T = 0; }
-  {
-    char* p = ws;
-    hdr = (NodeHdr*)p; p += sizeof(NodeHdr) * (size_t)NP;
-    win[0] = (Ent*)p; p += sizeof(Ent) * (size_t)NP * cap[0];
-    win[1] = (Ent*)p; p += sizeof(Ent) * (size_t)NP * cap[1];
-    freelist = (int32_t*)p; p += 4 * (size_t)NP;
-    retq = (int2*)p; p += 8 * (size_t)G.RQ;
-    cum[0] = (double*)p; p += 8 * (size_t)(MODEL == POB_MODEL_CTC ? rv[0].T : 0);
-    cum[1] = (double*)p; p += 8 * (size_t)(MODEL == POB_MODEL_CTC ? rv[1].T : 0);
-    sufmin = (int32_t*)p;
-  }
-  trace = G.trace + G.trace_off[item];
+    slot2e = (int16_t*)p; p += 2 * (size_t)NP;
+    const int eb = (EMAX + 15) & ~15;
+    a_last = (uint8_t*)p; p += eb;
+    a_pstat = (uint8_t*)p; p += eb;
+    a_same = (uint8_t*)p; p += eb;
+    a_inbeam = (uint8_t*)p; p += eb;
+    a_needed = (uint8_t*)p; p += eb;
+    cap[0] = G.CAP0; cap[1] = G.CAP1; mask[0] = G.CAP0 - 1; mask[1] = G.CAP1 - 1;
+    rv[0] = make_view(G.r[0], item);
+    if (mode != MODE_1D) rv[1] = make_view(G.r[1], item); else { rv[1] = rv[0]; rv[1].T = 0; }
+    char* q = ws;
+    hdr = (NodeHdr*)q; q += sizeof(NodeHdr) * (size_t)NP;
+    win[0] = (Ent*)q; q += sizeof(Ent) * (size_t)NP * cap[0];
+    win[1] = (Ent*)q; q += sizeof(Ent) * (size_t)NP * cap[1];
+    freelist = (int32_t*)q; q += 4 * (size_t)NP;
+    retq = (int2*)q; q += 8 * (size_t)RQ;
+    cum[0] = (double*)q; q += 8 * (size_t)(MODEL == POB_MODEL_CTC ? rv[0].T : 0);
+    cum[1] = (double*)q; q += 8 * (size_t)(MODEL == POB_MODEL_CTC ? rv[1].T : 0);
+    sufmin = (int32_t*)q;
+    trace = G.trace + G.trace_off[item];
   }
   __syncthreads();
   const int U = rv[0].T, V = rv[1].T;
   int32_t* otop = G.out_top + 4 * (size_t)item;
 
-  // ---- init pool
+  // ---- init pool and active slots
   for (int s = tid; s < NP; s += NT) {
     hdr[s].order = 0; hdr[s].state = -1;
-    freelist[s] = NP - 1 - s;  // pops come from the end: slot 0 first
+    freelist[s] = s;  // FIFO ring of free pool slots
     slot2e[s] = -1;
   }
+  for (int a = tid; a < EMAX; a += NT) {
+    a_slot[a] = -1; a_free[a] = EMAX - 1 - a; key[a] = make_double2(ninf(), 4.5e9);
+    a_inbeam[a] = 0; a_needed[a] = 0;
+  }
   if (tid == 0) {
-    for (int k = 0; k < SH_COUNT; ++k) sh[k] = 0;
-    sh[SH_NFREE] = NP; sh[SH_ORDER] = 1; sh[SH_TID] = 1;
+    for (int k = 0; k < 32; ++k) sh[k] = 0;
+    sh[SH_FQH] = 0; sh[SH_FQT] = NP; sh[SH_AFREE] = EMAX; sh[SH_ORDER] = 1; sh[SH_TID] = 1;
+    sh[SH_DMIN] = 0x7fffffff; sh[SH_FIRSTALIVE] = 0x7fffffff;
   }
   if (MODEL == POB_MODEL_CTC && tid < 2 && (tid == 0 || mode != MODE_1D)) {
     // PrefixTree.h:508-514: sequential running sum of the blank column
@@ -672,26 +741,39 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws,
   __syncthreads();
   if (U <= 0 || (mode != MODE_1D && V <= 0)) {
     if (tid == 0) { otop[0] = 0; otop[1] = -1; otop[2] = 0; otop[3] = POB_ST_EMPTY; G.out_score[item] = 0; }
+    __syncthreads();
     return;
   }
   // ---- seed: the 4 children of the root, updated at t = 0 (BeamSearch.h:24-30, :287-293)
   const int nbase = rv[0].S - 1;
   if (tid < nbase) {
-    const int slot = freelist[NP - 1 - tid];
+    const int a = tid, slot = tid;  // the first pool slots and active slots go to the root's children
     NodeHdr n;
     n.order = 1 + tid; n.state = 0; n.parent_slot = -1; n.parent_order = 0; n.parent_tid = 0; n.tid = -1;
     n.depth = 1; n.last = tid;
     for (int q = 0; q < 4; ++q) { n.kid_slot[q] = -1; n.kid_order[q] = 0; }
     n.lo[0] = n.lo[1] = 0; n.hi[0] = n.hi[1] = 0; n.maxp[0] = n.maxp[1] = ninf(); n.pad[0] = n.pad[1] = 0;
     hdr[slot] = n;
-    beam[tid] = slot;
+    a_slot[a] = slot; a_order[a] = n.order; a_par[a] = -1; a_pslot[a] = -1; a_porder[a] = 0; a_depth[a] = 1;
+    a_tid[a] = -1; a_ptid[a] = 0;
+    for (int q = 0; q < 4; ++q) { a_kid[4 * a + q] = -1; a_kido[4 * a + q] = 0; }
+    a_lo[2 * a] = a_lo[2 * a + 1] = 0; a_hi[2 * a] = a_hi[2 * a + 1] = 0;
+    a_maxp[2 * a] = a_maxp[2 * a + 1] = ninf(); a_last0[a] = ninf();
+    a_last[a] = (uint8_t)tid; a_pstat[a] = PS_ROOT; a_same[a] = 0; a_inbeam[a] = 1; a_needed[a] = 1;
+    slot2e[slot] = (int16_t)a;
+    beam[tid] = a;
     n_updates += (mode != MODE_1D) ? 2 : 1;
   }
+  if (tid == 0) {
+    sh[SH_FQH] = nbase; sh[SH_AFREE] = EMAX - nbase; sh[SH_ORDER] = 1 + nbase; sh[SH_NB] = nbase;
+    sh[SH_NUSED] = nbase;
+  }
   __syncthreads();
-  update_all(tid < nbase, tid < nbase ? beam[tid] : 0, 0, 0);
-  if (mode != MODE_1D) update_all(tid < nbase, tid < nbase ? beam[tid] : 0, 1, 0);
-  if (tid == 0) { sh[SH_NFREE] = NP - nbase; sh[SH_ORDER] = 1 + nbase; sh[SH_NB] = nbase; }
-  __syncthreads();
+  {
+    const double p = update_all(tid < nbase, tid, 0, 0);
+    if (mode == MODE_1D && tid < nbase) key[tid] = make_double2(no_nan(p), (double)a_order[tid]);
+    if (mode != MODE_1D) update_all(tid < nbase, tid, 1, 0);
+  }
 
   const int32_t* env = G.env ? G.env + 2 * G.env_off[item] : nullptr;
   const int32_t* envt = G.envt ? G.envt + 2 * G.envt_off[item] : nullptr;
@@ -715,58 +797,38 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws,
 
   if (mode == MODE_1D) {
     // BeamSearch.h:33-53
-    build_expanded(item, false);
+    expand_and_retire(-1, 0x7fffffff);
     for (int t = 1; t < U; ++t) {
-      const int nE = sh[SH_NE];
-      const bool mine = tid < nE && act[tid];
-      update_all(mine, mine ? E[tid] : 0, 0, t);
+      const bool mine = tid < EMAX && a_slot[tid] >= 0;
+      const double p = update_all(mine, tid, 0, t);
       if (mine) {
         n_updates++;
-        score[tid] = wptr(E[tid], 0, t)->prob;  // last_probability(): value at the last written t
-        eorder[tid] = hdr[E[tid]].order;
+        key[tid] = make_double2(no_nan(p), (double)a_order[tid]);  // last_probability(): value at the last t
       }
       __syncthreads();
-      save_old(nE);
-      prune(nE);
-      build_expanded(item, false);
-      retire_and_reclaim(nE, t, 0x7fffffff);  // the next step reads index t
+      prune();
+      dbg_record(G, nsteps);
+      expand_and_retire(t, 0x7fffffff);  // the next step reads index t
       ++nsteps;
     }
   } else if (mode == MODE_ROW) {
     // BeamSearch.h:127-167 (envelope) / :196-247 (no envelope: rows start at 1, band = [0, V))
-    build_expanded(item, sh[SH_NB] < W);
+    if (sh[SH_NB] < W) expand_bfs(); else expand_and_retire(-1, -1);
     for (int u = env ? 0 : 1; u < U; ++u) {
       int rs = env ? env[2 * u] : 0, re = env ? env[2 * u + 1] : V;
       rs = max(rs, 0); re = min(re, V);
-      const int nE = sh[SH_NE];
       {
-        const bool mine = tid < nE && act[tid];
-        update_all(mine, mine ? E[tid] : 0, 0, u);
+        const bool mine = tid < EMAX && a_slot[tid] >= 0;
+        update_all(mine, tid, 0, u);
         if (mine) n_updates++;
       }
       int t0[2] = {u, rs}, t1[2] = {u + 1, re};
-      sweep(nE, 2, t0, t1, false, n_updates);
-      if (tid < nE && act[tid]) {
-        score[tid] = wptr(E[tid], 0, u)->prob + smax[tid * 2 + 1];  // max_probability() (PrefixTree.h:107, :393)
-        eorder[tid] = hdr[E[tid]].order;
-      }
-      __syncthreads();
-      if (G.dbg_trace && nsteps >= G.dbg_step - 2 && nsteps <= G.dbg_step + 1 && tid < nE) {
-        // rows of 10 doubles at offset 4000 + ((step - (dbg_step-2)) * 160 + tid) * 10
-        double* o = G.dbg_trace + 4000 + ((nsteps - (G.dbg_step - 2)) * 160 + tid) * 10;
-        const NodeHdr& h = hdr[E[tid]];
-        o[0] = act[tid] ? (double)h.order : -1.0; o[1] = h.depth; o[2] = h.last; o[3] = h.parent_order;
-        o[4] = act[tid] ? score[tid] : 0; o[5] = wptr(E[tid], 0, u)->prob; o[6] = smax[tid * 2 + 1];
-        o[7] = h.lo[1]; o[8] = h.hi[1]; o[9] = E[tid];
-        if (h.parent_slot >= 0) { const NodeHdr& ph = hdr[h.parent_slot]; o[2] = ph.order; o[6] = ph.hi[0]; o[7] = ph.state; o[8] = slot2e[h.parent_slot]; o[1] = h.parent_slot; }
-      }
-      save_old(nE);
-      prune(nE);
+      sweep(2, t0, t1, n_updates);
+      prune();
       dbg_record(G, nsteps);
-      build_expanded(item, sh[SH_NB] < W);
       // read 0 is next read at index u; read 1 at >= (smallest band start of any later row) - 1
       const int nrs = (u + 1 < U) ? (env ? sufmin[u + 1] : 0) : 0x7ffffffe;
-      retire_and_reclaim(nE, u, nrs - 1);
+      if (sh[SH_NB] < W) expand_bfs(); else expand_and_retire(u, nrs - 1);
       ++nsteps;
     }
   } else {
@@ -781,8 +843,9 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws,
       else if (v < ers) {
         const int nb = sh[SH_NB];
         if (nb < W && tid == 0) sh[SH_STATUS] |= POB_ST_SHORT_BEAM_SKIP;
-        update_all(tid < nb, tid < nb ? beam[tid] : 0, 1, v);
-        if (tid < nb) n_updates++;
+        const bool mine = tid < EMAX && a_slot[tid] >= 0 && a_inbeam[tid];
+        update_all(mine, tid, 1, v);
+        if (mine) n_updates++;
         ++v; ++nsteps;
         continue;
       }
@@ -790,41 +853,34 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws,
       else if (u < ecs) {
         const int nb = sh[SH_NB];
         if (nb < W && tid == 0) sh[SH_STATUS] |= POB_ST_SHORT_BEAM_SKIP;
-        update_all(tid < nb, tid < nb ? beam[tid] : 0, 0, u);
-        if (tid < nb) n_updates++;
+        const bool mine = tid < EMAX && a_slot[tid] >= 0 && a_inbeam[tid];
+        update_all(mine, tid, 0, u);
+        if (mine) n_updates++;
         ++u; ++nsteps;
         continue;
       }
       if ((!rset || !cset) && tid == 0) sh[SH_STATUS] |= POB_ST_UNSET_BAND;
       row_end = min(row_end, V); col_end = min(col_end, U);
-      if (!have_E) { build_expanded(item, false); have_E = true; }
-      const int nE = sh[SH_NE];
+      if (!have_E) { expand_and_retire(-1, -1); have_E = true; }
       int t0[2] = {col_start, row_start}, t1[2] = {col_end, row_end};
-      sweep(nE, 3, t0, t1, false, n_updates);
-      if (tid < nE && act[tid]) {
-        score[tid] = smax[tid * 2] + smax[tid * 2 + 1];  // max_probability_sym() (PrefixTree.h:111, :397)
-        eorder[tid] = hdr[E[tid]].order;
-      }
-      __syncthreads();
-      save_old(nE);
-      prune(nE);
+      sweep(3, t0, t1, n_updates);
+      prune();
       dbg_record(G, nsteps);
-      build_expanded(item, false);  // next step's expansion, done eagerly so retirement knows who stays
-      retire_and_reclaim(nE, u, v);  // later reads are at t-1 >= u (read 0) and >= v (read 1)
+      expand_and_retire(u, v);  // later reads are at t-1 >= u (read 0) and >= v (read 1)
       ++u; ++v; ++nsteps;
     }
   }
   __syncthreads();
   if (tid == 0) {
-    const NodeHdr& top = hdr[beam[0]];
+    const int a = beam[0];
     double sc;
-    if (mode == MODE_1D) sc = wptr(beam[0], 0, top.hi[0] - 1)->prob;
-    else if (mode == MODE_ROW) sc = wptr(beam[0], 0, top.hi[0] - 1)->prob + top.maxp[1];
-    else sc = top.maxp[0] + top.maxp[1];
+    if (mode == MODE_1D) sc = a_last0[a];
+    else if (mode == MODE_ROW) sc = a_last0[a] + a_maxp[2 * a + 1];
+    else sc = a_maxp[2 * a] + a_maxp[2 * a + 1];
     G.out_score[item] = sc;
-    if (top.tid >= 0) { otop[0] = top.tid; otop[1] = -1; }
-    else { otop[0] = top.parent_tid; otop[1] = top.last; }
-    otop[2] = top.depth;
+    if (a_tid[a] >= 0) { otop[0] = a_tid[a]; otop[1] = -1; }
+    else { otop[0] = a_ptid[a]; otop[1] = a_last[a]; }
+    otop[2] = a_depth[a];
     otop[3] = sh[SH_STATUS];
   }
   // per-item counters
@@ -898,8 +954,9 @@ size_t ws_bytes(int model, int NP, int CAP0, int CAP1, int RQ, int Umax, int Vma
 }
 
 size_t smem_bytes(int W, int NP, int EMAX) {
-  size_t b = 512 + sizeof(double2) * 2 * EMAX * 2 + 8 * EMAX + 16 * EMAX + 4 * EMAX * 5 + 4 * ((W + 3) & ~3) + 4 * 32 +
-             2 * (size_t)NP + 2 * ((EMAX + 15) & ~15);
+  size_t b = 1024 + sizeof(double2) * 2 * EMAX * 2 + 16 * EMAX + 16 * EMAX + 8 * EMAX  // pub, key, maxp, last0
+             + 4 * EMAX * 8 + 32 * EMAX + 32 * EMAX                                      // ints, kids, lo/hi/plo/phi
+             + 4 * EMAX * 4 + 4 * ((W + 3) & ~3) + 4 * 32 + 2 * (size_t)NP + 5 * ((EMAX + 15) & ~15);
   return pob_align_up(b, 16);
 }
 
@@ -919,7 +976,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
                     int max_span1, int Umax, int Vmax, const int64_t* trace_off, uint32_t* trace, int32_t* top,
                     const int64_t* out_off, uint8_t* out_seq, int32_t* out_len, double* out_score,
                     int32_t* out_status) {
-  if (n_items <= 0) return POB_OK;
+  if (n_total <= 0) return POB_OK;
   if (W < 4 || W > 100) return POB_EUNSUPPORTED;
   if (r1.n_states != 5 || (r2 && r2->n_states != 5)) return POB_EUNSUPPORTED;
   BeamParams P;
@@ -937,14 +994,12 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
     long want = 64L * W;
     const long by_span = 3L * W * (span + 8) + 16L * W;
     if (by_span > want) want = by_span;
-    if (want > 65536) want = 65536;
+    if (want > 32768) want = 32768;
     P.NP = pow2_at_least((int)want);
     if (P.NP < 1024) P.NP = 1024;
   }
   if (const char* e = getenv("POB_DEBUG_NP")) P.NP = atoi(e);
   if (const char* e = getenv("POB_DEBUG_NORECLAIM")) P.dbg_noreclaim = atoi(e);
-  P.dbg_step = -1000;
-  if (const char* e = getenv("POB_DEBUG_STEP")) P.dbg_step = atoi(e);
   if (getenv("POB_DEBUG_TRACE")) {
     static double* dbg = nullptr;
     if (!dbg) cudaMalloc(&dbg, 200000 * sizeof(double));
@@ -973,8 +1028,8 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   else if (threads <= 512) { kern = ctc ? beam_kernel<M0, 512, 1> : beam_kernel<M1, 512, 1>; }
   else { kern = ctc ? beam_kernel<M0, 1024, 1> : beam_kernel<M1, 1024, 1>; }
   POB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // leave most of the unified L1/shared array to L1 (node headers and windows are served from it) but make
-  // sure the shared-memory carve-out does not cap residency
+  // leave most of the unified L1/shared array to L1 (window entries are served from it) but make sure the
+  // shared-memory carve-out does not cap residency
   {
     int want_blocks = 2048 / threads;
     if (want_blocks > 12) want_blocks = 12;
@@ -988,6 +1043,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   const size_t stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, Umax, Vmax);
   int grid = per_sm * ctx->sm_count;
   if (grid > n_items) grid = n_items;
+  if (grid < 1) grid = 1;
   // keep the workspace within a sane share of HBM
   const size_t budget = (size_t)96 << 30;
   while (grid > 1 && (size_t)grid * stride > budget) grid = grid * 3 / 4;
@@ -1001,7 +1057,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   P.work_counter = counter;
   P.counters = ctx->d_counters;
   P.trace = trace; P.trace_off = trace_off; P.out_top = top; P.out_score = out_score;
-  {
+  if (n_items > 0) {
     pob_prof_scope ps(ctx, mode == MODE_1D ? POB_K_BEAM_1D : POB_K_BEAM_2D);
     kern<<<grid, threads, smem, ctx->stream>>>(P);
   }
