@@ -256,7 +256,7 @@ struct Engine {
   }
 
   // all threads call this; `mine` selects the threads that own an active slot this phase
-  __device__ double update_all(bool mine, int a, int r, int t) {
+  __device__ __noinline__ double update_all(bool mine, int a, int r, int t) {
     UpdIn in;
     double p = 0;
     deferred_finalize();
@@ -270,9 +270,9 @@ struct Engine {
   // ---- time-major band sweep over the expanded beam (BeamSearch.h:361-375, :146-156) ----------------
   // reads_mask bit r: read r swept over [t0[r], t1[r]).  Resets max_prob of the swept reads, writes the
   // ranking keys.  Thread (2a + r) owns (active slot a, read r).
-  __device__ void sweep(int reads_mask, const int* t0, const int* t1, unsigned long long& n_updates) {
+  __device__ __noinline__ void sweep(int reads_mask, int s0, int e0, int s1, int e1, unsigned long long& n_updates) {
     const int tid = threadIdx.x;
-    const int len0 = (reads_mask & 1) ? t1[0] - t0[0] : 0, len1 = (reads_mask & 2) ? t1[1] - t0[1] : 0;
+    const int len0 = (reads_mask & 1) ? e0 - s0 : 0, len1 = (reads_mask & 2) ? e1 - s1 : 0;
     const int maxlen = max(len0, len1);
     const int a = tid >> 1, r = tid & 1;
     const bool used = a < EMAX && a_slot[a] >= 0;
@@ -294,7 +294,7 @@ struct Engine {
       const int slot = a_slot[a];
       const int last = a_last[a];
       lo = a_lo[2 * a + r]; hi = a_hi[2 * a + r];
-      ts = t0[r]; te = t1[r];
+      ts = r ? s1 : s0; te = r ? e1 : e0;
       wmask = mask[r];
       wb = wbase(slot, r);
       {
@@ -400,7 +400,7 @@ struct Engine {
 
   // ---- Beam::prune (Beam.h:93-108): rank by score desc, exact ties by creation order ----------
   // one barrier at the end; also clears the per-step flags
-  __device__ void prune() {
+  __device__ __noinline__ void prune() {
     const int tid = threadIdx.x;
     const bool two = (int)blockDim.x >= 2 * EMAX;
     const int a = two ? (tid >> 1) : tid;
@@ -451,10 +451,10 @@ struct Engine {
   }
 
   // fill an active slot for a node that did not exist (fresh) or comes back from retirement (revive)
-  __device__ void activate_fresh(int a, int slot, uint32_t order, int pa, int last) {
+  __device__ void activate_fresh(int a, int slot, uint32_t order, int pa, int last, int parent_tid) {
     NodeHdr n;
     n.order = order; n.state = 0; n.parent_slot = a_slot[pa]; n.parent_order = a_order[pa];
-    n.parent_tid = a_tid[pa]; n.tid = -1; n.depth = a_depth[pa] + 1; n.last = last;
+    n.parent_tid = parent_tid; n.tid = -1; n.depth = a_depth[pa] + 1; n.last = last;
     for (int q = 0; q < 4; ++q) { n.kid_slot[q] = -1; n.kid_order[q] = 0; }
     n.lo[0] = n.lo[1] = 0; n.hi[0] = n.hi[1] = 0; n.maxp[0] = n.maxp[1] = ninf(); n.pad[0] = n.pad[1] = 0;
     hdr[slot] = n;
@@ -493,30 +493,28 @@ struct Engine {
 
   // ---- expansion of the new beam + retirement + reclamation: three phases, three barriers ----------
   // dead0/dead1: every later read of read r is at an index >= dead_r.  The pool's free slots form a FIFO ring
-  // (pops at SH_FQH, pushes at SH_FQT), so recycling and allocation can share a phase.
-  __device__ void expand_and_retire(int dead0, int dead1) {
+  // (pops at SH_FQH, pushes at SH_FQT), so recycling and allocation can share a phase.  Thread 4b+c owns child
+  // c of beam[b].
+  __device__ __noinline__ void expand_and_retire(int dead0, int dead1) {
     const int tid = threadIdx.x;
     const int nb = sh[SH_NB];
-    // -- phase X1: beam threads classify their children.  A retired child that comes back is marked active
-    //    right away so that the queue inspection of the next phase sees its queue entry as stale.
-    int kinds = 0, nfresh = 0, nact = 0, first = 0, a = -1;
-    if (tid < nb) {
-      a = beam[tid];
-      a_needed[a] = 1;
-      first = a_tid[a] < 0;
-      for (int c = 0; c < 4; ++c) {
-        int kind = KID_FRESH;
-        const int ks = a_kid[4 * a + c];
-        if (ks >= 0) {
-          const int ka = slot2e[ks];
-          if (ka >= 0 && a_order[ka] == a_kido[4 * a + c]) { kind = KID_ACTIVE; a_needed[ka] = 1; }
-          else if (hdr[ks].order == a_kido[4 * a + c]) { kind = KID_REVIVE; hdr[ks].state = 0; }
-        }
-        kinds |= kind << (2 * c);
-        nfresh += kind == KID_FRESH;
-        nact += kind != KID_ACTIVE;
+    uint8_t* kindv = reinterpret_cast<uint8_t*>(tmpb);  // [4*nb] child classification
+    // -- phase X1: classify the children of the beam.  A retired child that comes back is marked active right
+    //    away so that the queue inspection of the next phase sees its queue entry as stale.
+    const int xb = tid >> 2, xc = tid & 3;
+    const bool xmine = tid < 4 * nb;
+    int a = -1, kind = KID_ACTIVE;
+    if (xmine) {
+      a = beam[xb];
+      kind = KID_FRESH;
+      const int ks = a_kid[4 * a + xc];
+      if (ks >= 0) {
+        const int ka = slot2e[ks];
+        if (ka >= 0 && a_order[ka] == a_kido[4 * a + xc]) { kind = KID_ACTIVE; a_needed[ka] = 1; }
+        else if (hdr[ks].order == a_kido[4 * a + xc]) { kind = KID_REVIVE; hdr[ks].state = 0; }
       }
-      tmpa[tid] = nfresh; tmpc[tid] = first;
+      kindv[tid] = (uint8_t)kind;
+      if (xc == 0) { a_needed[a] = 1; tmpc[xb] = a_tid[a] < 0; }
     }
     const int head = sh[SH_RQH], tail = sh[SH_RQT];
     const int navail = noreclaim ? 0 : min(tail - head, (int)blockDim.x);
@@ -526,7 +524,8 @@ struct Engine {
     const bool force = (fq_tail - fq_head) < 8 * W + 16 && navail > 0;
     __syncthreads();
     // -- phase X2: retire what the next expanded beam does not contain, freeze orphaned children, inspect the
-    //    retire queue (entries queued in earlier steps only: a node retired now is still readable)
+    //    retire queue (entries queued in earlier steps only: a node retired now is still readable); the child
+    //    threads compute their deterministic creation-order / trace-id offsets
     if (tid < EMAX && a_slot[tid] >= 0) {
       if (!a_needed[tid]) retire(tid);
       else if (a_pstat[tid] == PS_INE && !a_needed[a_par[tid]]) {
@@ -554,9 +553,15 @@ struct Engine {
       }
       if (st == 4) atomicMin(&sh[SH_FIRSTALIVE], tid);
     }
+    int obase = 0, fbase = 0, first = 0;
+    if (xmine) {
+      for (int j = 0; j < tid; ++j) obase += kindv[j] == KID_FRESH;  // fresh children created before mine
+      for (int j = 0; j < xb; ++j) fbase += tmpc[j];                   // beam nodes first expanded before mine
+      first = tmpc[xb];
+    }
     __syncthreads();
     // -- phase X3: consume the inspected queue entries (strictly from the head, up to the first live one);
-    //    beam threads create / revive the missing children
+    //    child threads create / revive the missing children
     {
       int fa = min(sh[SH_FIRSTALIVE], navail);
       if (force) { fa = navail; if (tid == 0) sh[SH_STATUS] |= POB_ST_POOL_OVERFLOW; }
@@ -571,38 +576,37 @@ struct Engine {
       }
       if (tid == 0) sh[SH_RQH] = head + fa;
     }
-    if (tid < nb) {
-      int obase = 0, fbase = 0;
-      for (int b = 0; b < tid; ++b) { obase += tmpa[b]; fbase += tmpc[b]; }
-      if (tid == nb - 1) { sh[SH_TOTALLOC] = obase + nfresh; sh[SH_TOTFIRST] = fbase + first; }
-      if (first) {
-        a_tid[a] = sh[SH_TID] + fbase;
-        trace[a_tid[a]] = ((uint32_t)a_ptid[a] << 2) | (uint32_t)a_last[a];
-      }
-      const int abase = (nact > 0) ? atomicSub(&sh[SH_AFREE], nact) : 0;   // active slots [abase-nact, abase)
-      const int pbase = (nfresh > 0) ? atomicAdd(&sh[SH_FQH], nfresh) : 0;  // ring entries [pbase, pbase+nfresh)
-      if ((nfresh > 0 && pbase + nfresh > fq_tail) || (nact > 0 && abase - nact < 0)) {
-        // cannot happen while the reclamation keeps its margin; refuse to corrupt memory if it does
-        atomicOr(&sh[SH_STATUS], POB_ST_POOL_OVERFLOW);
-        if (nact > 0) atomicAdd(&sh[SH_AFREE], nact);
-        if (nfresh > 0) atomicSub(&sh[SH_FQH], nfresh);
-      } else {
-        int k = 0, ai = 0, pi = 0;
-        for (int c = 0; c < 4; ++c) {
-          const int kind = (kinds >> (2 * c)) & 3;
-          if (kind == KID_ACTIVE) continue;
-          const int na = a_free[abase - 1 - ai]; ++ai;
+    if (xmine) {
+      const int my_tid = first ? sh[SH_TID] + fbase : a_tid[a];  // trace id of the beam node (my parent)
+      if (tid == 4 * nb - 1) { sh[SH_TOTALLOC] = obase + (kind == KID_FRESH); sh[SH_TOTFIRST] = fbase + first; }
+      if (kind != KID_ACTIVE) {
+        const int ai = atomicSub(&sh[SH_AFREE], 1) - 1;
+        int pi = -1;
+        if (kind == KID_FRESH) pi = atomicAdd(&sh[SH_FQH], 1);
+        if (ai < 0 || (kind == KID_FRESH && pi >= fq_tail)) {
+          // cannot happen while the reclamation keeps its margin; refuse to corrupt memory if it does
+          atomicOr(&sh[SH_STATUS], POB_ST_POOL_OVERFLOW);
+          atomicAdd(&sh[SH_AFREE], 1);
+          if (kind == KID_FRESH) atomicSub(&sh[SH_FQH], 1);
+        } else {
+          const int na = a_free[ai];
           if (kind == KID_FRESH) {
-            const int slot = freelist[(pbase + pi) % NP]; ++pi;
-            const uint32_t order = (uint32_t)(sh[SH_ORDER] + obase + k); ++k;
-            activate_fresh(na, slot, order, a, c);
-            a_kid[4 * a + c] = slot; a_kido[4 * a + c] = order;
+            const int slot = freelist[pi % NP];
+            const uint32_t order = (uint32_t)(sh[SH_ORDER] + obase);
+            activate_fresh(na, slot, order, a, xc, my_tid);
+            a_kid[4 * a + xc] = slot; a_kido[4 * a + xc] = order;
           } else {
-            activate_revived(na, a_kid[4 * a + c], a);
+            activate_revived(na, a_kid[4 * a + xc], a);
           }
+          atomicAdd(&sh[SH_NUSED], 1);
         }
-        if (nact > 0) atomicAdd(&sh[SH_NUSED], nact);
       }
+    }
+    __syncthreads();
+    // the first expansion of a beam node gives it its trace id (after every sibling has read the old value)
+    if (xmine && xc == 0 && first) {
+      a_tid[a] = sh[SH_TID] + fbase;
+      trace[a_tid[a]] = ((uint32_t)a_ptid[a] << 2) | (uint32_t)a_last[a];
     }
     __syncthreads();
   }
@@ -610,7 +614,7 @@ struct Engine {
   // ROW traversal while the beam is shorter than W (first row): the reference walks b < beam_width over a
   // list that grows as children are pushed (BeamSearch.h:132-144), i.e. a breadth-first closure.  Sequential,
   // runs once per item.
-  __device__ void expand_bfs() {
+  __device__ __noinline__ void expand_bfs() {
     if (threadIdx.x == 0) {
       int* list = tmpa;  // EMAX >= 4 + 4W entries
       int n = 0;
@@ -632,7 +636,7 @@ struct Engine {
             else {
               const int slot = freelist[(sh[SH_FQH]++) % NP];
               const uint32_t order = (uint32_t)sh[SH_ORDER]++;
-              activate_fresh(ka, slot, order, a, c);
+              activate_fresh(ka, slot, order, a, c, a_tid[a]);
               a_kid[4 * a + c] = slot; a_kido[4 * a + c] = order;
             }
             sh[SH_NUSED]++;
@@ -822,8 +826,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws,
         update_all(mine, tid, 0, u);
         if (mine) n_updates++;
       }
-      int t0[2] = {u, rs}, t1[2] = {u + 1, re};
-      sweep(2, t0, t1, n_updates);
+      sweep(2, u, u + 1, rs, re, n_updates);
       prune();
       dbg_record(G, nsteps);
       // read 0 is next read at index u; read 1 at >= (smallest band start of any later row) - 1
@@ -862,8 +865,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws,
       if ((!rset || !cset) && tid == 0) sh[SH_STATUS] |= POB_ST_UNSET_BAND;
       row_end = min(row_end, V); col_end = min(col_end, U);
       if (!have_E) { expand_and_retire(-1, -1); have_E = true; }
-      int t0[2] = {col_start, row_start}, t1[2] = {col_end, row_end};
-      sweep(3, t0, t1, n_updates);
+      sweep(3, col_start, col_end, row_start, row_end, n_updates);
       prune();
       dbg_record(G, nsteps);
       expand_and_retire(u, v);  // later reads are at t-1 >= u (read 0) and >= v (read 1)
