@@ -31,6 +31,9 @@
 #include "common.cuh"
 #include "launch.cuh"
 
+#pragma nv_diag_suppress 177
+#pragma nv_diag_suppress 550
+
 namespace {
 
 enum { MODE_1D = 0, MODE_ROW = 1, MODE_ROWCOL = 2 };
@@ -126,14 +129,13 @@ __device__ __forceinline__ ReadView make_view(const pob_reads& r, int item) {
 enum { SH_NB = 0, SH_NUSED, SH_FQH, SH_FQT, SH_AFREE, SH_ORDER, SH_TID, SH_STAMP, SH_RQH, SH_RQT, SH_STATUS, SH_FIRSTALIVE,
        SH_TOTALLOC, SH_TOTFIRST, SH_DMIN, SH_COUNT };
 
-// The engine object lives in shared memory (one per CTA).
-template <int MODEL>
-struct Engine {
-  typedef Entry<MODEL> Ent;
+// Per-CTA engine state.  Scalars and global-memory views live in a static __shared__ struct; the per-active-slot
+// arrays live in dynamic shared memory at offsets that depend only on EMAX / W / NP, so every access compiles
+// to LDS/STS (a pointer loaded from memory would be a generic pointer and cost a second, slower load).
+struct EngState {
   int W, NP, RQ, EMAX, mode, noreclaim;
-  // global workspace views
   NodeHdr* hdr;
-  Ent* win[2];
+  char* win[2];
   int32_t* freelist;
   int2* retq;
   double* cum[2];   // ctc: blank prefix sums of each read (root node values, PrefixTree.h:508-514)
@@ -142,50 +144,79 @@ struct Engine {
   int cap[2], mask[2];
   ReadView rv[2];
   uint32_t* trace;
-  // shared-memory state of the active slots (index a in [0, EMAX)); a_slot[a] < 0 = unused
-  int16_t* slot2e;     // [NP] pool slot -> active slot or -1
-  int32_t* a_slot;     // pool slot
-  uint32_t* a_order;
-  int32_t* a_par;      // active slot of the parent when a_pstat == PS_INE
-  int32_t* a_pslot;    // pool slot of the parent (window base when frozen)
-  uint32_t* a_porder;
-  int32_t* a_depth;
-  int32_t* a_tid;
-  int32_t* a_ptid;
-  int32_t* a_kid;      // [EMAX*4] pool slots of the children, -1 = never created
-  uint32_t* a_kido;    // [EMAX*4]
-  int32_t* a_lo;       // [EMAX*2]
-  int32_t* a_hi;
-  int32_t* a_plo;      // [EMAX*2] window bounds of a frozen parent
-  int32_t* a_phi;
-  double* a_maxp;      // [EMAX*2]
-  double* a_last0;     // [EMAX] value of read 0 at its last written t
-  double2* key;        // [EMAX] (ranking score, creation order)
-  double2* pub;        // [2][EMAX][2] (prob, gap) exchanged between parents and children in a sweep
-  uint8_t* a_last;
-  uint8_t* a_pstat;
-  uint8_t* a_same;     // parent's last base == own last base (merge-repeats reads the parent's gap value)
-  uint8_t* a_inbeam;
-  uint8_t* a_needed;
-  int32_t* beam;       // [W] active slots in rank order
-  int32_t* a_free;     // [EMAX] stack of unused active slots
-  int32_t* tmpa;       // [EMAX] scratch
-  int32_t* tmpb;
-  int32_t* tmpc;
-  int32_t* sh;         // scalars SH_*
+};
+__shared__ EngState g_es;
+extern __shared__ __align__(16) char pob_smem[];
 
-  __device__ __forceinline__ Ent* wbase(int slot, int r) const { return win[r] + (size_t)slot * cap[r]; }
+// Shared-memory arrays of the active slots (index a in [0, EMAX)); a_slot[a] < 0 = unused.
+//   slot2e  [NP]      pool slot -> active slot or -1
+//   a_slot            pool slot                 a_order / a_porder   creation order of the node / its parent
+//   a_par             active slot of the parent when a_pstat == PS_INE
+//   a_pslot           pool slot of the parent (window base when frozen)
+//   a_kid/a_kido [4]  pool slots / orders of the children, -1 = never created
+//   a_lo/a_hi [2]     window bounds per read;   a_plo/a_phi [2] bounds of a frozen parent
+//   a_maxp [2]        max_prob[] of the reference nodes;  a_last0 value of read 0 at its last written t
+//   key               (ranking score, creation order);   pub [2][EMAX][2] (prob, gap) parent -> child exchange
+//   a_same            parent's last base == own last base (merge-repeats reads the parent's gap value)
+//   beam [W]          active slots in rank order;  a_free stack of unused active slots;  sh scalars SH_*
+#define POB_VIEWS                                                                                   \
+  const int EMAX = g_es.EMAX, W = g_es.W, NP = g_es.NP, RQ = g_es.RQ, mode = g_es.mode;             \
+  char* const sm_ = pob_smem;                                                                       \
+  double2* const pub = (double2*)sm_;                                                               \
+  double2* const key = (double2*)(sm_ + 64 * EMAX);                                                 \
+  double* const a_maxp = (double*)(sm_ + 80 * EMAX);                                                \
+  double* const a_last0 = (double*)(sm_ + 96 * EMAX);                                               \
+  int32_t* const a_slot = (int32_t*)(sm_ + 104 * EMAX);                                             \
+  uint32_t* const a_order = (uint32_t*)(sm_ + 108 * EMAX);                                          \
+  int32_t* const a_par = (int32_t*)(sm_ + 112 * EMAX);                                              \
+  int32_t* const a_pslot = (int32_t*)(sm_ + 116 * EMAX);                                            \
+  uint32_t* const a_porder = (uint32_t*)(sm_ + 120 * EMAX);                                         \
+  int32_t* const a_depth = (int32_t*)(sm_ + 124 * EMAX);                                            \
+  int32_t* const a_tid = (int32_t*)(sm_ + 128 * EMAX);                                              \
+  int32_t* const a_ptid = (int32_t*)(sm_ + 132 * EMAX);                                             \
+  int32_t* const a_kid = (int32_t*)(sm_ + 136 * EMAX);                                              \
+  uint32_t* const a_kido = (uint32_t*)(sm_ + 152 * EMAX);                                           \
+  int32_t* const a_lo = (int32_t*)(sm_ + 168 * EMAX);                                               \
+  int32_t* const a_hi = (int32_t*)(sm_ + 176 * EMAX);                                               \
+  int32_t* const a_plo = (int32_t*)(sm_ + 184 * EMAX);                                              \
+  int32_t* const a_phi = (int32_t*)(sm_ + 192 * EMAX);                                              \
+  int32_t* const a_free = (int32_t*)(sm_ + 200 * EMAX);                                             \
+  int32_t* const tmpa = (int32_t*)(sm_ + 204 * EMAX);                                               \
+  int32_t* const tmpb = (int32_t*)(sm_ + 208 * EMAX);                                               \
+  int32_t* const tmpc = (int32_t*)(sm_ + 212 * EMAX);                                               \
+  int32_t* const beam = (int32_t*)(sm_ + 216 * EMAX);                                               \
+  int32_t* const sh = beam + ((W + 3) & ~3);                                                        \
+  int16_t* const slot2e = (int16_t*)(sh + 32);                                                      \
+  uint8_t* const a_last = (uint8_t*)(slot2e + NP);                                                  \
+  const int eb_ = (EMAX + 15) & ~15;                                                                \
+  uint8_t* const a_pstat = a_last + eb_;                                                            \
+  uint8_t* const a_same = a_pstat + eb_;                                                            \
+  uint8_t* const a_inbeam = a_same + eb_;                                                           \
+  uint8_t* const a_needed = a_inbeam + eb_;                                                         \
+  NodeHdr* const hdr = g_es.hdr;                                                                    \
+  int32_t* const freelist = g_es.freelist;                                                          \
+  int2* const retq = g_es.retq;                                                                     \
+  uint32_t* const trace = g_es.trace;
+
+template <int MODEL>
+struct Engine {
+  typedef Entry<MODEL> Ent;
+
+  __device__ __forceinline__ Ent* wbase(int slot, int r) const {
+    return reinterpret_cast<Ent*>(g_es.win[r]) + (size_t)slot * g_es.cap[r];
+  }
 
   // value of the root at time t (parent of depth-1 nodes)
   __device__ __forceinline__ double root_prob(int r, int t) const {
     if (t == -1) return 0.0;
-    if (MODEL == POB_MODEL_CTC) return (t >= 0 && t < rv[r].T) ? cum[r][t] : ninf();
+    if (MODEL == POB_MODEL_CTC) return (t >= 0 && t < g_es.rv[r].T) ? g_es.cum[r][t] : ninf();
     return ninf();
   }
 
   // bookkeeping that must not race with the phase that produced it: run by thread 0 at the start of a
   // compute phase (separated by barriers from every reader)
   __device__ __forceinline__ void deferred_finalize() {
+    POB_VIEWS
     if (threadIdx.x == 0) {
       sh[SH_ORDER] += sh[SH_TOTALLOC]; sh[SH_TOTALLOC] = 0;
       sh[SH_TID] += sh[SH_TOTFIRST]; sh[SH_TOTFIRST] = 0;
@@ -203,16 +234,17 @@ struct Engine {
   };
 
   __device__ __forceinline__ void update_gather(int a, int r, int t, UpdIn& in) const {
+    POB_VIEWS
     const int slot = a_slot[a];
     const int last = a_last[a];
     in.lo = a_lo[2 * a + r]; in.hi = a_hi[2 * a + r];
     const bool self_ok = (t - 1 >= in.lo && t - 1 < in.hi);
-    const Ent* se = wbase(slot, r) + (t & mask[r]);
+    const Ent* se = wbase(slot, r) + (t & g_es.mask[r]);
     in.p_prev = self_ok ? se->prob : ninf();
     in.ng_prev = ninf();
     if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.ng_prev = self_ok ? se->nogap : ninf();
-    in.ylast = rv[r].at(t, rv[r].pcol(last));
-    in.yblank = rv[r].at(t, rv[r].cblank);
+    in.ylast = g_es.rv[r].at(t, g_es.rv[r].pcol(last));
+    in.yblank = g_es.rv[r].at(t, g_es.rv[r].cblank);
     const int ps = a_pstat[a];
     if (ps == PS_ROOT) {
       in.pv = root_prob(r, t - 1);
@@ -223,7 +255,7 @@ struct Engine {
       if (ps == PS_INE) { const int pa = a_par[a]; plo = a_lo[2 * pa + r]; phi = a_hi[2 * pa + r]; }
       else { plo = a_plo[2 * a + r]; phi = a_phi[2 * a + r]; }
       if (t - 1 >= plo && t - 1 < phi) {
-        const Ent* pe = wbase(a_pslot[a], r) + (t & mask[r]);
+        const Ent* pe = wbase(a_pslot[a], r) + (t & g_es.mask[r]);
         if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.pv = a_same[a] ? pe->gap : pe->prob;
         else in.pv = pe->prob;
       } else {
@@ -233,6 +265,7 @@ struct Engine {
   }
 
   __device__ __forceinline__ double update_commit(int a, int r, int t, const UpdIn& in) {
+    POB_VIEWS
     Ent out;
     double prob;
     if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
@@ -244,11 +277,11 @@ struct Engine {
       prob = lae(in.pv + in.ylast, in.p_prev + in.yblank);
       out.prob = prob;
     }
-    *(wbase(a_slot[a], r) + ((t + 1) & mask[r])) = out;
+    *(wbase(a_slot[a], r) + ((t + 1) & g_es.mask[r])) = out;
     int lo = in.lo, hi = in.hi;
     if (t >= hi) { if (t > hi) lo = t; hi = t + 1; }
     else if (t < lo) { lo = t; hi = t + 1; }
-    if (hi - lo > cap[r]) lo = hi - cap[r];
+    if (hi - lo > g_es.cap[r]) lo = hi - g_es.cap[r];
     a_lo[2 * a + r] = lo; a_hi[2 * a + r] = hi;
     if (prob > a_maxp[2 * a + r]) a_maxp[2 * a + r] = prob;
     if (r == 0) a_last0[a] = prob;
@@ -271,6 +304,7 @@ struct Engine {
   // reads_mask bit r: read r swept over [t0[r], t1[r]).  Resets max_prob of the swept reads, writes the
   // ranking keys.  Thread (2a + r) owns (active slot a, read r).
   __device__ __noinline__ void sweep(int reads_mask, int s0, int e0, int s1, int e1, unsigned long long& n_updates) {
+    POB_VIEWS
     const int tid = threadIdx.x;
     const int len0 = (reads_mask & 1) ? e0 - s0 : 0, len1 = (reads_mask & 2) ? e1 - s1 : 0;
     const int maxlen = max(len0, len1);
@@ -295,10 +329,10 @@ struct Engine {
       const int last = a_last[a];
       lo = a_lo[2 * a + r]; hi = a_hi[2 * a + r];
       ts = r ? s1 : s0; te = r ? e1 : e0;
-      wmask = mask[r];
+      wmask = g_es.mask[r];
       wb = wbase(slot, r);
       {
-        const ReadView v = rv[r];
+        const ReadView v = g_es.rv[r];
         f64 = v.f64;
         const long es = f64 ? 8 : 4;
         const long rowb = (long)v.S * es;
@@ -378,7 +412,7 @@ struct Engine {
       if (te > ts) {
         if (ts > hi || ts < lo) { lo = ts; hi = te; }  // window bookkeeping for the contiguous write [ts, te)
         else hi = max(hi, te);
-        if (hi - lo > cap[r]) lo = hi - cap[r];
+        if (hi - lo > g_es.cap[r]) lo = hi - g_es.cap[r];
         a_lo[2 * a + r] = lo; a_hi[2 * a + r] = hi;
         a_maxp[2 * a + r] = maxv;  // reset + max over the band
       } else {
@@ -401,6 +435,7 @@ struct Engine {
   // ---- Beam::prune (Beam.h:93-108): rank by score desc, exact ties by creation order ----------
   // one barrier at the end; also clears the per-step flags
   __device__ __noinline__ void prune() {
+    POB_VIEWS
     const int tid = threadIdx.x;
     const bool two = (int)blockDim.x >= 2 * EMAX;
     const int a = two ? (tid >> 1) : tid;
@@ -433,6 +468,7 @@ struct Engine {
 
   // ---- retire an active slot: write the header home, queue the node for reclamation ----
   __device__ void retire(int a) {
+    POB_VIEWS
     const int slot = a_slot[a];
     NodeHdr& h = hdr[slot];
     h.tid = a_tid[a];
@@ -452,6 +488,7 @@ struct Engine {
 
   // fill an active slot for a node that did not exist (fresh) or comes back from retirement (revive)
   __device__ void activate_fresh(int a, int slot, uint32_t order, int pa, int last, int parent_tid) {
+    POB_VIEWS
     NodeHdr n;
     n.order = order; n.state = 0; n.parent_slot = a_slot[pa]; n.parent_order = a_order[pa];
     n.parent_tid = parent_tid; n.tid = -1; n.depth = a_depth[pa] + 1; n.last = last;
@@ -470,6 +507,7 @@ struct Engine {
   }
 
   __device__ void activate_revived(int a, int slot, int pa) {
+    POB_VIEWS
     NodeHdr& h = hdr[slot];
     h.state = 0;
     a_slot[a] = slot; a_order[a] = h.order; a_par[a] = pa; a_pslot[a] = h.parent_slot; a_porder[a] = h.parent_order;
@@ -496,6 +534,7 @@ struct Engine {
   // (pops at SH_FQH, pushes at SH_FQT), so recycling and allocation can share a phase.  Thread 4b+c owns child
   // c of beam[b].
   __device__ __noinline__ void expand_and_retire(int dead0, int dead1) {
+    POB_VIEWS
     const int tid = threadIdx.x;
     const int nb = sh[SH_NB];
     uint8_t* kindv = reinterpret_cast<uint8_t*>(tmpb);  // [4*nb] child classification
@@ -517,7 +556,7 @@ struct Engine {
       if (xc == 0) { a_needed[a] = 1; tmpc[xb] = a_tid[a] < 0; }
     }
     const int head = sh[SH_RQH], tail = sh[SH_RQT];
-    const int navail = noreclaim ? 0 : min(tail - head, (int)blockDim.x);
+    const int navail = g_es.noreclaim ? 0 : min(tail - head, (int)blockDim.x);
     const int dmin = sh[SH_DMIN];
     const int fq_head = sh[SH_FQH], fq_tail = sh[SH_FQT];
     // pool pressure: recycle live retirees too (flagged; the reference never frees anything)
@@ -615,6 +654,7 @@ struct Engine {
   // list that grows as children are pushed (BeamSearch.h:132-144), i.e. a breadth-first closure.  Sequential,
   // runs once per item.
   __device__ __noinline__ void expand_bfs() {
+    POB_VIEWS
     if (threadIdx.x == 0) {
       int* list = tmpa;  // EMAX >= 4 + 4W entries
       int n = 0;
@@ -649,6 +689,7 @@ struct Engine {
   }
 
   __device__ void dbg_record(const BeamParams& G, long step) {
+    POB_VIEWS
     if (!G.dbg_trace) return;
     if (threadIdx.x == 0 && step < 50000) {
       double sum = 0;
@@ -661,64 +702,34 @@ struct Engine {
     }
   }
 
-  __device__ void run_item(const BeamParams& G, int item, char* ws, char* smem);
+  __device__ void run_item(const BeamParams& G, int item, char* ws);
 };
 
 template <int MODEL>
-__device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws, char* smem) {
+__device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws) {
   const int tid = threadIdx.x, NT = blockDim.x;
   unsigned long long n_updates = 0;
-  // ---- carve shared memory (the engine object itself sits at the front) and the global workspace
+  // ---- engine state of this item: scalars + views of the CTA's global workspace
   if (tid == 0) {
-    W = G.W; NP = G.NP; RQ = G.RQ; EMAX = G.EMAX; mode = G.mode; noreclaim = G.dbg_noreclaim;
-    char* p = smem + ((sizeof(Engine<MODEL>) + 15) & ~(size_t)15);
-    pub = (double2*)p; p += sizeof(double2) * 2 * EMAX * 2;
-    key = (double2*)p; p += sizeof(double2) * EMAX;
-    a_maxp = (double*)p; p += 8 * EMAX * 2;
-    a_last0 = (double*)p; p += 8 * EMAX;
-    a_slot = (int32_t*)p; p += 4 * EMAX;
-    a_order = (uint32_t*)p; p += 4 * EMAX;
-    a_par = (int32_t*)p; p += 4 * EMAX;
-    a_pslot = (int32_t*)p; p += 4 * EMAX;
-    a_porder = (uint32_t*)p; p += 4 * EMAX;
-    a_depth = (int32_t*)p; p += 4 * EMAX;
-    a_tid = (int32_t*)p; p += 4 * EMAX;
-    a_ptid = (int32_t*)p; p += 4 * EMAX;
-    a_kid = (int32_t*)p; p += 16 * EMAX;
-    a_kido = (uint32_t*)p; p += 16 * EMAX;
-    a_lo = (int32_t*)p; p += 8 * EMAX;
-    a_hi = (int32_t*)p; p += 8 * EMAX;
-    a_plo = (int32_t*)p; p += 8 * EMAX;
-    a_phi = (int32_t*)p; p += 8 * EMAX;
-    a_free = (int32_t*)p; p += 4 * EMAX;
-    tmpa = (int32_t*)p; p += 4 * EMAX;
-    tmpb = (int32_t*)p; p += 4 * EMAX;
-    tmpc = (int32_t*)p; p += 4 * EMAX;
-    beam = (int32_t*)p; p += 4 * ((W + 3) & ~3);
-    sh = (int32_t*)p; p += 4 * 32;
-    slot2e = (int16_t*)p; p += 2 * (size_t)NP;
-    const int eb = (EMAX + 15) & ~15;
-    a_last = (uint8_t*)p; p += eb;
-    a_pstat = (uint8_t*)p; p += eb;
-    a_same = (uint8_t*)p; p += eb;
-    a_inbeam = (uint8_t*)p; p += eb;
-    a_needed = (uint8_t*)p; p += eb;
-    cap[0] = G.CAP0; cap[1] = G.CAP1; mask[0] = G.CAP0 - 1; mask[1] = G.CAP1 - 1;
-    rv[0] = make_view(G.r[0], item);
-    if (mode != MODE_1D) rv[1] = make_view(G.r[1], item); else { rv[1] = rv[0]; rv[1].T = 0; }
+    g_es.W = G.W; g_es.NP = G.NP; g_es.RQ = G.RQ; g_es.EMAX = G.EMAX; g_es.mode = G.mode;
+    g_es.noreclaim = G.dbg_noreclaim;
+    g_es.cap[0] = G.CAP0; g_es.cap[1] = G.CAP1; g_es.mask[0] = G.CAP0 - 1; g_es.mask[1] = G.CAP1 - 1;
+    g_es.rv[0] = make_view(G.r[0], item);
+    if (G.mode != MODE_1D) g_es.rv[1] = make_view(G.r[1], item); else { g_es.rv[1] = g_es.rv[0]; g_es.rv[1].T = 0; }
     char* q = ws;
-    hdr = (NodeHdr*)q; q += sizeof(NodeHdr) * (size_t)NP;
-    win[0] = (Ent*)q; q += sizeof(Ent) * (size_t)NP * cap[0];
-    win[1] = (Ent*)q; q += sizeof(Ent) * (size_t)NP * cap[1];
-    freelist = (int32_t*)q; q += 4 * (size_t)NP;
-    retq = (int2*)q; q += 8 * (size_t)RQ;
-    cum[0] = (double*)q; q += 8 * (size_t)(MODEL == POB_MODEL_CTC ? rv[0].T : 0);
-    cum[1] = (double*)q; q += 8 * (size_t)(MODEL == POB_MODEL_CTC ? rv[1].T : 0);
-    sufmin = (int32_t*)q;
-    trace = G.trace + G.trace_off[item];
+    g_es.hdr = (NodeHdr*)q; q += sizeof(NodeHdr) * (size_t)G.NP;
+    g_es.win[0] = q; q += sizeof(Ent) * (size_t)G.NP * G.CAP0;
+    g_es.win[1] = q; q += sizeof(Ent) * (size_t)G.NP * G.CAP1;
+    g_es.freelist = (int32_t*)q; q += 4 * (size_t)G.NP;
+    g_es.retq = (int2*)q; q += 8 * (size_t)G.RQ;
+    g_es.cum[0] = (double*)q; q += 8 * (size_t)(MODEL == POB_MODEL_CTC ? g_es.rv[0].T : 0);
+    g_es.cum[1] = (double*)q; q += 8 * (size_t)(MODEL == POB_MODEL_CTC ? g_es.rv[1].T : 0);
+    g_es.sufmin = (int32_t*)q;
+    g_es.trace = G.trace + G.trace_off[item];
   }
   __syncthreads();
-  const int U = rv[0].T, V = rv[1].T;
+  POB_VIEWS
+  const int U = g_es.rv[0].T, V = g_es.rv[1].T;
   int32_t* otop = G.out_top + 4 * (size_t)item;
 
   // ---- init pool and active slots
@@ -738,9 +749,9 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws,
   }
   if (MODEL == POB_MODEL_CTC && tid < 2 && (tid == 0 || mode != MODE_1D)) {
     // PrefixTree.h:508-514: sequential running sum of the blank column
-    const ReadView& v = rv[tid];
+    const ReadView& v = g_es.rv[tid];
     double s = 0;
-    for (int t = 0; t < v.T; ++t) { s += v.at(t, v.cblank); cum[tid][t] = s; }
+    for (int t = 0; t < v.T; ++t) { s += v.at(t, v.cblank); g_es.cum[tid][t] = s; }
   }
   __syncthreads();
   if (U <= 0 || (mode != MODE_1D && V <= 0)) {
@@ -749,7 +760,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws,
     return;
   }
   // ---- seed: the 4 children of the root, updated at t = 0 (BeamSearch.h:24-30, :287-293)
-  const int nbase = rv[0].S - 1;
+  const int nbase = g_es.rv[0].S - 1;
   if (tid < nbase) {
     const int a = tid, slot = tid;  // the first pool slots and active slots go to the root's children
     NodeHdr n;
@@ -793,7 +804,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws,
         if (tid + d < 32) v = min(v, o);
       }
       v = min(v, carry);
-      if (i < U) sufmin[i] = v;
+      if (i < U) g_es.sufmin[i] = v;
       carry = __shfl_sync(0xffffffffu, v, 0);
     }
   }
@@ -830,7 +841,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws,
       prune();
       dbg_record(G, nsteps);
       // read 0 is next read at index u; read 1 at >= (smallest band start of any later row) - 1
-      const int nrs = (u + 1 < U) ? (env ? sufmin[u + 1] : 0) : 0x7ffffffe;
+      const int nrs = (u + 1 < U) ? (env ? g_es.sufmin[u + 1] : 0) : 0x7ffffffe;
       if (sh[SH_NB] < W) expand_bfs(); else expand_and_retire(u, nrs - 1);
       ++nsteps;
     }
@@ -894,10 +905,9 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws,
 
 template <int MODEL, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) beam_kernel(BeamParams P) {
-  extern __shared__ __align__(16) char smem[];
   __shared__ int s_item;
   char* ws = P.ws + (size_t)blockIdx.x * P.ws_stride;
-  Engine<MODEL>& eng = *reinterpret_cast<Engine<MODEL>*>(smem);
+  Engine<MODEL> eng;
   for (;;) {
     if (threadIdx.x == 0) s_item = atomicAdd(P.work_counter, 1);
     __syncthreads();
@@ -913,7 +923,7 @@ __global__ void __launch_bounds__(MAXT, MINB) beam_kernel(BeamParams P) {
       }
       continue;
     }
-    eng.run_item(P, item, ws, smem);
+    eng.run_item(P, item, ws);
   }
 }
 
@@ -956,9 +966,8 @@ size_t ws_bytes(int model, int NP, int CAP0, int CAP1, int RQ, int Umax, int Vma
 }
 
 size_t smem_bytes(int W, int NP, int EMAX) {
-  size_t b = 1024 + sizeof(double2) * 2 * EMAX * 2 + 16 * EMAX + 16 * EMAX + 8 * EMAX  // pub, key, maxp, last0
-             + 4 * EMAX * 8 + 32 * EMAX + 32 * EMAX                                      // ints, kids, lo/hi/plo/phi
-             + 4 * EMAX * 4 + 4 * ((W + 3) & ~3) + 4 * 32 + 2 * (size_t)NP + 5 * ((EMAX + 15) & ~15);
+  // must match POB_VIEWS
+  size_t b = 216 * (size_t)EMAX + 4 * ((W + 3) & ~3) + 4 * 32 + 2 * (size_t)NP + 5 * ((EMAX + 15) & ~15);
   return pob_align_up(b, 16);
 }
 
