@@ -76,7 +76,7 @@ struct BeamParams {
   const int32_t* order;     // item processing order or NULL
   const int32_t* skip;      // per item != 0 -> not searched
   int n_items, W, mode, NP, CAP0, CAP1, RQ, EMAX;
-  int dbg_noreclaim;
+  int dbg_noreclaim, dbg_noreuse;
   double* dbg_trace;        // optional: [step][2] = (top score, sum of beam scores) after each prune
   char* ws;                 // workspace, one stride per resident CTA
   size_t ws_stride;
@@ -127,7 +127,7 @@ __device__ __forceinline__ ReadView make_view(const pob_reads& r, int item) {
 }
 
 enum { SH_NB = 0, SH_NUSED, SH_FQH, SH_FQT, SH_AFREE, SH_ORDER, SH_TID, SH_STAMP, SH_RQH, SH_RQT, SH_STATUS, SH_FIRSTALIVE,
-       SH_TOTALLOC, SH_TOTFIRST, SH_DMIN, SH_COUNT };
+       SH_TOTALLOC, SH_TOTFIRST, SH_DMIN, SH_TB0, SH_TB1, SH_COUNT };
 
 // Per-CTA engine state.  Scalars and global-memory views live in a static __shared__ struct; the per-active-slot
 // arrays live in dynamic shared memory at offsets that depend only on EMAX / W / NP, so every access compiles
@@ -155,6 +155,7 @@ extern __shared__ __align__(16) char pob_smem[];
 //   a_pslot           pool slot of the parent (window base when frozen)
 //   a_kid/a_kido [4]  pool slots / orders of the children, -1 = never created
 //   a_lo/a_hi [2]     window bounds per read;   a_plo/a_phi [2] bounds of a frozen parent
+//   a_che [2]         clean end per read (see sweep)
 //   a_maxp [2]        max_prob[] of the reference nodes;  a_last0 value of read 0 at its last written t
 //   key               (ranking score, creation order);   pub [2][EMAX][2] (prob, gap) parent -> child exchange
 //   a_same            parent's last base == own last base (merge-repeats reads the parent's gap value)
@@ -184,7 +185,8 @@ extern __shared__ __align__(16) char pob_smem[];
   int32_t* const tmpa = (int32_t*)(sm_ + 204 * EMAX);                                               \
   int32_t* const tmpb = (int32_t*)(sm_ + 208 * EMAX);                                               \
   int32_t* const tmpc = (int32_t*)(sm_ + 212 * EMAX);                                               \
-  int32_t* const beam = (int32_t*)(sm_ + 216 * EMAX);                                               \
+  int32_t* const a_che = (int32_t*)(sm_ + 216 * EMAX);                                              \
+  int32_t* const beam = (int32_t*)(sm_ + 224 * EMAX);                                               \
   int32_t* const sh = beam + ((W + 3) & ~3);                                                        \
   int16_t* const slot2e = (int16_t*)(sh + 32);                                                      \
   uint8_t* const a_last = (uint8_t*)(slot2e + NP);                                                  \
@@ -283,6 +285,7 @@ struct Engine {
     else if (t < lo) { lo = t; hi = t + 1; }
     if (hi - lo > g_es.cap[r]) lo = hi - g_es.cap[r];
     a_lo[2 * a + r] = lo; a_hi[2 * a + r] = hi;
+    if (t >= a_che[2 * a + r]) a_che[2 * a + r] = t + 1;  // a single update extends (or restarts) the clean range
     if (prob > a_maxp[2 * a + r]) a_maxp[2 * a + r] = prob;
     if (r == 0) a_last0[a] = prob;
     return prob;
@@ -300,125 +303,258 @@ struct Engine {
     return p;
   }
 
-  // ---- time-major band sweep over the expanded beam (BeamSearch.h:361-375, :146-156) ----------------
-  // reads_mask bit r: read r swept over [t0[r], t1[r]).  Resets max_prob of the swept reads, writes the
-  // ranking keys.  Thread (2a + r) owns (active slot a, read r).
-  __device__ __noinline__ void sweep(int reads_mask, int s0, int e0, int s1, int e1, unsigned long long& n_updates) {
+  // value a child reads from its frozen parent for an update at time t (the parent's entry at t-1)
+  __device__ __forceinline__ double frozen_at(const Ent* pwb, int t, int wmask, int plo, int phi, bool same) const {
+    if (t - 1 < plo || t - 1 >= phi) return ninf();
+    const Ent* q = pwb + (t & wmask);
+    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) return same ? q->gap : q->prob;
+    else return q->prob;
+  }
+
+  // ---- band sweep over the expanded beam (BeamSearch.h:361-375, :146-156), incremental ----------------
+  // reads_mask bit r: read r swept over [s_r, e_r).  Thread (2a + r) owns (active slot a, read r).
+  //
+  // The reference recomputes every node over the whole band at every step.  Recomputing an entry whose
+  // inputs did not change reproduces the same value, so only the entries that can differ are computed:
+  //   * a_che[a][r] ("clean end"): entries [.., che) of the node's window were produced by the previous
+  //     sweep / single updates from inputs that are still current; cs = clamp(che, s, e) is where new work
+  //     starts (new and revived nodes: cs = s);
+  //   * phase A (no barrier): each item computes [cs, min(e, Tb)) on its own; all parent entries it reads
+  //     there are final because Tb = 1 + min over live-parent items of the parent's cs;
+  //   * phase B (one barrier per timestep): the time-major loop over [Tb, e) with parent values exchanged
+  //     through shared memory.  A node whose live parent produced a new value at t-1 recomputes from t on
+  //     even inside its own clean range (dirtiness propagates down the tree);
+  //   * clean entries only contribute to the band maximum (max_prob is reset every step in the reference).
+  // `full` disables the reuse (every node recomputed from s): the literal reference schedule.
+  __device__ __noinline__ void sweep(int reads_mask, int s0, int e0, int s1, int e1, bool full,
+                                     unsigned long long& n_updates) {
     POB_VIEWS
     const int tid = threadIdx.x;
-    const int len0 = (reads_mask & 1) ? e0 - s0 : 0, len1 = (reads_mask & 2) ? e1 - s1 : 0;
-    const int maxlen = max(len0, len1);
     const int a = tid >> 1, r = tid & 1;
     const bool used = a < EMAX && a_slot[a] >= 0;
     const bool on = used && ((reads_mask >> r) & 1);
-    int lo = 0, hi = 0, plo = 0, phi = 0, pstat = PS_DEAD, pa = 0;
+    int lo = 0, hi = 0, plo = 0, phi = 0, pstat = PS_DEAD, pa = 0, cs = 0;
     bool same = false;
-    double p_prev = ninf(), ng_prev = ninf(), maxv = ninf();
-    int ts = 0, te = 0;
+    double p_prev = ninf(), ng_prev = ninf(), g_prev = ninf(), maxv = ninf();
+    const int ts = r ? s1 : s0, te = r ? e1 : e0;
     Ent* wb = nullptr;
     const Ent* pwb = nullptr;
     int wmask = 0;
     const char* ylast_p = nullptr;
     const char* yblank_p = nullptr;
-    long ystep = 0;
-    bool f64 = false;
-    double ylast = 0, yblank = 0;
+    long ystep = 0, ycol_last = 0, ycol_blank = 0;
+    const char* ybase = nullptr;
+    bool f64 = false, yrc = false;
+    int yT = 0;
+    long yrowb = 0;
     deferred_finalize();
-    if (on) {
+    if (on && te > ts) {
       const int slot = a_slot[a];
       const int last = a_last[a];
       lo = a_lo[2 * a + r]; hi = a_hi[2 * a + r];
-      ts = r ? s1 : s0; te = r ? e1 : e0;
       wmask = g_es.mask[r];
       wb = wbase(slot, r);
       {
         const ReadView v = g_es.rv[r];
-        f64 = v.f64;
+        f64 = v.f64; yrc = v.rc; yT = v.T;
         const long es = f64 ? 8 : 4;
-        const long rowb = (long)v.S * es;
-        const char* row0 = (const char*)v.base + (long)v.prow(ts) * rowb;
-        ystep = v.rc ? -rowb : rowb;
-        ylast_p = row0 + (long)v.pcol(last) * es;
-        yblank_p = row0 + (long)v.cblank * es;
+        yrowb = (long)v.S * es;
+        ybase = (const char*)v.base;
+        ystep = v.rc ? -yrowb : yrowb;
+        ycol_last = (long)v.pcol(last) * es;
+        ycol_blank = (long)v.cblank * es;
       }
-      double g_prev = ninf();
-      if (ts - 1 >= lo && ts - 1 < hi) {
-        const Ent* se = wb + (ts & wmask);
-        p_prev = se->prob;
-        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { ng_prev = se->nogap; g_prev = se->gap; }
-      }
+      const int che = a_che[2 * a + r];
+      cs = full ? ts : min(max(che, ts), te);
       pstat = a_pstat[a];
       same = a_same[a] != 0;
-      if (pstat == PS_INE) pa = a_par[a];
-      else if (pstat == PS_FROZEN) { plo = a_plo[2 * a + r]; phi = a_phi[2 * a + r]; pwb = wbase(a_pslot[a], r); }
-      // publish the stored values at ts-1 for children whose parent is swept too
-      double2 pb; pb.x = p_prev; pb.y = g_prev;
-      pub[a * 2 + r] = pb;
-      if (ts < te) {
-        if (f64) { ylast = __ldg((const double*)ylast_p); yblank = __ldg((const double*)yblank_p); }
-        else { ylast = (double)__ldg((const float*)ylast_p); yblank = (double)__ldg((const float*)yblank_p); }
+      if (pstat == PS_INE) {
+        pa = a_par[a];
+        const int pche = a_che[2 * pa + r];
+        const int pcs = full ? ts : min(max(pche, ts), te);
+        atomicMin(&sh[SH_TB0 + r], pcs + 1);
+        plo = a_lo[2 * pa + r]; phi = a_hi[2 * pa + r]; pwb = wbase(a_pslot[a], r);
+      } else if (pstat == PS_FROZEN) {
+        plo = a_plo[2 * a + r]; phi = a_phi[2 * a + r]; pwb = wbase(a_pslot[a], r);
+      }
+      // clean part of the band: only the maximum is needed
+      for (int t = ts; t < cs; ++t) {
+        if (t >= lo && t < hi) {
+          const double v = (wb + ((t + 1) & wmask))->prob;
+          if (v > maxv) maxv = v;
+        }
       }
     }
     __syncthreads();
-    const double2* pub_rd = pub + (size_t)pa * 2 + r;
-    double2* pub_wr = pub + (size_t)(a < EMAX ? a : 0) * 2 + r;
-    const int pstride = EMAX * 2;
-    for (int it = 0; it < maxlen; ++it) {
-      const int t = ts + it;
-      const bool go = on && t < te;
-      if (go) {
-        double pv;
-        if (pstat == PS_INE) {
-          const double2 pb = pub_rd[(it & 1) * pstride];
-          pv = (MODEL == POB_MODEL_CTC_MERGE_REPEATS && same) ? pb.y : pb.x;
-        } else if (pstat == PS_FROZEN) {
-          if (t - 1 >= plo && t - 1 < phi) {
-            const Ent* q = pwb + (t & wmask);
-            if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pv = same ? q->gap : q->prob;
-            else pv = q->prob;
-          } else pv = ninf();
-        } else if (pstat == PS_ROOT) pv = root_prob(r, t - 1);
-        else pv = ninf();
-        const double yl = ylast, yb = yblank;
-        // next timestep's probabilities: issued now, consumed after the barrier
-        ylast_p += ystep; yblank_p += ystep;
-        if (t + 1 < te) {
-          if (f64) { ylast = __ldg((const double*)ylast_p); yblank = __ldg((const double*)yblank_p); }
-          else { ylast = (double)__ldg((const float*)ylast_p); yblank = (double)__ldg((const float*)yblank_p); }
+    const int Tb0 = sh[SH_TB0], Tb1 = sh[SH_TB1];
+    const int Tb = r ? Tb1 : Tb0;  // first timestep of this read that needs the synchronised loop
+    bool computing = false;        // p_prev / ng_prev hold the node's values at the previous timestep
+    // ---- phase A: private work [cs, min(te, Tb))
+    if (on && te > ts) {
+      const int limA = min(te, Tb);
+      if (cs < limA) {
+        if (cs - 1 >= lo && cs - 1 < hi) {
+          const Ent* se = wb + (cs & wmask);
+          p_prev = se->prob;
+          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { ng_prev = se->nogap; }
         }
-        double prob;
-        double2 pb;
-        Ent* o = wb + ((t + 1) & wmask);
-        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
-          const double gp = p_prev + yb;
-          const double ng = lae(pv + yl, ng_prev + yl);
-          prob = lae(gp, ng);
-          double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
-          *reinterpret_cast<double4*>(o) = v4;
-          ng_prev = ng;
-          pb.x = prob; pb.y = gp;
-        } else {
-          prob = lae(pv + yl, p_prev + yb);
-          o->prob = prob;
-          pb.x = prob; pb.y = ninf();
+        computing = true;
+        const char* row = ybase + (long)(yrc ? (yT - 1 - cs) : cs) * yrowb;
+        ylast_p = row + ycol_last; yblank_p = row + ycol_blank;
+        double yl, yb;
+        if (f64) { yl = __ldg((const double*)ylast_p); yb = __ldg((const double*)yblank_p); }
+        else { yl = (double)__ldg((const float*)ylast_p); yb = (double)__ldg((const float*)yblank_p); }
+        double pv = ninf();
+        if (pstat == PS_INE || pstat == PS_FROZEN) pv = frozen_at(pwb, cs, wmask, plo, phi, same);
+        else if (pstat == PS_ROOT) pv = root_prob(r, cs - 1);
+        for (int t = cs; t < limA; ++t) {
+          // inputs of the next timestep are requested before this one is evaluated
+          double yl_n = 0, yb_n = 0, pv_n = ninf();
+          ylast_p += ystep; yblank_p += ystep;
+          if (t + 1 < limA) {
+            if (f64) { yl_n = __ldg((const double*)ylast_p); yb_n = __ldg((const double*)yblank_p); }
+            else { yl_n = (double)__ldg((const float*)ylast_p); yb_n = (double)__ldg((const float*)yblank_p); }
+            if (pstat == PS_INE || pstat == PS_FROZEN) pv_n = frozen_at(pwb, t + 1, wmask, plo, phi, same);
+            else if (pstat == PS_ROOT) pv_n = root_prob(r, t);
+          }
+          double prob;
+          Ent* o = wb + ((t + 1) & wmask);
+          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
+            const double gp = p_prev + yb;
+            const double ng = lae(pv + yl, ng_prev + yl);
+            prob = lae(gp, ng);
+            double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
+            *reinterpret_cast<double4*>(o) = v4;
+            ng_prev = ng; g_prev = gp;
+          } else {
+            prob = lae(pv + yl, p_prev + yb);
+            o->prob = prob;
+          }
+          p_prev = prob;
+          if (prob > maxv) maxv = prob;
+          yl = yl_n; yb = yb_n; pv = pv_n;
         }
-        p_prev = prob;
-        if (prob > maxv) maxv = prob;
-        pub_wr[((it + 1) & 1) * pstride] = pb;
+      }
+    }
+    // ---- phase B: synchronised time-major loop over [Tb, te)
+    const int iters = max(max((reads_mask & 1) ? e0 - Tb0 : 0, (reads_mask & 2) ? e1 - Tb1 : 0), 0);
+    if (iters > 0) {
+      uint8_t* const pchg = reinterpret_cast<uint8_t*>(tmpa);  // [2][EMAX*2] "parent value changed" flags
+      const bool inB = on && te > ts && Tb < te;
+      double ylast = 0, yblank = 0;
+      if (inB) {
+        // publish the node's value at Tb-1: computed in phase A, or a stored clean entry
+        double2 pb; pb.x = ninf(); pb.y = ninf();
+        const int tp = Tb - 1;
+        if (computing) { pb.x = p_prev; pb.y = g_prev; }
+        else if (tp >= lo && tp < hi) {
+          const Ent* se = wb + ((tp + 1) & wmask);
+          pb.x = se->prob;
+          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pb.y = se->gap;
+        }
+        pub[a * 2 + r] = pb;
+        pchg[a * 2 + r] = computing;
+        const char* row = ybase + (long)(yrc ? (yT - 1 - Tb) : Tb) * yrowb;
+        ylast_p = row + ycol_last; yblank_p = row + ycol_blank;
+        if (f64) { ylast = __ldg((const double*)ylast_p); yblank = __ldg((const double*)yblank_p); }
+        else { ylast = (double)__ldg((const float*)ylast_p); yblank = (double)__ldg((const float*)yblank_p); }
       }
       __syncthreads();
+      const double2* pub_rd = pub + (size_t)pa * 2 + r;
+      double2* pub_wr = pub + (size_t)(a < EMAX ? a : 0) * 2 + r;
+      const int pstride = EMAX * 2;
+      double fz_next = ninf();
+      if (inB && pstat == PS_FROZEN) fz_next = frozen_at(pwb, Tb, wmask, plo, phi, same);
+      for (int it = 0; it < iters; ++it) {
+        const int t = Tb + it;
+        const bool go = inB && t < te;
+        if (go) {
+          double pv;
+          bool pchanged = false;
+          if (pstat == PS_INE) {
+            const double2 pb = pub_rd[(it & 1) * pstride];
+            pv = (MODEL == POB_MODEL_CTC_MERGE_REPEATS && same) ? pb.y : pb.x;
+            pchanged = pchg[(it & 1) * pstride + pa * 2 + r] != 0;
+          } else if (pstat == PS_FROZEN) {
+            pv = fz_next;
+            if (t + 1 < te) fz_next = frozen_at(pwb, t + 1, wmask, plo, phi, same);
+          } else if (pstat == PS_ROOT) pv = root_prob(r, t - 1);
+          else pv = ninf();
+          const double yl = ylast, yb = yblank;
+          ylast_p += ystep; yblank_p += ystep;
+          if (t + 1 < te) {
+            if (f64) { ylast = __ldg((const double*)ylast_p); yblank = __ldg((const double*)yblank_p); }
+            else { ylast = (double)__ldg((const float*)ylast_p); yblank = (double)__ldg((const float*)yblank_p); }
+          }
+          const bool must = computing || t >= cs || pchanged;
+          double2 pb;
+          if (must) {
+            if (!computing) {
+              // first recomputed timestep of a node that was clean so far: fetch its own values at t-1
+              computing = true;
+              p_prev = ninf(); ng_prev = ninf();
+              if (t - 1 >= lo && t - 1 < hi) {
+                const Ent* se = wb + (t & wmask);
+                p_prev = se->prob;
+                if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_prev = se->nogap;
+              }
+              if (t < cs) {
+                // dirtied inside its clean range: the clean maximum may include entries that change now
+                cs = t;
+                maxv = ninf();
+                for (int q = ts; q < t; ++q) {
+                  if (q >= lo && q < hi) {
+                    const double v = (wb + ((q + 1) & wmask))->prob;
+                    if (v > maxv) maxv = v;
+                  }
+                }
+              }
+            }
+            double prob;
+            Ent* o = wb + ((t + 1) & wmask);
+            if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
+              const double gp = p_prev + yb;
+              const double ng = lae(pv + yl, ng_prev + yl);
+              prob = lae(gp, ng);
+              double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
+              *reinterpret_cast<double4*>(o) = v4;
+              ng_prev = ng;
+              pb.x = prob; pb.y = gp;
+            } else {
+              prob = lae(pv + yl, p_prev + yb);
+              o->prob = prob;
+              pb.x = prob; pb.y = ninf();
+            }
+            p_prev = prob;
+            if (prob > maxv) maxv = prob;
+          } else {
+            // still clean at t: hand the stored value to the children
+            pb.x = ninf(); pb.y = ninf();
+            if (t >= lo && t < hi) {
+              const Ent* se = wb + ((t + 1) & wmask);
+              pb.x = se->prob;
+              if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pb.y = se->gap;
+            }
+          }
+          pub_wr[((it + 1) & 1) * pstride] = pb;
+          pchg[((it + 1) & 1) * pstride + a * 2 + r] = must;
+        }
+        __syncthreads();
+      }
     }
     if (on) {
       if (te > ts) {
-        if (ts > hi || ts < lo) { lo = ts; hi = te; }  // window bookkeeping for the contiguous write [ts, te)
+        // window bookkeeping: after this sweep every entry of [ts, te) is current
+        if (ts > hi || ts < lo) { lo = ts; hi = te; }
         else hi = max(hi, te);
         if (hi - lo > g_es.cap[r]) lo = hi - g_es.cap[r];
         a_lo[2 * a + r] = lo; a_hi[2 * a + r] = hi;
+        a_che[2 * a + r] = te;
         a_maxp[2 * a + r] = maxv;  // reset + max over the band
       } else {
         maxv = a_maxp[2 * a + r];  // empty band: max_prob left stale (A.6b)
       }
-      n_updates += (unsigned long long)max(te - ts, 0);
+      n_updates += (unsigned long long)max(te - ts, 0);  // algorithmic count: what the reference evaluates
     }
     // ranking keys: row_col = max0 + max1 (PrefixTree.h:111, :397); row = value(0, u) + max1 (:107, :393)
     const double other = __shfl_xor_sync(0xffffffffu, maxv, 1);
@@ -442,7 +578,10 @@ struct Engine {
     const int half = two ? (tid & 1) : 0;
     const bool cand = a < EMAX && a_slot[a] >= 0;
     int rank = 0;
-    if (tid == 0) { sh[SH_NB] = min(sh[SH_NUSED], W); sh[SH_DMIN] = 0x7fffffff; }
+    if (tid == 0) {
+      sh[SH_NB] = min(sh[SH_NUSED], W); sh[SH_DMIN] = 0x7fffffff;
+      sh[SH_TB0] = 0x7fffffff; sh[SH_TB1] = 0x7fffffff;  // for the next sweep
+    }
     if (cand) {
       const double2 k = key[a];
       const int mid = two ? (EMAX >> 1) : EMAX;
@@ -500,6 +639,7 @@ struct Engine {
     for (int q = 0; q < 4; ++q) { a_kid[4 * a + q] = -1; a_kido[4 * a + q] = 0; }
     a_lo[2 * a] = a_lo[2 * a + 1] = 0; a_hi[2 * a] = a_hi[2 * a + 1] = 0;
     a_maxp[2 * a] = a_maxp[2 * a + 1] = ninf(); a_last0[a] = ninf();
+    a_che[2 * a] = a_che[2 * a + 1] = -1;
     a_last[a] = (uint8_t)last; a_pstat[a] = PS_INE; a_same[a] = (a_last[pa] == last);
     a_inbeam[a] = 0; a_needed[a] = 1;
     key[a] = make_double2(ninf(), 4.5e9);
@@ -523,6 +663,7 @@ struct Engine {
     }
     a_lo[2 * a] = h.lo[0]; a_lo[2 * a + 1] = h.lo[1]; a_hi[2 * a] = h.hi[0]; a_hi[2 * a + 1] = h.hi[1];
     a_maxp[2 * a] = h.maxp[0]; a_maxp[2 * a + 1] = h.maxp[1]; a_last0[a] = ninf();
+    a_che[2 * a] = a_che[2 * a + 1] = -1;  // retained entries are stale with respect to the live parent
     a_last[a] = (uint8_t)h.last; a_pstat[a] = PS_INE; a_same[a] = (a_last[pa] == h.last);
     a_inbeam[a] = 0; a_needed[a] = 1;
     key[a] = make_double2(ninf(), 4.5e9);
@@ -550,7 +691,7 @@ struct Engine {
       if (ks >= 0) {
         const int ka = slot2e[ks];
         if (ka >= 0 && a_order[ka] == a_kido[4 * a + xc]) { kind = KID_ACTIVE; a_needed[ka] = 1; }
-        else if (hdr[ks].order == a_kido[4 * a + xc]) { kind = KID_REVIVE; hdr[ks].state = 0; }
+        else if (hdr[ks].order == a_kido[4 * a + xc]) { kind = KID_REVIVE; hdr[ks].state = 0; }  // line now in L1 for X3
       }
       kindv[tid] = (uint8_t)kind;
       if (xc == 0) { a_needed[a] = 1; tmpc[xb] = a_tid[a] < 0; }
@@ -746,6 +887,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     for (int k = 0; k < 32; ++k) sh[k] = 0;
     sh[SH_FQH] = 0; sh[SH_FQT] = NP; sh[SH_AFREE] = EMAX; sh[SH_ORDER] = 1; sh[SH_TID] = 1;
     sh[SH_DMIN] = 0x7fffffff; sh[SH_FIRSTALIVE] = 0x7fffffff;
+    sh[SH_TB0] = 0x7fffffff; sh[SH_TB1] = 0x7fffffff;
   }
   if (MODEL == POB_MODEL_CTC && tid < 2 && (tid == 0 || mode != MODE_1D)) {
     // PrefixTree.h:508-514: sequential running sum of the blank column
@@ -774,6 +916,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     for (int q = 0; q < 4; ++q) { a_kid[4 * a + q] = -1; a_kido[4 * a + q] = 0; }
     a_lo[2 * a] = a_lo[2 * a + 1] = 0; a_hi[2 * a] = a_hi[2 * a + 1] = 0;
     a_maxp[2 * a] = a_maxp[2 * a + 1] = ninf(); a_last0[a] = ninf();
+    a_che[2 * a] = a_che[2 * a + 1] = -1;
     a_last[a] = (uint8_t)tid; a_pstat[a] = PS_ROOT; a_same[a] = 0; a_inbeam[a] = 1; a_needed[a] = 1;
     slot2e[slot] = (int16_t)a;
     beam[tid] = a;
@@ -837,7 +980,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
         update_all(mine, tid, 0, u);
         if (mine) n_updates++;
       }
-      sweep(2, u, u + 1, rs, re, n_updates);
+      sweep(2, u, u + 1, rs, re, true, n_updates);
       prune();
       dbg_record(G, nsteps);
       // read 0 is next read at index u; read 1 at >= (smallest band start of any later row) - 1
@@ -876,7 +1019,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
       if ((!rset || !cset) && tid == 0) sh[SH_STATUS] |= POB_ST_UNSET_BAND;
       row_end = min(row_end, V); col_end = min(col_end, U);
       if (!have_E) { expand_and_retire(-1, -1); have_E = true; }
-      sweep(3, col_start, col_end, row_start, row_end, n_updates);
+      sweep(3, col_start, col_end, row_start, row_end, G.dbg_noreuse != 0, n_updates);
       prune();
       dbg_record(G, nsteps);
       expand_and_retire(u, v);  // later reads are at t-1 >= u (read 0) and >= v (read 1)
@@ -967,7 +1110,7 @@ size_t ws_bytes(int model, int NP, int CAP0, int CAP1, int RQ, int Umax, int Vma
 
 size_t smem_bytes(int W, int NP, int EMAX) {
   // must match POB_VIEWS
-  size_t b = 216 * (size_t)EMAX + 4 * ((W + 3) & ~3) + 4 * 32 + 2 * (size_t)NP + 5 * ((EMAX + 15) & ~15);
+  size_t b = 224 * (size_t)EMAX + 4 * ((W + 3) & ~3) + 4 * 32 + 2 * (size_t)NP + 5 * ((EMAX + 15) & ~15);
   return pob_align_up(b, 16);
 }
 
@@ -1011,6 +1154,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   }
   if (const char* e = getenv("POB_DEBUG_NP")) P.NP = atoi(e);
   if (const char* e = getenv("POB_DEBUG_NORECLAIM")) P.dbg_noreclaim = atoi(e);
+  if (const char* e = getenv("POB_DEBUG_NOREUSE")) P.dbg_noreuse = atoi(e);
   if (getenv("POB_DEBUG_TRACE")) {
     static double* dbg = nullptr;
     if (!dbg) cudaMalloc(&dbg, 200000 * sizeof(double));
