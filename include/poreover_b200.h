@@ -153,6 +153,15 @@ int pob_align_banded(pob_ctx* ctx, int where, const uint8_t* seq1, const int64_t
                      const int64_t* off2, int n_pairs, int band_width, int match, int mismatch, int gap_cost,
                      uint8_t* out_a1, uint8_t* out_a2, int32_t* out_alen, int32_t* out_matches);
 
+/* Full (unbanded) Needleman-Wunsch, the `--alignment full` path.
+ * replaces: align.global_pair (align.pyx:29-98).  Same output packing as pob_align_banded.  out_dp (may be
+ * NULL) receives each pair's (l1+1) x (l2+1) int32 DP matrix at dp_off[p] (the third return value of the
+ * reference function). */
+int pob_align_global(pob_ctx* ctx, int where, const uint8_t* seq1, const int64_t* off1, const uint8_t* seq2,
+                     const int64_t* off2, int n_pairs, int match, int mismatch, int gap_cost, uint8_t* out_a1,
+                     uint8_t* out_a2, int32_t* out_alen, int32_t* out_matches, const int64_t* dp_off,
+                     int32_t* out_dp);
+
 /* Alignment columns -> per-timestep envelope over read 2.
  * replaces: envelope.get_alignment_columns (envelope.py:26-44) + envelope.build_envelope (:46-87)
  * a1/a2 packed gapped rows at aln_off[p] with length alen[p]; s2s1/s2s2 int32 packed at soff1/soff2

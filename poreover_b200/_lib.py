@@ -53,6 +53,7 @@ SIGNATURES = {
     "pob_viterbi": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, vp]),
     "pob_viterbi_flipflop": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
     "pob_align_banded": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "pob_align_global": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "pob_build_envelope": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
     "pob_beam_search": (i32, [vp, i32, vp, i32, i32, vp, vp, vp, vp]),
     "pob_beam_search_2d": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),

@@ -14,7 +14,8 @@ def global_pair_banded(seq1, seq2, band_width=BAND_DEFAULT, match=MATCH_DEFAULT,
 
 
 def global_pair(seq1, seq2, match=MATCH_DEFAULT, mismatch=MISMATCH_DEFAULT, gap_cost=GAP_DEFAULT):
-    """Full Needleman-Wunsch (align.pyx:29-98), reachable through `pair-decode --alignment full`.
+    """Full Needleman-Wunsch with constant gap penalty (align.pyx:29-98), the `--alignment full` path.
 
-    Not on the default path; not built yet, and there is no CPU fallback."""
-    raise NotImplementedError("global_pair (--alignment full) is not implemented on the GPU backend yet")
+    Returns (align1, align2, dpMatrix) like the reference: two lists of characters and the int DP matrix."""
+    r = batch.align_global_batch([seq1], [seq2], match, mismatch, gap_cost, return_dp=True)[0]
+    return list(r[0]), list(r[1]), r[3]

@@ -271,3 +271,53 @@ def flipflop_viterbi_batch(arrays, rc=None, return_path=False, device=None):
     maps = [s2s[o:o + l].astype(np.int64) for o, l in zip(offs, ln[:b.n])]
     paths = [path[o:o + t].astype(np.int64) for o, t in zip(offs, b.lens)] if return_path else None
     return seqs, maps, paths
+
+
+def forward_batch(arrays, labels, model="ctc", rc=None, layout=_lib.BLANK_LAST, device=None):
+    """Exact forward log-probability of one label per read.  labels: strings over ACGT.
+
+    replaces decoding_cpp.cpp_forward (decoding_cpp.pyx:49-65)."""
+    if model not in _lib.MODEL:
+        raise ValueError("unknown model %r" % model)
+    b = _as_batch(arrays, rc, layout)
+    ctx = get_ctx(device)
+    n = b.n
+    lab_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(l) for l in labels], out=lab_off[1:])
+    lab = np.zeros(int(lab_off[-1]) + 8, dtype=np.uint8)
+    for l, o in zip(labels, lab_off[:-1]):
+        lab[o:o + len(l)] = ["ACGT".index(c) for c in l]
+    out = np.zeros(max(n, 1), dtype=np.float64)
+    rs = b.struct()
+    check(lib().pob_forward(ctx.h, _lib.HOST, C.byref(rs), ptr(lab), ptr(lab_off), _lib.MODEL[model], ptr(out)),
+          "pob_forward")
+    return out[:n].copy()
+
+
+def align_global_batch(seqs1, seqs2, match=2, mismatch=-1, gap_cost=-1, return_dp=False, device=None):
+    """Full Needleman-Wunsch for many pairs.  Returns list of (row1, row2, matches[, dp]).
+
+    replaces align.global_pair (align.pyx:29-98)."""
+    n = len(seqs1)
+    ctx = get_ctx(device)
+    b1, o1 = _pack_bytes(seqs1)
+    b2, o2 = _pack_bytes(seqs2)
+    aln_off = o1 + o2 + 8 * np.arange(n + 1, dtype=np.int64)
+    a1 = np.zeros(int(aln_off[-1]) + 1, dtype=np.uint8)
+    a2 = np.zeros(int(aln_off[-1]) + 1, dtype=np.uint8)
+    alen = np.zeros(max(n, 1), dtype=np.int32)
+    mat = np.zeros(max(n, 1), dtype=np.int32)
+    dp_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum((np.diff(o1) + 1) * (np.diff(o2) + 1), out=dp_off[1:])
+    dp = np.zeros(int(dp_off[-1]) + 1, dtype=np.int32) if return_dp else None
+    check(lib().pob_align_global(ctx.h, _lib.HOST, ptr(b1), ptr(o1), ptr(b2), ptr(o2), n, match, mismatch, gap_cost,
+                                 ptr(a1), ptr(a2), ptr(alen), ptr(mat), ptr(dp_off), ptr(dp)), "pob_align_global")
+    out = []
+    for p in range(n):
+        o, l = int(aln_off[p]), int(alen[p])
+        r = (a1[o:o + l].tobytes().decode(), a2[o:o + l].tobytes().decode(), int(mat[p]))
+        if return_dp:
+            l1, l2 = int(o1[p + 1] - o1[p]), int(o2[p + 1] - o2[p])
+            r = r + (dp[dp_off[p]:dp_off[p + 1]].reshape(l1 + 1, l2 + 1).copy(),)
+        out.append(r)
+    return out

@@ -168,8 +168,99 @@ int pob_build_envelope(pob_ctx* ctx, int where, const uint8_t* a1, const uint8_t
   POB_CUDA(cudaStreamSynchronize(ctx->stream));
   return POB_OK;
 }
-int pob_forward(pob_ctx*, int, const pob_reads_t*, const uint8_t*, const int64_t*, int, double*) {
-  return POB_EUNSUPPORTED;
+int pob_forward(pob_ctx* ctx, int where, const pob_reads_t* reads, const uint8_t* labels, const int64_t* lab_off,
+                int model, double* out_logp) {
+  if (!ctx) return POB_EINVAL;
+  POB_TRY(check_reads(reads, 2, 9));
+  if (reads->dtype != POB_F32 && reads->dtype != POB_F64) return POB_EINVAL;
+  if (model != POB_MODEL_CTC && model != POB_MODEL_CTC_MERGE_REPEATS) return POB_EINVAL;
+  const int n = reads->n;
+  if (n == 0) return POB_OK;
+  if (!labels || !lab_off || !out_logp) return POB_EINVAL;
+  POB_CUDA(cudaSetDevice(ctx->device));
+  POB_TRY(pob_arena_reset(ctx));
+  std::vector<int64_t> off, loff;
+  std::vector<int32_t> len;
+  POB_TRY(fetch_i64(ctx, where, reads->row_off, (size_t)n + 1, off));
+  POB_TRY(fetch_i64(ctx, where, lab_off, (size_t)n + 1, loff));
+  if (reads->row_len) POB_TRY(fetch_i32(ctx, where, reads->row_len, (size_t)n, len));
+  std::vector<int64_t> scr_off(n + 1);
+  scr_off[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    const int64_t T = reads->row_len ? len[i] : off[i + 1] - off[i];
+    scr_off[i + 1] = scr_off[i] + 5 * T + 8;
+  }
+  pob_reads_t d = *reads;
+  const uint8_t* d_lab = labels;
+  const int64_t* d_loff = lab_off;
+  double* d_out = out_logp;
+  if (where == POB_HOST) {
+    POB_TRY(stage_reads(ctx, reads, &d));
+    POB_TRY(stage_in(ctx, labels, (size_t)loff[n], &d_lab, 8));
+    POB_TRY(stage_in(ctx, lab_off, (size_t)n + 1, &d_loff));
+    POB_TRY(stage_out(ctx, out_logp, (size_t)n, &d_out));
+  }
+  const int64_t* d_scr_off;
+  POB_TRY(upload(ctx, scr_off, &d_scr_off));
+  double* scratch;
+  POB_TRY(pob_take(ctx, (size_t)scr_off[n] + 8, &scratch));
+  POB_TRY(pob_forward_launch(ctx, d, d_lab, d_loff, model, scratch, d_scr_off, d_out));
+  if (where == POB_HOST) POB_TRY(copy_back(ctx, out_logp, d_out, (size_t)n));
+  POB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return POB_OK;
+}
+
+int pob_align_global(pob_ctx* ctx, int where, const uint8_t* seq1, const int64_t* off1, const uint8_t* seq2,
+                     const int64_t* off2, int n, int match, int mismatch, int gap, uint8_t* out_a1, uint8_t* out_a2,
+                     int32_t* out_alen, int32_t* out_matches, const int64_t* dp_off, int32_t* out_dp) {
+  if (!ctx || n < 0) return POB_EINVAL;
+  if (n == 0) return POB_OK;
+  if (!seq1 || !seq2 || !off1 || !off2 || !out_a1 || !out_a2 || !out_alen) return POB_EINVAL;
+  if (out_dp && !dp_off) return POB_EINVAL;
+  POB_CUDA(cudaSetDevice(ctx->device));
+  POB_TRY(pob_arena_reset(ctx));
+  std::vector<int64_t> o1, o2;
+  POB_TRY(fetch_i64(ctx, where, off1, (size_t)n + 1, o1));
+  POB_TRY(fetch_i64(ctx, where, off2, (size_t)n + 1, o2));
+  std::vector<int64_t> h_dp_off(n + 1), aln_off(n + 1);
+  h_dp_off[0] = 0;
+  for (int p = 0; p < n; ++p) {
+    const int64_t l1 = o1[p + 1] - o1[p], l2 = o2[p + 1] - o2[p];
+    h_dp_off[p + 1] = h_dp_off[p] + (l1 + 1) * (l2 + 1);
+    aln_off[p] = o1[p] + o2[p] + 8 * (int64_t)p;
+  }
+  aln_off[n] = o1[n] + o2[n] + 8 * (int64_t)n;
+  const uint8_t *d_s1 = seq1, *d_s2 = seq2;
+  const int64_t *d_o1 = off1, *d_o2 = off2;
+  uint8_t *d_a1 = out_a1, *d_a2 = out_a2;
+  int32_t *d_alen = out_alen, *d_match = out_matches;
+  if (where == POB_HOST) {
+    POB_TRY(stage_in(ctx, seq1, (size_t)o1[n], &d_s1, 8));
+    POB_TRY(stage_in(ctx, seq2, (size_t)o2[n], &d_s2, 8));
+    POB_TRY(stage_in(ctx, off1, (size_t)n + 1, &d_o1));
+    POB_TRY(stage_in(ctx, off2, (size_t)n + 1, &d_o2));
+    POB_TRY(stage_out(ctx, out_a1, (size_t)aln_off[n], &d_a1));
+    POB_TRY(stage_out(ctx, out_a2, (size_t)aln_off[n], &d_a2));
+    POB_TRY(stage_out(ctx, out_alen, (size_t)n, &d_alen));
+    POB_TRY(stage_out(ctx, out_matches, (size_t)n, &d_match));
+  }
+  const int64_t *d_dpoff, *d_alnoff;
+  POB_TRY(upload(ctx, h_dp_off, &d_dpoff));
+  POB_TRY(upload(ctx, aln_off, &d_alnoff));
+  int32_t* dp;
+  if (where == POB_DEVICE && out_dp) dp = out_dp;  // caller's packing must equal (l1+1)*(l2+1) per pair
+  else POB_TRY(pob_take(ctx, (size_t)h_dp_off[n] + 1, &dp));
+  POB_TRY(pob_global_pair_launch(ctx, d_s1, d_o1, d_s2, d_o2, n, match, mismatch, gap, d_dpoff, dp, d_alnoff, d_a1,
+                                 d_a2, d_alen, d_match));
+  if (where == POB_HOST) {
+    POB_TRY(copy_back(ctx, out_a1, d_a1, (size_t)aln_off[n]));
+    POB_TRY(copy_back(ctx, out_a2, d_a2, (size_t)aln_off[n]));
+    POB_TRY(copy_back(ctx, out_alen, d_alen, (size_t)n));
+    POB_TRY(copy_back(ctx, out_matches, d_match, (size_t)n));
+    if (out_dp) POB_TRY(copy_back(ctx, out_dp, dp, (size_t)h_dp_off[n]));
+  }
+  POB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return POB_OK;
 }
 
 }  // extern "C"

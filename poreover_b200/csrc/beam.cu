@@ -377,11 +377,16 @@ struct Engine {
       } else if (pstat == PS_FROZEN) {
         plo = a_plo[2 * a + r]; phi = a_phi[2 * a + r]; pwb = wbase(a_pslot[a], r);
       }
-      // clean part of the band: only the maximum is needed
-      for (int t = ts; t < cs; ++t) {
-        if (t >= lo && t < hi) {
-          const double v = (wb + ((t + 1) & wmask))->prob;
-          if (v > maxv) maxv = v;
+      // clean part of the band: only the maximum is needed (independent loads, four in flight)
+      {
+        const int c0 = max(ts, lo), c1 = min(cs, hi);
+        for (int t = c0; t < c1; t += 4) {
+          double v0 = ninf(), v1 = ninf(), v2 = ninf(), v3 = ninf();
+          v0 = (wb + ((t + 1) & wmask))->prob;
+          if (t + 1 < c1) v1 = (wb + ((t + 2) & wmask))->prob;
+          if (t + 2 < c1) v2 = (wb + ((t + 3) & wmask))->prob;
+          if (t + 3 < c1) v3 = (wb + ((t + 4) & wmask))->prob;
+          maxv = fmax(fmax(maxv, v0), fmax(fmax(v1, v2), v3));
         }
       }
     }

@@ -43,5 +43,8 @@ def cpp_beam_search_2d(y1_, y2_, envelope_ranges_=None, beam_width_=25, alphabet
 
 
 def cpp_forward(y_, label_, alphabet_="ACGT", model_="ctc"):
-    """decoding_cpp.pyx:49-65 -> forward (PrefixTree.h:710-759)."""
-    raise NotImplementedError("cpp_forward is not built on the GPU backend yet (SURVEY.md section 8(f) rank 4)")
+    """decoding_cpp.pyx:49-65 -> forward (PrefixTree.h:710-759): log-probability of `label_` given y_."""
+    y = _prep(y_)
+    _check_alphabet(alphabet_, y)
+    lab = label_ if alphabet_ == "ACGT" else label_.translate(str.maketrans(alphabet_, "ACGT"))
+    return float(batch.forward_batch([y], [lab], model_)[0])
