@@ -64,12 +64,130 @@ __device__ __forceinline__ int argmax5(const float* r, bool rc) {
   return b;
 }
 
-template <int LAYOUT>
+// One read, one warp.  RC / KIND / PATH are compile-time so the per-row work is a handful of compares and
+// selects; chunks whose 32 groups are all complete take a path without per-row validity tests.
+template <int LAYOUT, bool RC, int KIND, bool PATH>
+__device__ __forceinline__ void viterbi5_read(const float* __restrict__ base, int T, int lane, uint8_t* __restrict__ oseq,
+                                              int32_t* __restrict__ os2s, int8_t* __restrict__ opath, int& nout_o,
+                                              int& pfirst_o, int& plast_o) {
+  const int G = (T + 3) >> 2;          // groups of 4 rows
+  const int Gfull = T >> 2;            // complete groups
+  const int nch = (G + 31) >> 5;
+  const bool aligned = (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+  float cur[20], nxt[20];
+  auto load_group = [&](int c, float* dst) {
+    const int gi = (c << 5) + lane;
+    if (gi >= G) return;
+    const int g = RC ? (G - 1 - gi) : gi;
+    const float* p = base + (size_t)g * 20;
+    if (aligned && g < Gfull) {
+      const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const float4 v = ldg_stream(q + i);
+        dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+      }
+    } else {
+      const int nv = min(20, (T - 4 * g) * 5);
+#pragma unroll
+      for (int i = 0; i < 20; ++i) dst[i] = (i < nv) ? __ldg(p + i) : 0.f;
+    }
+  };
+  int carry = -1, nout = 0, pfirst = -1, plast = -1;
+  if (nch > 0) load_group(0, cur);
+  for (int c = 0; c < nch; ++c) {
+    if (c + 1 < nch) load_group(c + 1, nxt);
+    const int gi = (c << 5) + lane;
+    const int g = RC ? (G - 1 - gi) : gi;
+    // the chunk is "full" when all of its 32 groups are complete groups of the read
+    const bool full = RC ? ((c << 5) + 31 < G && (G - 1 - (c << 5)) < Gfull) : ((c << 5) + 32 <= Gfull);
+    int p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = argmax5<LAYOUT>(cur + 5 * (RC ? 3 - j : j), RC);  // logical order
+    const int t0 = RC ? (T - 4 * g - 4) : 4 * g;  // logical time of the lane's first row (full groups)
+    unsigned em = 0;
+    if (full) {
+      int prev = __shfl_up_sync(0xffffffffu, p[3], 1);
+      if (lane == 0) prev = carry;
+      carry = __shfl_sync(0xffffffffu, p[3], 31);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool e = (p[j] != 4) && (KIND == POB_KIND_POREOVER || p[j] != prev);
+        em |= (e ? 1u : 0u) << j;
+        prev = p[j];
+      }
+      if (PATH) {
+        // four consecutive logical timesteps: one 32-bit store when the destination is 4-byte aligned
+        const unsigned pk = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
+        if (((reinterpret_cast<uintptr_t>(opath) + t0) & 3) == 0) *reinterpret_cast<unsigned*>(opath + t0) = pk;
+        else { opath[t0] = p[0]; opath[t0 + 1] = p[1]; opath[t0 + 2] = p[2]; opath[t0 + 3] = p[3]; }
+      }
+      if (c == 0 && lane == 0) pfirst = p[0];
+      if (t0 + 4 == T) plast = p[3];
+    } else {
+      const bool have = gi < G;
+      int last = -1;
+      bool valid[4];
+      int tt[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pr = RC ? (4 * g + 3 - j) : (4 * g + j);
+        valid[j] = have && pr < T;
+        tt[j] = RC ? (T - 1 - pr) : pr;
+        if (valid[j]) last = p[j];
+      }
+      int prev = __shfl_up_sync(0xffffffffu, last, 1);
+      if (lane == 0) prev = carry;
+      carry = __shfl_sync(0xffffffffu, last, 31);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (valid[j]) {
+          const bool e = (p[j] != 4) && (KIND == POB_KIND_POREOVER || p[j] != prev);
+          em |= (e ? 1u : 0u) << j;
+          prev = p[j];
+          if (tt[j] == 0) pfirst = p[j];
+          if (tt[j] == T - 1) plast = p[j];
+          if (PATH) opath[tt[j]] = (int8_t)p[j];
+        }
+      }
+    }
+    int total;
+    int off = nout + warp_excl_scan(__popc(em), lane, total);
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (em & (1u << j)) {
+          oseq[off] = (uint8_t)("ACGT"[p[j]]);
+          if (os2s) os2s[off] = t0 + j;
+          ++off;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (em & (1u << j)) {
+          const int pr = RC ? (4 * g + 3 - j) : (4 * g + j);
+          oseq[off] = (uint8_t)("ACGT"[p[j]]);
+          if (os2s) os2s[off] = RC ? (T - 1 - pr) : pr;
+          ++off;
+        }
+      }
+    }
+    nout += total;
+#pragma unroll
+    for (int i = 0; i < 20; ++i) cur[i] = nxt[i];
+  }
+  nout_o = nout;
+  pfirst_o = __reduce_max_sync(0xffffffffu, pfirst);
+  plast_o = __reduce_max_sync(0xffffffffu, plast);
+}
+
+template <int LAYOUT, int KIND, bool PATH>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 viterbi5_f32_kernel(const float* __restrict__ data, const int64_t* __restrict__ row_off,
-                    const int32_t* __restrict__ row_len, const uint8_t* __restrict__ rcflag, int n, int kind, uint8_t* __restrict__ out_seq,
-                    int32_t* __restrict__ out_s2s, int8_t* __restrict__ out_path, int32_t* __restrict__ out_len,
-                    int32_t* __restrict__ out_status) {
+                    const int32_t* __restrict__ row_len, const uint8_t* __restrict__ rcflag, int n,
+                    uint8_t* __restrict__ out_seq, int32_t* __restrict__ out_s2s, int8_t* __restrict__ out_path,
+                    int32_t* __restrict__ out_len, int32_t* __restrict__ out_status) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= n) return;
@@ -77,95 +195,17 @@ viterbi5_f32_kernel(const float* __restrict__ data, const int64_t* __restrict__ 
   const int T = pob_read_len(row_off, row_len, r);
   const bool rc = rcflag ? (rcflag[r] != 0) : false;
   const float* base = data + ro * 5;
-  const int G = (T + 3) >> 2;
-  const int nch = (G + 31) >> 5;
-  const bool aligned = (reinterpret_cast<uintptr_t>(base) & 15) == 0;
-
-  float cur[20], nxt[20];
-  auto load_group = [&](int c, float* dst) {
-    int gi = (c << 5) + lane;
-    if (gi >= G) return;
-    int g = rc ? (G - 1 - gi) : gi;
-    const float* p = base + (size_t)g * 20;
-    if (aligned && 4 * g + 4 <= T) {
-      const float4* q = reinterpret_cast<const float4*>(p);
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        float4 v = ldg_stream(q + i);
-        dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
-      }
-    } else {
-      int nv = (T - 4 * g) * 5;
-#pragma unroll
-      for (int i = 0; i < 20; ++i) dst[i] = (i < nv) ? __ldg(p + i) : 0.f;
-    }
-  };
-
-  int carry = -1;           // path value at the last timestep of the previous chunk
-  int nout = 0;             // bases emitted so far
-  int pfirst = -1, plast = -1;
   uint8_t* oseq = out_seq + ro;
   int32_t* os2s = out_s2s ? out_s2s + ro : nullptr;
-  int8_t* opath = out_path ? out_path + ro : nullptr;
-
-  if (nch > 0) load_group(0, cur);
-  for (int c = 0; c < nch; ++c) {
-    if (c + 1 < nch) load_group(c + 1, nxt);
-    const int gi = (c << 5) + lane;
-    const bool have = gi < G;
-    const int g = rc ? (G - 1 - gi) : gi;
-    int pp[4];  // argmax of the lane's 4 physical rows (compile-time register indexing)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) pp[j] = argmax5<LAYOUT>(cur + 5 * j, rc);
-    int p[4], tt[4];
-    bool valid[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int pr = rc ? (4 * g + 3 - j) : (4 * g + j);  // physical row of the lane's j-th logical row
-      valid[j] = have && pr < T;
-      tt[j] = rc ? (T - 1 - pr) : pr;
-      p[j] = rc ? pp[3 - j] : pp[j];
-    }
-    int last = -1;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (valid[j]) last = p[j];
-    int prev = __shfl_up_sync(0xffffffffu, last, 1);
-    if (lane == 0) prev = carry;
-    carry = __shfl_sync(0xffffffffu, last, 31);  // chunks before the final one are full
-    unsigned em = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (valid[j]) {
-        bool e = (p[j] != 4) && (kind == POB_KIND_POREOVER || p[j] != prev);
-        em |= (e ? 1u : 0u) << j;
-        prev = p[j];
-        if (tt[j] == 0) pfirst = p[j];
-        if (tt[j] == T - 1) plast = p[j];
-        if (opath) opath[tt[j]] = (int8_t)p[j];
-      }
-    }
-    int cnt = __popc(em), total;
-    int off = nout + warp_excl_scan(cnt, lane, total);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (em & (1u << j)) {
-        oseq[off] = (uint8_t)("ACGT"[p[j]]);
-        if (os2s) os2s[off] = tt[j];
-        ++off;
-      }
-    }
-    nout += total;
-#pragma unroll
-    for (int i = 0; i < 20; ++i) cur[i] = nxt[i];
-  }
-  pfirst = __reduce_max_sync(0xffffffffu, pfirst);
-  plast = __reduce_max_sync(0xffffffffu, plast);
+  int8_t* opath = PATH ? out_path + ro : nullptr;
+  int nout, pfirst, plast;
+  if (rc) viterbi5_read<LAYOUT, true, KIND, PATH>(base, T, lane, oseq, os2s, opath, nout, pfirst, plast);
+  else viterbi5_read<LAYOUT, false, KIND, PATH>(base, T, lane, oseq, os2s, opath, nout, pfirst, plast);
   if (lane == 0) {
     out_len[r] = nout;
     int st = (T == 0) ? POB_ST_EMPTY : 0;
     // pair_decode.py:136 compares path[0] with path[-1]; equal bases drop the first one
-    if (kind == POB_KIND_BONITO && T > 0 && pfirst != 4 && pfirst == plast) st |= POB_ST_MAPPING_WRAP;
+    if (KIND == POB_KIND_BONITO && T > 0 && pfirst != 4 && pfirst == plast) st |= POB_ST_MAPPING_WRAP;
     if (out_status) out_status[r] = st;
   }
 }
@@ -237,12 +277,20 @@ int pob_viterbi_launch(pob_ctx* ctx, const pob_reads& rd, int kind, uint8_t* out
   dim3 grid((rd.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   pob_prof_scope ps(ctx, POB_K_VITERBI);
   if (rd.dtype == POB_F32 && rd.n_states == 5) {
-    if (rd.layout == POB_BLANK_LAST)
-      viterbi5_f32_kernel<POB_BLANK_LAST><<<grid, block, 0, ctx->stream>>>(
-          (const float*)rd.data, rd.row_off, rd.row_len, rd.rc, rd.n, kind, out_seq, out_s2s, out_path, out_len, out_status);
-    else
-      viterbi5_f32_kernel<POB_BLANK_FIRST><<<grid, block, 0, ctx->stream>>>(
-          (const float*)rd.data, rd.row_off, rd.row_len, rd.rc, rd.n, kind, out_seq, out_s2s, out_path, out_len, out_status);
+#define POB_VIT(LAY, KND, PTH)                                                                              \
+  viterbi5_f32_kernel<LAY, KND, PTH><<<grid, block, 0, ctx->stream>>>((const float*)rd.data, rd.row_off, rd.row_len, \
+                                                                      rd.rc, rd.n, out_seq, out_s2s, out_path,      \
+                                                                      out_len, out_status)
+    const bool bl = rd.layout == POB_BLANK_LAST, bon = kind == POB_KIND_BONITO, pth = out_path != nullptr;
+    if (bl && bon && pth) POB_VIT(POB_BLANK_LAST, POB_KIND_BONITO, true);
+    else if (bl && bon) POB_VIT(POB_BLANK_LAST, POB_KIND_BONITO, false);
+    else if (bl && pth) POB_VIT(POB_BLANK_LAST, POB_KIND_POREOVER, true);
+    else if (bl) POB_VIT(POB_BLANK_LAST, POB_KIND_POREOVER, false);
+    else if (bon && pth) POB_VIT(POB_BLANK_FIRST, POB_KIND_BONITO, true);
+    else if (bon) POB_VIT(POB_BLANK_FIRST, POB_KIND_BONITO, false);
+    else if (pth) POB_VIT(POB_BLANK_FIRST, POB_KIND_POREOVER, true);
+    else POB_VIT(POB_BLANK_FIRST, POB_KIND_POREOVER, false);
+#undef POB_VIT
   } else if (rd.dtype == POB_F32) {
     viterbi_generic_kernel<float><<<grid, block, 0, ctx->stream>>>((const float*)rd.data, rd.row_off, rd.row_len, rd.rc, rd.n,
                                                                    rd.n_states, rd.layout, kind, out_seq, out_s2s, out_path,
