@@ -1153,7 +1153,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
     long want = 64L * W;
     const long by_span = 3L * W * (span + 8) + 16L * W;
     if (by_span > want) want = by_span;
-    if (want > 32768) want = 32768;
+    if (want > 65536) want = 65536;
     P.NP = pow2_at_least((int)want);
     if (P.NP < 1024) P.NP = 1024;
   }
@@ -1169,9 +1169,6 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   }
   P.CAP0 = pow2_at_least(max_span0 + 3);
   P.CAP1 = pow2_at_least(max_span1 + 3);
-  // keep one CTA's workspace under ~160 MB so that a full wave of CTAs fits in HBM (wide-band batches then
-  // run with a smaller pool and rely on the overflow flag)
-  while (P.NP > 1024 && ws_bytes(model, P.NP, P.CAP0, P.CAP1, 2 * P.NP, Umax, Vmax) > ((size_t)160 << 20)) P.NP >>= 1;
   P.RQ = P.NP * 2;
   // the band sweep wants one thread per (node, read); the single-read search one per node
   int threads = (((mode == MODE_1D ? 1 : 2) * P.EMAX + 31) / 32) * 32;
@@ -1200,13 +1197,21 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   int per_sm = 0;
   POB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) return POB_EUNSUPPORTED;
-  const size_t stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, Umax, Vmax);
+  // Workspace: one stride per resident CTA.  Prefer a full wave of CTAs; when the pool of a wide-band batch
+  // makes that too large for HBM, first run fewer CTAs, then (only if a single CTA still does not fit) shrink
+  // the pool and rely on the overflow flag.
   int grid = per_sm * ctx->sm_count;
   if (grid > n_items) grid = n_items;
   if (grid < 1) grid = 1;
-  // keep the workspace within a sane share of HBM
   const size_t budget = (size_t)96 << 30;
+  size_t stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, Umax, Vmax);
+  while (grid > 1 && (size_t)grid * stride > budget && stride > ((size_t)192 << 20)) {
+    // wide bands are rare inside a batch: a smaller pool is usually enough, keep the parallelism
+    if (P.NP > 8192) { P.NP >>= 1; P.RQ = P.NP * 2; stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, Umax, Vmax); }
+    else break;
+  }
   while (grid > 1 && (size_t)grid * stride > budget) grid = grid * 3 / 4;
+  while (P.NP > 1024 && stride > budget) { P.NP >>= 1; P.RQ = P.NP * 2; stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, Umax, Vmax); }
   P.ws_stride = stride;
   P.ws = (char*)pob_arena_take(ctx, (size_t)grid * stride);
   if (!P.ws) return POB_ENOMEM;

@@ -80,3 +80,25 @@ def test_long_pair_wide_band(oracle):
     seqs, sc, st = batch.beam_search_2d_batch([lp1], [lp2], [env], 5, "ctc_merge_repeats", "row_col")
     assert seqs[0] == want["consensus"] and abs(sc[0] - want["score"]) < TOL
     assert not (st[0] & _lib.ST_POOL_OVERFLOW)
+
+
+def test_real_pair_from_reference_data(tmp_path):
+    """The reference's own real-data pair (data/reads/read1.npy + read2.npy, PoreOverNet logits, 62,000 and
+    75,600 timesteps, bands up to ~1450 wide) through the fused pipeline; expectations recorded from the real
+    reference by tests/golden/make_golden_real.py."""
+    import os
+    from poreover_b200.decoding import decode as gdecode
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "real_pair.npz"))
+    arrays = []
+    for name in ("read1", "read2"):
+        f = tmp_path / (name + ".npy")
+        np.save(f, g[name])
+        arrays.append(gdecode.model_from_trace(str(f), "poreover").device_array())
+    assert arrays[0].shape == (62000, 5) and arrays[1].shape == (75600, 5)
+    for W in (5, 25):
+        r = batch.pair_decode_batch([arrays[0]], [arrays[1]], "poreover", beam_width=W, rc2=True)[0]
+        assert r["basecall1"] == str(g["basecall1"])
+        assert (r["length1"], r["length2"]) == (int(g["length1"]), int(g["length2"]))
+        assert r["identity"] == float(g["identity"])
+        assert r["consensus"] == str(g["consensus_w%d" % W]), W
+        assert not (r["status"] & (_lib.ST_POOL_OVERFLOW | _lib.ST_SHORT_BEAM_SKIP | _lib.ST_UNSET_BAND))
