@@ -10,7 +10,7 @@ import threading
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libporeover_b200.so")
+LIB_PATH = os.environ.get("POB_DEBUG_LIB") or os.path.join(HERE, "libporeover_b200.so")  # override: instrumented debug builds (tools/)
 
 HOST, DEVICE = 0, 1
 F32, F64, U8_TRACE = 0, 1, 2

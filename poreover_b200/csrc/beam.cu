@@ -56,15 +56,18 @@ struct __align__(16) NodeHdr {  // 128 bytes, home record of a node in the globa
   int32_t pad[2];
 };
 
+// A node's window for one read is a ring of `cap` time keys stored as separate arrays (structure of arrays):
+// prob[cap], and for the merge-repeats tree gap[cap], nogap[cap].  The band maximum scans only prob[], children read
+// prob[] or gap[] of their parent, the node itself prob[] and nogap[]: every access touches 8-byte values that sit
+// next to the values of neighbouring time keys, so a band occupies as few cache lines as possible.
 template <int MODEL>
-struct Entry;
-template <>
-struct __align__(32) Entry<POB_MODEL_CTC_MERGE_REPEATS> {
-  double prob, gap, nogap, pad;
-};
-template <>
-struct __align__(8) Entry<POB_MODEL_CTC> {
-  double prob;
+struct Win {
+  double* b;
+  int cap;
+  __device__ __forceinline__ double& prob(int i) const { return b[i]; }
+  __device__ __forceinline__ double& gap(int i) const { return b[cap + i]; }
+  __device__ __forceinline__ double& nogap(int i) const { return b[2 * cap + i]; }
+  static __host__ __device__ constexpr int arrays() { return MODEL == POB_MODEL_CTC_MERGE_REPEATS ? 3 : 1; }
 };
 
 struct BeamParams {
@@ -127,7 +130,7 @@ __device__ __forceinline__ ReadView make_view(const pob_reads& r, int item) {
 }
 
 enum { SH_NB = 0, SH_NUSED, SH_FQH, SH_FQT, SH_AFREE, SH_ORDER, SH_TID, SH_STAMP, SH_RQH, SH_RQT, SH_STATUS, SH_FIRSTALIVE,
-       SH_TOTALLOC, SH_TOTFIRST, SH_DMIN, SH_TB0, SH_TB1, SH_COUNT };
+       SH_TOTALLOC, SH_TOTFIRST, SH_DMIN, SH_TB0, SH_TB1, SH_VIRGIN, SH_COUNT };
 
 // Per-CTA engine state.  Scalars and global-memory views live in a static __shared__ struct; the per-active-slot
 // arrays live in dynamic shared memory at offsets that depend only on EMAX / W / NP, so every access compiles
@@ -146,6 +149,23 @@ struct EngState {
   uint32_t* trace;
 };
 __shared__ EngState g_es;
+
+// Optional per-phase cycle attribution (tools/phase_clocks.py builds a second library with -DPOB_PHASE_CLOCKS):
+// thread 0 accumulates the cycles between consecutive marks into g_phase_clk[mark id].
+#ifdef POB_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[32];
+__shared__ long long g_pclk_last;
+#define PCLK(i)                                                                  \
+  do {                                                                           \
+    if (threadIdx.x == 0) {                                                      \
+      const long long c_ = clock64();                                            \
+      atomicAdd(&g_phase_clk[i], (unsigned long long)(c_ - g_pclk_last));        \
+      g_pclk_last = c_;                                                          \
+    }                                                                            \
+  } while (0)
+#else
+#define PCLK(i) do { } while (0)
+#endif
 extern __shared__ __align__(16) char pob_smem[];
 
 // Shared-memory arrays of the active slots (index a in [0, EMAX)); a_slot[a] < 0 = unused.
@@ -202,10 +222,13 @@ extern __shared__ __align__(16) char pob_smem[];
 
 template <int MODEL>
 struct Engine {
-  typedef Entry<MODEL> Ent;
+  typedef Win<MODEL> Ent;
 
-  __device__ __forceinline__ Ent* wbase(int slot, int r) const {
-    return reinterpret_cast<Ent*>(g_es.win[r]) + (size_t)slot * g_es.cap[r];
+  __device__ __forceinline__ Ent wbase(int slot, int r) const {
+    Ent w;
+    w.cap = g_es.cap[r];
+    w.b = reinterpret_cast<double*>(g_es.win[r]) + (size_t)slot * (Ent::arrays() * w.cap);
+    return w;
   }
 
   // value of the root at time t (parent of depth-1 nodes)
@@ -241,10 +264,11 @@ struct Engine {
     const int last = a_last[a];
     in.lo = a_lo[2 * a + r]; in.hi = a_hi[2 * a + r];
     const bool self_ok = (t - 1 >= in.lo && t - 1 < in.hi);
-    const Ent* se = wbase(slot, r) + (t & g_es.mask[r]);
-    in.p_prev = self_ok ? se->prob : ninf();
+    const Ent se = wbase(slot, r);
+    const int si = t & g_es.mask[r];
+    in.p_prev = self_ok ? se.prob(si) : ninf();
     in.ng_prev = ninf();
-    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.ng_prev = self_ok ? se->nogap : ninf();
+    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.ng_prev = self_ok ? se.nogap(si) : ninf();
     in.ylast = g_es.rv[r].at(t, g_es.rv[r].pcol(last));
     in.yblank = g_es.rv[r].at(t, g_es.rv[r].cblank);
     const int ps = a_pstat[a];
@@ -257,9 +281,10 @@ struct Engine {
       if (ps == PS_INE) { const int pa = a_par[a]; plo = a_lo[2 * pa + r]; phi = a_hi[2 * pa + r]; }
       else { plo = a_plo[2 * a + r]; phi = a_phi[2 * a + r]; }
       if (t - 1 >= plo && t - 1 < phi) {
-        const Ent* pe = wbase(a_pslot[a], r) + (t & g_es.mask[r]);
-        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.pv = a_same[a] ? pe->gap : pe->prob;
-        else in.pv = pe->prob;
+        const Ent pe = wbase(a_pslot[a], r);
+        const int pi = t & g_es.mask[r];
+        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.pv = a_same[a] ? pe.gap(pi) : pe.prob(pi);
+        else in.pv = pe.prob(pi);
       } else {
         in.pv = ninf();
       }
@@ -268,18 +293,18 @@ struct Engine {
 
   __device__ __forceinline__ double update_commit(int a, int r, int t, const UpdIn& in) {
     POB_VIEWS
-    Ent out;
+    const Ent out = wbase(a_slot[a], r);
+    const int oi = (t + 1) & g_es.mask[r];
     double prob;
     if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
       const double gp = in.p_prev + in.yblank;
       const double ng = lae(in.pv + in.ylast, in.ng_prev + in.ylast);
       prob = lae(gp, ng);
-      out.prob = prob; out.gap = gp; out.nogap = ng; out.pad = 0;
+      out.prob(oi) = prob; out.gap(oi) = gp; out.nogap(oi) = ng;
     } else {
       prob = lae(in.pv + in.ylast, in.p_prev + in.yblank);
-      out.prob = prob;
+      out.prob(oi) = prob;
     }
-    *(wbase(a_slot[a], r) + ((t + 1) & g_es.mask[r])) = out;
     int lo = in.lo, hi = in.hi;
     if (t >= hi) { if (t > hi) lo = t; hi = t + 1; }
     else if (t < lo) { lo = t; hi = t + 1; }
@@ -300,15 +325,16 @@ struct Engine {
     __syncthreads();
     if (mine) p = update_commit(a, r, t, in);
     __syncthreads();
+    PCLK(11);
     return p;
   }
 
   // value a child reads from its frozen parent for an update at time t (the parent's entry at t-1)
-  __device__ __forceinline__ double frozen_at(const Ent* pwb, int t, int wmask, int plo, int phi, bool same) const {
+  __device__ __forceinline__ double frozen_at(const Ent& pwb, int t, int wmask, int plo, int phi, bool same) const {
     if (t - 1 < plo || t - 1 >= phi) return ninf();
-    const Ent* q = pwb + (t & wmask);
-    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) return same ? q->gap : q->prob;
-    else return q->prob;
+    const int q = t & wmask;
+    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) return same ? pwb.gap(q) : pwb.prob(q);
+    else return pwb.prob(q);
   }
 
   // ---- band sweep over the expanded beam (BeamSearch.h:361-375, :146-156), incremental ----------------
@@ -337,8 +363,8 @@ struct Engine {
     bool same = false;
     double p_prev = ninf(), ng_prev = ninf(), g_prev = ninf(), maxv = ninf();
     const int ts = r ? s1 : s0, te = r ? e1 : e0;
-    Ent* wb = nullptr;
-    const Ent* pwb = nullptr;
+    Ent wb, pwb;
+    wb.b = nullptr; wb.cap = 0; pwb.b = nullptr; pwb.cap = 0;
     int wmask = 0;
     const char* ylast_p = nullptr;
     const char* yblank_p = nullptr;
@@ -380,17 +406,16 @@ struct Engine {
       // clean part of the band: only the maximum is needed (independent loads, four in flight)
       {
         const int c0 = max(ts, lo), c1 = min(cs, hi);
-        for (int t = c0; t < c1; t += 4) {
-          double v0 = ninf(), v1 = ninf(), v2 = ninf(), v3 = ninf();
-          v0 = (wb + ((t + 1) & wmask))->prob;
-          if (t + 1 < c1) v1 = (wb + ((t + 2) & wmask))->prob;
-          if (t + 2 < c1) v2 = (wb + ((t + 3) & wmask))->prob;
-          if (t + 3 < c1) v3 = (wb + ((t + 4) & wmask))->prob;
-          maxv = fmax(fmax(maxv, v0), fmax(fmax(v1, v2), v3));
+        for (int t = c0; t < c1; t += 8) {
+          double v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = (t + q < c1) ? wb.prob((t + q + 1) & wmask) : ninf();
+          maxv = fmax(maxv, fmax(fmax(fmax(v[0], v[1]), fmax(v[2], v[3])), fmax(fmax(v[4], v[5]), fmax(v[6], v[7]))));
         }
       }
     }
     __syncthreads();
+    PCLK(1);
     const int Tb0 = sh[SH_TB0], Tb1 = sh[SH_TB1];
     const int Tb = r ? Tb1 : Tb0;  // first timestep of this read that needs the synchronised loop
     bool computing = false;        // p_prev / ng_prev hold the node's values at the previous timestep
@@ -399,9 +424,9 @@ struct Engine {
       const int limA = min(te, Tb);
       if (cs < limA) {
         if (cs - 1 >= lo && cs - 1 < hi) {
-          const Ent* se = wb + (cs & wmask);
-          p_prev = se->prob;
-          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { ng_prev = se->nogap; }
+          const int si = cs & wmask;
+          p_prev = wb.prob(si);
+          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { ng_prev = wb.nogap(si); }
         }
         computing = true;
         const char* row = ybase + (long)(yrc ? (yT - 1 - cs) : cs) * yrowb;
@@ -423,17 +448,16 @@ struct Engine {
             else if (pstat == PS_ROOT) pv_n = root_prob(r, t);
           }
           double prob;
-          Ent* o = wb + ((t + 1) & wmask);
+          const int oi = (t + 1) & wmask;
           if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
             const double gp = p_prev + yb;
             const double ng = lae(pv + yl, ng_prev + yl);
             prob = lae(gp, ng);
-            double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
-            *reinterpret_cast<double4*>(o) = v4;
+            wb.prob(oi) = prob; wb.gap(oi) = gp; wb.nogap(oi) = ng;
             ng_prev = ng; g_prev = gp;
           } else {
             prob = lae(pv + yl, p_prev + yb);
-            o->prob = prob;
+            wb.prob(oi) = prob;
           }
           p_prev = prob;
           if (prob > maxv) maxv = prob;
@@ -441,6 +465,7 @@ struct Engine {
         }
       }
     }
+    PCLK(2);
     // ---- phase B: synchronised time-major loop over [Tb, te)
     const int iters = max(max((reads_mask & 1) ? e0 - Tb0 : 0, (reads_mask & 2) ? e1 - Tb1 : 0), 0);
     if (iters > 0) {
@@ -453,9 +478,9 @@ struct Engine {
         const int tp = Tb - 1;
         if (computing) { pb.x = p_prev; pb.y = g_prev; }
         else if (tp >= lo && tp < hi) {
-          const Ent* se = wb + ((tp + 1) & wmask);
-          pb.x = se->prob;
-          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pb.y = se->gap;
+          const int si = (tp + 1) & wmask;
+          pb.x = wb.prob(si);
+          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pb.y = wb.gap(si);
         }
         pub[a * 2 + r] = pb;
         pchg[a * 2 + r] = computing;
@@ -465,6 +490,7 @@ struct Engine {
         else { ylast = (double)__ldg((const float*)ylast_p); yblank = (double)__ldg((const float*)yblank_p); }
       }
       __syncthreads();
+      PCLK(3);
       const double2* pub_rd = pub + (size_t)pa * 2 + r;
       double2* pub_wr = pub + (size_t)(a < EMAX ? a : 0) * 2 + r;
       const int pstride = EMAX * 2;
@@ -499,9 +525,9 @@ struct Engine {
               computing = true;
               p_prev = ninf(); ng_prev = ninf();
               if (t - 1 >= lo && t - 1 < hi) {
-                const Ent* se = wb + (t & wmask);
-                p_prev = se->prob;
-                if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_prev = se->nogap;
+                const int si = t & wmask;
+                p_prev = wb.prob(si);
+                if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_prev = wb.nogap(si);
               }
               if (t < cs) {
                 // dirtied inside its clean range: the clean maximum may include entries that change now
@@ -509,25 +535,24 @@ struct Engine {
                 maxv = ninf();
                 for (int q = ts; q < t; ++q) {
                   if (q >= lo && q < hi) {
-                    const double v = (wb + ((q + 1) & wmask))->prob;
+                    const double v = wb.prob((q + 1) & wmask);
                     if (v > maxv) maxv = v;
                   }
                 }
               }
             }
             double prob;
-            Ent* o = wb + ((t + 1) & wmask);
+            const int oi = (t + 1) & wmask;
             if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
               const double gp = p_prev + yb;
               const double ng = lae(pv + yl, ng_prev + yl);
               prob = lae(gp, ng);
-              double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
-              *reinterpret_cast<double4*>(o) = v4;
+              wb.prob(oi) = prob; wb.gap(oi) = gp; wb.nogap(oi) = ng;
               ng_prev = ng;
               pb.x = prob; pb.y = gp;
             } else {
               prob = lae(pv + yl, p_prev + yb);
-              o->prob = prob;
+              wb.prob(oi) = prob;
               pb.x = prob; pb.y = ninf();
             }
             p_prev = prob;
@@ -536,9 +561,9 @@ struct Engine {
             // still clean at t: hand the stored value to the children
             pb.x = ninf(); pb.y = ninf();
             if (t >= lo && t < hi) {
-              const Ent* se = wb + ((t + 1) & wmask);
-              pb.x = se->prob;
-              if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pb.y = se->gap;
+              const int si = (t + 1) & wmask;
+              pb.x = wb.prob(si);
+              if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pb.y = wb.gap(si);
             }
           }
           pub_wr[((it + 1) & 1) * pstride] = pb;
@@ -546,6 +571,7 @@ struct Engine {
         }
         __syncthreads();
       }
+      PCLK(4);
     }
     if (on) {
       if (te > ts) {
@@ -571,6 +597,7 @@ struct Engine {
       }
     }
     __syncthreads();
+    PCLK(5);
   }
 
   // ---- Beam::prune (Beam.h:93-108): rank by score desc, exact ties by creation order ----------
@@ -608,6 +635,7 @@ struct Engine {
       }
     }
     __syncthreads();
+    PCLK(6);
   }
 
   // ---- retire an active slot: write the header home, queue the node for reclamation ----
@@ -706,8 +734,10 @@ struct Engine {
     const int dmin = sh[SH_DMIN];
     const int fq_head = sh[SH_FQH], fq_tail = sh[SH_FQT];
     // pool pressure: recycle live retirees too (flagged; the reference never frees anything)
-    const bool force = (fq_tail - fq_head) < 8 * W + 16 && navail > 0;
+    const int virgin0 = sh[SH_VIRGIN];
+    const bool force = (fq_tail - fq_head) + (NP - virgin0) < 8 * W + 16 && navail > 0;
     __syncthreads();
+    PCLK(7);
     // -- phase X2: retire what the next expanded beam does not contain, freeze orphaned children, inspect the
     //    retire queue (entries queued in earlier steps only: a node retired now is still readable); the child
     //    threads compute their deterministic creation-order / trace-id offsets
@@ -745,6 +775,7 @@ struct Engine {
       first = tmpc[xb];
     }
     __syncthreads();
+    PCLK(8);
     // -- phase X3: consume the inspected queue entries (strictly from the head, up to the first live one);
     //    child threads create / revive the missing children
     {
@@ -766,17 +797,25 @@ struct Engine {
       if (tid == 4 * nb - 1) { sh[SH_TOTALLOC] = obase + (kind == KID_FRESH); sh[SH_TOTFIRST] = fbase + first; }
       if (kind != KID_ACTIVE) {
         const int ai = atomicSub(&sh[SH_AFREE], 1) - 1;
-        int pi = -1;
-        if (kind == KID_FRESH) pi = atomicAdd(&sh[SH_FQH], 1);
-        if (ai < 0 || (kind == KID_FRESH && pi >= fq_tail)) {
+        // a fresh node takes a recycled slot from the ring, else the next never-used slot: the pool slots in
+        // circulation (and with them the cache footprint of the windows) grow only to the live-node high-water mark
+        int slot = -1;
+        if (kind == KID_FRESH && ai >= 0) {
+          const int pi = atomicAdd(&sh[SH_FQH], 1);
+          if (pi < fq_tail) slot = freelist[pi % NP];
+          else {
+            atomicSub(&sh[SH_FQH], 1);
+            const int v = atomicAdd(&sh[SH_VIRGIN], 1);
+            if (v < NP) slot = v; else atomicSub(&sh[SH_VIRGIN], 1);
+          }
+        }
+        if (ai < 0 || (kind == KID_FRESH && slot < 0)) {
           // cannot happen while the reclamation keeps its margin; refuse to corrupt memory if it does
           atomicOr(&sh[SH_STATUS], POB_ST_POOL_OVERFLOW);
           atomicAdd(&sh[SH_AFREE], 1);
-          if (kind == KID_FRESH) atomicSub(&sh[SH_FQH], 1);
         } else {
           const int na = a_free[ai];
           if (kind == KID_FRESH) {
-            const int slot = freelist[pi % NP];
             const uint32_t order = (uint32_t)(sh[SH_ORDER] + obase);
             activate_fresh(na, slot, order, a, xc, my_tid);
             a_kid[4 * a + xc] = slot; a_kido[4 * a + xc] = order;
@@ -788,12 +827,14 @@ struct Engine {
       }
     }
     __syncthreads();
+    PCLK(9);
     // the first expansion of a beam node gives it its trace id (after every sibling has read the old value)
     if (xmine && xc == 0 && first) {
       a_tid[a] = sh[SH_TID] + fbase;
       trace[a_tid[a]] = ((uint32_t)a_ptid[a] << 2) | (uint32_t)a_last[a];
     }
     __syncthreads();
+    PCLK(10);
   }
 
   // ROW traversal while the beam is shorter than W (first row): the reference walks b < beam_width over a
@@ -816,11 +857,11 @@ struct Engine {
           const int ks = a_kid[4 * a + c];
           int ka = -1;
           if (ks >= 0) { const int x = slot2e[ks]; if (x >= 0 && a_order[x] == a_kido[4 * a + c]) ka = x; }
-          if (ka < 0 && sh[SH_AFREE] > 0 && sh[SH_FQT] - sh[SH_FQH] > 0) {
+          if (ka < 0 && sh[SH_AFREE] > 0 && (sh[SH_FQT] - sh[SH_FQH] > 0 || sh[SH_VIRGIN] < NP)) {
             ka = a_free[--sh[SH_AFREE]];
             if (ks >= 0 && hdr[ks].order == a_kido[4 * a + c]) activate_revived(ka, ks, a);
             else {
-              const int slot = freelist[(sh[SH_FQH]++) % NP];
+              const int slot = (sh[SH_FQT] - sh[SH_FQH] > 0) ? freelist[(sh[SH_FQH]++) % NP] : sh[SH_VIRGIN]++;
               const uint32_t order = (uint32_t)sh[SH_ORDER]++;
               activate_fresh(ka, slot, order, a, c, a_tid[a]);
               a_kid[4 * a + c] = slot; a_kido[4 * a + c] = order;
@@ -855,6 +896,9 @@ template <int MODEL>
 __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws) {
   const int tid = threadIdx.x, NT = blockDim.x;
   unsigned long long n_updates = 0;
+#ifdef POB_PHASE_CLOCKS
+  if (tid == 0) g_pclk_last = clock64();
+#endif
   // ---- engine state of this item: scalars + views of the CTA's global workspace
   if (tid == 0) {
     g_es.W = G.W; g_es.NP = G.NP; g_es.RQ = G.RQ; g_es.EMAX = G.EMAX; g_es.mode = G.mode;
@@ -864,8 +908,8 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     if (G.mode != MODE_1D) g_es.rv[1] = make_view(G.r[1], item); else { g_es.rv[1] = g_es.rv[0]; g_es.rv[1].T = 0; }
     char* q = ws;
     g_es.hdr = (NodeHdr*)q; q += sizeof(NodeHdr) * (size_t)G.NP;
-    g_es.win[0] = q; q += sizeof(Ent) * (size_t)G.NP * G.CAP0;
-    g_es.win[1] = q; q += sizeof(Ent) * (size_t)G.NP * G.CAP1;
+    g_es.win[0] = q; q += 8 * (size_t)Ent::arrays() * G.NP * G.CAP0;
+    g_es.win[1] = q; q += 8 * (size_t)Ent::arrays() * G.NP * G.CAP1;
     g_es.freelist = (int32_t*)q; q += 4 * (size_t)G.NP;
     g_es.retq = (int2*)q; q += 8 * (size_t)G.RQ;
     g_es.cum[0] = (double*)q; q += 8 * (size_t)(MODEL == POB_MODEL_CTC ? g_es.rv[0].T : 0);
@@ -879,18 +923,16 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
   int32_t* otop = G.out_top + 4 * (size_t)item;
 
   // ---- init pool and active slots
-  for (int s = tid; s < NP; s += NT) {
-    hdr[s].order = 0; hdr[s].state = -1;
-    freelist[s] = s;  // FIFO ring of free pool slots
-    slot2e[s] = -1;
-  }
+  // Pool slots: [0, nbase) go to the root's children, the rest are "virgin" (never used by this item, headers
+  // unwritten) until an allocation finds the FIFO ring of recycled slots empty.
+  for (int s = tid; s < NP; s += NT) slot2e[s] = -1;
   for (int a = tid; a < EMAX; a += NT) {
     a_slot[a] = -1; a_free[a] = EMAX - 1 - a; key[a] = make_double2(ninf(), 4.5e9);
     a_inbeam[a] = 0; a_needed[a] = 0;
   }
   if (tid == 0) {
     for (int k = 0; k < 32; ++k) sh[k] = 0;
-    sh[SH_FQH] = 0; sh[SH_FQT] = NP; sh[SH_AFREE] = EMAX; sh[SH_ORDER] = 1; sh[SH_TID] = 1;
+    sh[SH_FQH] = 0; sh[SH_FQT] = 0; sh[SH_VIRGIN] = 0; sh[SH_AFREE] = EMAX; sh[SH_ORDER] = 1; sh[SH_TID] = 1;
     sh[SH_DMIN] = 0x7fffffff; sh[SH_FIRSTALIVE] = 0x7fffffff;
     sh[SH_TB0] = 0x7fffffff; sh[SH_TB1] = 0x7fffffff;
   }
@@ -928,7 +970,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     n_updates += (mode != MODE_1D) ? 2 : 1;
   }
   if (tid == 0) {
-    sh[SH_FQH] = nbase; sh[SH_AFREE] = EMAX - nbase; sh[SH_ORDER] = 1 + nbase; sh[SH_NB] = nbase;
+    sh[SH_VIRGIN] = nbase; sh[SH_AFREE] = EMAX - nbase; sh[SH_ORDER] = 1 + nbase; sh[SH_NB] = nbase;
     sh[SH_NUSED] = nbase;
   }
   __syncthreads();
@@ -938,6 +980,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     if (mode != MODE_1D) update_all(tid < nbase, tid, 1, 0);
   }
 
+  PCLK(0);  // item setup + seed
   const int32_t* env = G.env ? G.env + 2 * G.env_off[item] : nullptr;
   const int32_t* envt = G.envt ? G.envt + 2 * G.envt_off[item] : nullptr;
   long nsteps = 0;
@@ -1097,6 +1140,19 @@ __global__ void backtrace_kernel(const uint32_t* __restrict__ trace, const int64
 }
 
 }  // namespace
+// debug export (not part of the ABI): cycles per engine phase, only in builds with -DPOB_PHASE_CLOCKS
+extern "C" int pob_debug_phase_clocks(unsigned long long* out32, int reset) {
+#ifdef POB_PHASE_CLOCKS
+  POB_CUDA(cudaMemcpyFromSymbol(out32, g_phase_clk, 32 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[32] = {0};
+    POB_CUDA(cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z)));
+  }
+  return POB_OK;
+#else
+  return POB_EUNSUPPORTED;
+#endif
+}
 double* g_pob_dbg_trace = nullptr;
 extern "C" int pob_debug_trace(pob_ctx* ctx, double* out, int n) {
   if (!g_pob_dbg_trace) return POB_EINVAL;
@@ -1106,7 +1162,7 @@ extern "C" int pob_debug_trace(pob_ctx* ctx, double* out, int n) {
 namespace {
 
 size_t ws_bytes(int model, int NP, int CAP0, int CAP1, int RQ, int Umax, int Vmax) {
-  const size_t es = model == POB_MODEL_CTC ? 8 : 32;
+  const size_t es = model == POB_MODEL_CTC ? 8 : 24;
   size_t b = sizeof(NodeHdr) * (size_t)NP + es * (size_t)NP * ((size_t)CAP0 + CAP1) + 4 * (size_t)NP + 8 * (size_t)RQ;
   if (model == POB_MODEL_CTC) b += 8 * ((size_t)Umax + Vmax + 2);
   b += 4 * ((size_t)Umax + 2);
@@ -1178,10 +1234,16 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   if (smem > 200 * 1024) return POB_EUNSUPPORTED;
   void (*kern)(BeamParams);
   const bool ctc = model == POB_MODEL_CTC;
+  int max_cta_sm = 0;  // 0 = as many as fit
+  if (const char* e = getenv("POB_DEBUG_CTA_PER_SM")) max_cta_sm = atoi(e);
   constexpr int M0 = POB_MODEL_CTC, M1 = POB_MODEL_CTC_MERGE_REPEATS;
   if (threads <= 64) { threads = 64; kern = ctc ? beam_kernel<M0, 64, 12> : beam_kernel<M1, 64, 12>; }
   else if (threads <= 128) { kern = ctc ? beam_kernel<M0, 128, 6> : beam_kernel<M1, 128, 6>; }
-  else if (threads <= 288) { kern = ctc ? beam_kernel<M0, 288, 3> : beam_kernel<M1, 288, 3>; }
+  else if (threads <= 288) {
+    kern = ctc ? beam_kernel<M0, 288, 3> : beam_kernel<M1, 288, 3>;
+    if (max_cta_sm == 2) kern = ctc ? beam_kernel<M0, 288, 2> : beam_kernel<M1, 288, 2>;
+    if (max_cta_sm == 1) kern = ctc ? beam_kernel<M0, 288, 1> : beam_kernel<M1, 288, 1>;
+  }
   else if (threads <= 512) { kern = ctc ? beam_kernel<M0, 512, 1> : beam_kernel<M1, 512, 1>; }
   else { kern = ctc ? beam_kernel<M0, 1024, 1> : beam_kernel<M1, 1024, 1>; }
   POB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1190,6 +1252,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   {
     int want_blocks = 2048 / threads;
     if (want_blocks > 12) want_blocks = 12;
+    if (max_cta_sm > 0 && want_blocks > max_cta_sm) want_blocks = max_cta_sm;
     int pct = (int)((want_blocks * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
     if (pct > 100) pct = 100;
     POB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
@@ -1197,6 +1260,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   int per_sm = 0;
   POB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) return POB_EUNSUPPORTED;
+  if (max_cta_sm > 0 && per_sm > max_cta_sm) per_sm = max_cta_sm;
   // Workspace: one stride per resident CTA.  Prefer a full wave of CTAs; when the pool of a wide-band batch
   // makes that too large for HBM, first run fewer CTAs, then (only if a single CTA still does not fit) shrink
   // the pool and rely on the overflow flag.
