@@ -7,8 +7,9 @@ Mbases/s, next to the reference CPU decoder on the host cores).
 
 A "step" is one pass of the hot path (viterbi x2 -> mapping -> banded NW -> envelope -> row_col beam
 search) over one batch of synthetic Bonito-shaped pairs (T ~ 5000, beam width 25, --reverse_complement).
-Weak scaling: every GPU gets its own `--pairs-per-gpu` pairs (default 1250 = 10k pairs / 8 GPUs, the
-configuration the metric is quoted on); pairs shard by pair, no data-path collective.
+The workload is BASELINE.json configs[2]: one 10k-pair batch (T ~ 5000, beam width 25); it fits one GPU, so every
+GPU decodes its own `--pairs-per-gpu` = 10000 pairs per step (weak scaling; pairs shard by pair, no data-path
+collective).  `--unique-pairs` distinct synthetic pairs are generated per rank and tiled to the batch size.
 """
 import argparse
 import ctypes as C
@@ -31,13 +32,15 @@ def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
-def make_pairs(first, count, T):
+def make_pairs(first, count, T, unique=None):
+    unique = min(count, unique or count)
     l1, l2 = [], []
-    for k in range(first, first + count):
+    for k in range(first, first + unique):
         p1, p2, _ = synth.make_pair(k, T)
         l1.append(synth.bonito_log_prob(p1))  # exactly what the reference loader hands to the decoders
         l2.append(synth.bonito_log_prob(p2))
-    return l1, l2
+    reps = -(-count // unique)
+    return (l1 * reps)[:count], (l2 * reps)[:count]
 
 
 class ClockSampler:
@@ -156,7 +159,8 @@ def run_reference(args):
 def workload_config(args, pairs_per_unit):
     return {"workload": "pair-decode of synthetic bonito pairs (2 reads, T~%d x5 CTC, --reverse_complement, "
                         "beam_width %d, padding 5, banded NW 500, row_col)" % (args.T, args.beam_width),
-            "pairs_per_gpu_per_step": pairs_per_unit, "T": args.T, "beam_width": args.beam_width,
+            "pairs_per_gpu_per_step": pairs_per_unit, "unique_pairs_per_gpu": min(pairs_per_unit, args.unique_pairs),
+            "T": args.T, "beam_width": args.beam_width,
             "cache": "inputs per step (%.0f MB/GPU) exceed the 126 MB L2" % (pairs_per_unit * 2.04 * args.T * 20 / 1e6),
             "sharding": "by pair, no collective"}
 
@@ -176,7 +180,7 @@ def run_ours(args):
     ctx = _lib.get_ctx(local)
     L = lib()
     P = args.pairs_per_gpu
-    l1, l2 = make_pairs(rank * P, P, args.T)
+    l1, l2 = make_pairs(rank * args.unique_pairs, P, args.T, args.unique_pairs)
     b1 = batch.ReadBatch(l1)
     b2 = batch.ReadBatch(l2, rc=np.ones(P, dtype=np.uint8))
     n = P
@@ -290,9 +294,9 @@ def run_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        reps = max(1, int(np.ceil(args.viterbi_reads / (2.0 * P))))
-        arrays = (l1 + l2) * reps
-        arrays = arrays[:args.viterbi_reads]
+        half = max(1, min(P, args.viterbi_reads // 2))
+        reps = max(1, int(np.ceil(args.viterbi_reads / (2.0 * half))))
+        arrays = ((l1[:half] + l2[:half]) * reps)[:args.viterbi_reads]
         vb = batch.ReadBatch(arrays)
         dv = dev_reads(vb)
         rows = vb.total_rows
@@ -354,10 +358,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs-per-gpu", type=int, default=1250)
+    ap.add_argument("--pairs-per-gpu", type=int, default=10000)
+    ap.add_argument("--unique-pairs", type=int, default=2500, help="distinct synthetic pairs per GPU (tiled to the batch)")
     ap.add_argument("--T", type=int, default=5000)
     ap.add_argument("--beam-width", type=int, default=25)
     ap.add_argument("--viterbi-reads", type=int, default=10000)

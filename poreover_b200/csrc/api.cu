@@ -110,15 +110,15 @@ int pob_align_banded(pob_ctx* ctx, int where, const uint8_t* seq1, const int64_t
     POB_TRY(stage_out(ctx, out_alen, (size_t)n, &d_alen));
     POB_TRY(stage_out(ctx, out_matches, (size_t)n, &d_match));
   }
-  const int64_t *d_moff, *d_rboff, *d_alnoff;
-  POB_TRY(upload(ctx, m_off, &d_moff));
+  const int64_t *d_rboff, *d_alnoff;
   POB_TRY(upload(ctx, rb_off, &d_rboff));
   POB_TRY(upload(ctx, aln_off, &d_alnoff));
-  int32_t *M, *rowband;
-  POB_TRY(pob_take(ctx, (size_t)m_off[n] + 1, &M));
+  int32_t* rowband;
   POB_TRY(pob_take(ctx, (size_t)rb_off[n] + 1, &rowband));
-  POB_TRY(pob_nw_launch(ctx, d_s1, d_o1, nullptr, d_s2, d_o2, nullptr, nullptr, n, band, match, mismatch, gap, SZ,
-                        d_moff, M, d_rboff, rowband, d_alnoff, d_a1, d_a2, d_alen, d_match));
+  std::vector<int64_t> cells(n);
+  for (int p = 0; p < n; ++p) cells[p] = m_off[p + 1] - m_off[p];
+  POB_TRY(nw_run_chunked(ctx, d_s1, d_o1, nullptr, d_s2, d_o2, nullptr, nullptr, n, band, match, mismatch, gap, SZ, cells,
+                         d_rboff, rowband, d_alnoff, d_a1, d_a2, d_alen, d_match));
   if (where == POB_HOST) {
     POB_TRY(copy_back(ctx, out_a1, d_a1, (size_t)aln_off[n]));
     POB_TRY(copy_back(ctx, out_a2, d_a2, (size_t)aln_off[n]));

@@ -56,18 +56,15 @@ struct __align__(16) NodeHdr {  // 128 bytes, home record of a node in the globa
   int32_t pad[2];
 };
 
-// A node's window for one read is a ring of `cap` time keys stored as separate arrays (structure of arrays):
-// prob[cap], and for the merge-repeats tree gap[cap], nogap[cap].  The band maximum scans only prob[], children read
-// prob[] or gap[] of their parent, the node itself prob[] and nogap[]: every access touches 8-byte values that sit
-// next to the values of neighbouring time keys, so a band occupies as few cache lines as possible.
 template <int MODEL>
-struct Win {
-  double* b;
-  int cap;
-  __device__ __forceinline__ double& prob(int i) const { return b[i]; }
-  __device__ __forceinline__ double& gap(int i) const { return b[cap + i]; }
-  __device__ __forceinline__ double& nogap(int i) const { return b[2 * cap + i]; }
-  static __host__ __device__ constexpr int arrays() { return MODEL == POB_MODEL_CTC_MERGE_REPEATS ? 3 : 1; }
+struct Entry;
+template <>
+struct __align__(32) Entry<POB_MODEL_CTC_MERGE_REPEATS> {
+  double prob, gap, nogap, pad;
+};
+template <>
+struct __align__(8) Entry<POB_MODEL_CTC> {
+  double prob;
 };
 
 struct BeamParams {
@@ -80,6 +77,8 @@ struct BeamParams {
   const int32_t* skip;      // per item != 0 -> not searched
   int n_items, W, mode, NP, CAP0, CAP1, RQ, EMAX;
   int dbg_noreclaim, dbg_noreuse;
+  int inspect_every;        // the retire queue is inspected every this many expansions (its headers are cold)
+  int prefetch;             // pull the probability rows / envelope entries of coming steps towards the SM
   double* dbg_trace;        // optional: [step][2] = (top score, sum of beam scores) after each prune
   char* ws;                 // workspace, one stride per resident CTA
   size_t ws_stride;
@@ -101,6 +100,9 @@ __device__ __forceinline__ double lae(double a, double b) {
   const float d = (float)(fmin(a, b) - m);
   return m + (double)log1pf(expf(d));
 }
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // physical address helpers for one read of the batch
 struct ReadView {
@@ -130,13 +132,13 @@ __device__ __forceinline__ ReadView make_view(const pob_reads& r, int item) {
 }
 
 enum { SH_NB = 0, SH_NUSED, SH_FQH, SH_FQT, SH_AFREE, SH_ORDER, SH_TID, SH_STAMP, SH_RQH, SH_RQT, SH_STATUS, SH_FIRSTALIVE,
-       SH_TOTALLOC, SH_TOTFIRST, SH_DMIN, SH_TB0, SH_TB1, SH_VIRGIN, SH_COUNT };
+       SH_TOTALLOC, SH_TOTFIRST, SH_DMIN, SH_TB0, SH_TB1, SH_XSTEP, SH_COUNT };
 
 // Per-CTA engine state.  Scalars and global-memory views live in a static __shared__ struct; the per-active-slot
 // arrays live in dynamic shared memory at offsets that depend only on EMAX / W / NP, so every access compiles
 // to LDS/STS (a pointer loaded from memory would be a generic pointer and cost a second, slower load).
 struct EngState {
-  int W, NP, RQ, EMAX, mode, noreclaim;
+  int W, NP, RQ, EMAX, mode, noreclaim, inspect_every;
   NodeHdr* hdr;
   char* win[2];
   int32_t* freelist;
@@ -222,13 +224,10 @@ extern __shared__ __align__(16) char pob_smem[];
 
 template <int MODEL>
 struct Engine {
-  typedef Win<MODEL> Ent;
+  typedef Entry<MODEL> Ent;
 
-  __device__ __forceinline__ Ent wbase(int slot, int r) const {
-    Ent w;
-    w.cap = g_es.cap[r];
-    w.b = reinterpret_cast<double*>(g_es.win[r]) + (size_t)slot * (Ent::arrays() * w.cap);
-    return w;
+  __device__ __forceinline__ Ent* wbase(int slot, int r) const {
+    return reinterpret_cast<Ent*>(g_es.win[r]) + (size_t)slot * g_es.cap[r];
   }
 
   // value of the root at time t (parent of depth-1 nodes)
@@ -264,11 +263,10 @@ struct Engine {
     const int last = a_last[a];
     in.lo = a_lo[2 * a + r]; in.hi = a_hi[2 * a + r];
     const bool self_ok = (t - 1 >= in.lo && t - 1 < in.hi);
-    const Ent se = wbase(slot, r);
-    const int si = t & g_es.mask[r];
-    in.p_prev = self_ok ? se.prob(si) : ninf();
+    const Ent* se = wbase(slot, r) + (t & g_es.mask[r]);
+    in.p_prev = self_ok ? se->prob : ninf();
     in.ng_prev = ninf();
-    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.ng_prev = self_ok ? se.nogap(si) : ninf();
+    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.ng_prev = self_ok ? se->nogap : ninf();
     in.ylast = g_es.rv[r].at(t, g_es.rv[r].pcol(last));
     in.yblank = g_es.rv[r].at(t, g_es.rv[r].cblank);
     const int ps = a_pstat[a];
@@ -281,10 +279,9 @@ struct Engine {
       if (ps == PS_INE) { const int pa = a_par[a]; plo = a_lo[2 * pa + r]; phi = a_hi[2 * pa + r]; }
       else { plo = a_plo[2 * a + r]; phi = a_phi[2 * a + r]; }
       if (t - 1 >= plo && t - 1 < phi) {
-        const Ent pe = wbase(a_pslot[a], r);
-        const int pi = t & g_es.mask[r];
-        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.pv = a_same[a] ? pe.gap(pi) : pe.prob(pi);
-        else in.pv = pe.prob(pi);
+        const Ent* pe = wbase(a_pslot[a], r) + (t & g_es.mask[r]);
+        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.pv = a_same[a] ? pe->gap : pe->prob;
+        else in.pv = pe->prob;
       } else {
         in.pv = ninf();
       }
@@ -293,18 +290,18 @@ struct Engine {
 
   __device__ __forceinline__ double update_commit(int a, int r, int t, const UpdIn& in) {
     POB_VIEWS
-    const Ent out = wbase(a_slot[a], r);
-    const int oi = (t + 1) & g_es.mask[r];
+    Ent out;
     double prob;
     if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
       const double gp = in.p_prev + in.yblank;
       const double ng = lae(in.pv + in.ylast, in.ng_prev + in.ylast);
       prob = lae(gp, ng);
-      out.prob(oi) = prob; out.gap(oi) = gp; out.nogap(oi) = ng;
+      out.prob = prob; out.gap = gp; out.nogap = ng; out.pad = 0;
     } else {
       prob = lae(in.pv + in.ylast, in.p_prev + in.yblank);
-      out.prob(oi) = prob;
+      out.prob = prob;
     }
+    *(wbase(a_slot[a], r) + ((t + 1) & g_es.mask[r])) = out;
     int lo = in.lo, hi = in.hi;
     if (t >= hi) { if (t > hi) lo = t; hi = t + 1; }
     else if (t < lo) { lo = t; hi = t + 1; }
@@ -330,11 +327,11 @@ struct Engine {
   }
 
   // value a child reads from its frozen parent for an update at time t (the parent's entry at t-1)
-  __device__ __forceinline__ double frozen_at(const Ent& pwb, int t, int wmask, int plo, int phi, bool same) const {
+  __device__ __forceinline__ double frozen_at(const Ent* pwb, int t, int wmask, int plo, int phi, bool same) const {
     if (t - 1 < plo || t - 1 >= phi) return ninf();
-    const int q = t & wmask;
-    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) return same ? pwb.gap(q) : pwb.prob(q);
-    else return pwb.prob(q);
+    const Ent* q = pwb + (t & wmask);
+    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) return same ? q->gap : q->prob;
+    else return q->prob;
   }
 
   // ---- band sweep over the expanded beam (BeamSearch.h:361-375, :146-156), incremental ----------------
@@ -363,8 +360,8 @@ struct Engine {
     bool same = false;
     double p_prev = ninf(), ng_prev = ninf(), g_prev = ninf(), maxv = ninf();
     const int ts = r ? s1 : s0, te = r ? e1 : e0;
-    Ent wb, pwb;
-    wb.b = nullptr; wb.cap = 0; pwb.b = nullptr; pwb.cap = 0;
+    Ent* wb = nullptr;
+    const Ent* pwb = nullptr;
     int wmask = 0;
     const char* ylast_p = nullptr;
     const char* yblank_p = nullptr;
@@ -406,11 +403,13 @@ struct Engine {
       // clean part of the band: only the maximum is needed (independent loads, four in flight)
       {
         const int c0 = max(ts, lo), c1 = min(cs, hi);
-        for (int t = c0; t < c1; t += 8) {
-          double v[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = (t + q < c1) ? wb.prob((t + q + 1) & wmask) : ninf();
-          maxv = fmax(maxv, fmax(fmax(fmax(v[0], v[1]), fmax(v[2], v[3])), fmax(fmax(v[4], v[5]), fmax(v[6], v[7]))));
+        for (int t = c0; t < c1; t += 4) {
+          double v0 = ninf(), v1 = ninf(), v2 = ninf(), v3 = ninf();
+          v0 = (wb + ((t + 1) & wmask))->prob;
+          if (t + 1 < c1) v1 = (wb + ((t + 2) & wmask))->prob;
+          if (t + 2 < c1) v2 = (wb + ((t + 3) & wmask))->prob;
+          if (t + 3 < c1) v3 = (wb + ((t + 4) & wmask))->prob;
+          maxv = fmax(fmax(maxv, v0), fmax(fmax(v1, v2), v3));
         }
       }
     }
@@ -424,9 +423,9 @@ struct Engine {
       const int limA = min(te, Tb);
       if (cs < limA) {
         if (cs - 1 >= lo && cs - 1 < hi) {
-          const int si = cs & wmask;
-          p_prev = wb.prob(si);
-          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { ng_prev = wb.nogap(si); }
+          const Ent* se = wb + (cs & wmask);
+          p_prev = se->prob;
+          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { ng_prev = se->nogap; }
         }
         computing = true;
         const char* row = ybase + (long)(yrc ? (yT - 1 - cs) : cs) * yrowb;
@@ -448,16 +447,17 @@ struct Engine {
             else if (pstat == PS_ROOT) pv_n = root_prob(r, t);
           }
           double prob;
-          const int oi = (t + 1) & wmask;
+          Ent* o = wb + ((t + 1) & wmask);
           if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
             const double gp = p_prev + yb;
             const double ng = lae(pv + yl, ng_prev + yl);
             prob = lae(gp, ng);
-            wb.prob(oi) = prob; wb.gap(oi) = gp; wb.nogap(oi) = ng;
+            double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
+            *reinterpret_cast<double4*>(o) = v4;
             ng_prev = ng; g_prev = gp;
           } else {
             prob = lae(pv + yl, p_prev + yb);
-            wb.prob(oi) = prob;
+            o->prob = prob;
           }
           p_prev = prob;
           if (prob > maxv) maxv = prob;
@@ -478,9 +478,9 @@ struct Engine {
         const int tp = Tb - 1;
         if (computing) { pb.x = p_prev; pb.y = g_prev; }
         else if (tp >= lo && tp < hi) {
-          const int si = (tp + 1) & wmask;
-          pb.x = wb.prob(si);
-          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pb.y = wb.gap(si);
+          const Ent* se = wb + ((tp + 1) & wmask);
+          pb.x = se->prob;
+          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pb.y = se->gap;
         }
         pub[a * 2 + r] = pb;
         pchg[a * 2 + r] = computing;
@@ -525,9 +525,9 @@ struct Engine {
               computing = true;
               p_prev = ninf(); ng_prev = ninf();
               if (t - 1 >= lo && t - 1 < hi) {
-                const int si = t & wmask;
-                p_prev = wb.prob(si);
-                if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_prev = wb.nogap(si);
+                const Ent* se = wb + (t & wmask);
+                p_prev = se->prob;
+                if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_prev = se->nogap;
               }
               if (t < cs) {
                 // dirtied inside its clean range: the clean maximum may include entries that change now
@@ -535,24 +535,25 @@ struct Engine {
                 maxv = ninf();
                 for (int q = ts; q < t; ++q) {
                   if (q >= lo && q < hi) {
-                    const double v = wb.prob((q + 1) & wmask);
+                    const double v = (wb + ((q + 1) & wmask))->prob;
                     if (v > maxv) maxv = v;
                   }
                 }
               }
             }
             double prob;
-            const int oi = (t + 1) & wmask;
+            Ent* o = wb + ((t + 1) & wmask);
             if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
               const double gp = p_prev + yb;
               const double ng = lae(pv + yl, ng_prev + yl);
               prob = lae(gp, ng);
-              wb.prob(oi) = prob; wb.gap(oi) = gp; wb.nogap(oi) = ng;
+              double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
+              *reinterpret_cast<double4*>(o) = v4;
               ng_prev = ng;
               pb.x = prob; pb.y = gp;
             } else {
               prob = lae(pv + yl, p_prev + yb);
-              wb.prob(oi) = prob;
+              o->prob = prob;
               pb.x = prob; pb.y = ninf();
             }
             p_prev = prob;
@@ -561,9 +562,9 @@ struct Engine {
             // still clean at t: hand the stored value to the children
             pb.x = ninf(); pb.y = ninf();
             if (t >= lo && t < hi) {
-              const int si = (t + 1) & wmask;
-              pb.x = wb.prob(si);
-              if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pb.y = wb.gap(si);
+              const Ent* se = wb + ((t + 1) & wmask);
+              pb.x = se->prob;
+              if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pb.y = se->gap;
             }
           }
           pub_wr[((it + 1) & 1) * pstride] = pb;
@@ -711,7 +712,6 @@ struct Engine {
     POB_VIEWS
     const int tid = threadIdx.x;
     const int nb = sh[SH_NB];
-    uint8_t* kindv = reinterpret_cast<uint8_t*>(tmpb);  // [4*nb] child classification
     // -- phase X1: classify the children of the beam.  A retired child that comes back is marked active right
     //    away so that the queue inspection of the next phase sees its queue entry as stale.
     const int xb = tid >> 2, xc = tid & 3;
@@ -726,16 +726,25 @@ struct Engine {
         if (ka >= 0 && a_order[ka] == a_kido[4 * a + xc]) { kind = KID_ACTIVE; a_needed[ka] = 1; }
         else if (hdr[ks].order == a_kido[4 * a + xc]) { kind = KID_REVIVE; hdr[ks].state = 0; }  // line now in L1 for X3
       }
-      kindv[tid] = (uint8_t)kind;
-      if (xc == 0) { a_needed[a] = 1; tmpc[xb] = a_tid[a] < 0; }
+      if (xc == 0) a_needed[a] = 1;
     }
+    // deterministic creation-order / trace-id offsets: prefix counts over the child threads (warp ballots + the
+    // per-warp totals in shared memory).  Fresh children are numbered in thread order; a beam node gets its trace
+    // id at its first expansion, numbered in beam order.
+    const unsigned lane = tid & 31, wid = tid >> 5;
+    const unsigned m_fresh = __ballot_sync(0xffffffffu, xmine && kind == KID_FRESH);
+    const unsigned m_first = __ballot_sync(0xffffffffu, xmine && xc == 0 && a_tid[xmine ? a : 0] < 0);
+    if (lane == 0) { tmpc[2 * wid] = __popc(m_fresh); tmpc[2 * wid + 1] = __popc(m_first); }
     const int head = sh[SH_RQH], tail = sh[SH_RQT];
-    const int navail = g_es.noreclaim ? 0 : min(tail - head, (int)blockDim.x);
-    const int dmin = sh[SH_DMIN];
     const int fq_head = sh[SH_FQH], fq_tail = sh[SH_FQT];
+    const int nfree = fq_tail - fq_head;
+    // Retired nodes' headers are cold (HBM): look at the queue only every few expansions, unless slots run short
+    const int xstep = sh[SH_XSTEP];
+    const bool inspect = !g_es.noreclaim && (xstep % g_es.inspect_every == 0 || nfree < 16 * W + 32);
+    const int navail = inspect ? min(tail - head, (int)blockDim.x) : 0;
+    const int dmin = sh[SH_DMIN];
     // pool pressure: recycle live retirees too (flagged; the reference never frees anything)
-    const int virgin0 = sh[SH_VIRGIN];
-    const bool force = (fq_tail - fq_head) + (NP - virgin0) < 8 * W + 16 && navail > 0;
+    const bool force = nfree < 8 * W + 16 && navail > 0;
     __syncthreads();
     PCLK(7);
     // -- phase X2: retire what the next expanded beam does not contain, freeze orphaned children, inspect the
@@ -770,9 +779,10 @@ struct Engine {
     }
     int obase = 0, fbase = 0, first = 0;
     if (xmine) {
-      for (int j = 0; j < tid; ++j) obase += kindv[j] == KID_FRESH;  // fresh children created before mine
-      for (int j = 0; j < xb; ++j) fbase += tmpc[j];                   // beam nodes first expanded before mine
-      first = tmpc[xb];
+      obase = __popc(m_fresh & ((1u << lane) - 1u));                 // fresh children created before mine
+      fbase = __popc(m_first & ((1u << (lane & ~3u)) - 1u));         // beam nodes first expanded before mine
+      first = (m_first >> (lane & ~3u)) & 1u;
+      for (unsigned w = 0; w < wid; ++w) { obase += tmpc[2 * w]; fbase += tmpc[2 * w + 1]; }
     }
     __syncthreads();
     PCLK(8);
@@ -790,32 +800,24 @@ struct Engine {
           retq[atomicAdd(&sh[SH_RQT], 1) % RQ] = make_int2(rslot, rstamp);  // look again one queue cycle later
         }
       }
-      if (tid == 0) sh[SH_RQH] = head + fa;
+      if (tid == 0) { sh[SH_RQH] = head + fa; sh[SH_XSTEP] = xstep + 1; }
     }
     if (xmine) {
       const int my_tid = first ? sh[SH_TID] + fbase : a_tid[a];  // trace id of the beam node (my parent)
       if (tid == 4 * nb - 1) { sh[SH_TOTALLOC] = obase + (kind == KID_FRESH); sh[SH_TOTFIRST] = fbase + first; }
       if (kind != KID_ACTIVE) {
         const int ai = atomicSub(&sh[SH_AFREE], 1) - 1;
-        // a fresh node takes a recycled slot from the ring, else the next never-used slot: the pool slots in
-        // circulation (and with them the cache footprint of the windows) grow only to the live-node high-water mark
-        int slot = -1;
-        if (kind == KID_FRESH && ai >= 0) {
-          const int pi = atomicAdd(&sh[SH_FQH], 1);
-          if (pi < fq_tail) slot = freelist[pi % NP];
-          else {
-            atomicSub(&sh[SH_FQH], 1);
-            const int v = atomicAdd(&sh[SH_VIRGIN], 1);
-            if (v < NP) slot = v; else atomicSub(&sh[SH_VIRGIN], 1);
-          }
-        }
-        if (ai < 0 || (kind == KID_FRESH && slot < 0)) {
+        int pi = -1;
+        if (kind == KID_FRESH) pi = atomicAdd(&sh[SH_FQH], 1);
+        if (ai < 0 || (kind == KID_FRESH && pi >= fq_tail)) {
           // cannot happen while the reclamation keeps its margin; refuse to corrupt memory if it does
           atomicOr(&sh[SH_STATUS], POB_ST_POOL_OVERFLOW);
           atomicAdd(&sh[SH_AFREE], 1);
+          if (kind == KID_FRESH) atomicSub(&sh[SH_FQH], 1);
         } else {
           const int na = a_free[ai];
           if (kind == KID_FRESH) {
+            const int slot = freelist[pi % NP];
             const uint32_t order = (uint32_t)(sh[SH_ORDER] + obase);
             activate_fresh(na, slot, order, a, xc, my_tid);
             a_kid[4 * a + xc] = slot; a_kido[4 * a + xc] = order;
@@ -857,11 +859,11 @@ struct Engine {
           const int ks = a_kid[4 * a + c];
           int ka = -1;
           if (ks >= 0) { const int x = slot2e[ks]; if (x >= 0 && a_order[x] == a_kido[4 * a + c]) ka = x; }
-          if (ka < 0 && sh[SH_AFREE] > 0 && (sh[SH_FQT] - sh[SH_FQH] > 0 || sh[SH_VIRGIN] < NP)) {
+          if (ka < 0 && sh[SH_AFREE] > 0 && sh[SH_FQT] - sh[SH_FQH] > 0) {
             ka = a_free[--sh[SH_AFREE]];
             if (ks >= 0 && hdr[ks].order == a_kido[4 * a + c]) activate_revived(ka, ks, a);
             else {
-              const int slot = (sh[SH_FQT] - sh[SH_FQH] > 0) ? freelist[(sh[SH_FQH]++) % NP] : sh[SH_VIRGIN]++;
+              const int slot = freelist[(sh[SH_FQH]++) % NP];
               const uint32_t order = (uint32_t)sh[SH_ORDER]++;
               activate_fresh(ka, slot, order, a, c, a_tid[a]);
               a_kid[4 * a + c] = slot; a_kido[4 * a + c] = order;
@@ -902,14 +904,14 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
   // ---- engine state of this item: scalars + views of the CTA's global workspace
   if (tid == 0) {
     g_es.W = G.W; g_es.NP = G.NP; g_es.RQ = G.RQ; g_es.EMAX = G.EMAX; g_es.mode = G.mode;
-    g_es.noreclaim = G.dbg_noreclaim;
+    g_es.noreclaim = G.dbg_noreclaim; g_es.inspect_every = G.inspect_every;
     g_es.cap[0] = G.CAP0; g_es.cap[1] = G.CAP1; g_es.mask[0] = G.CAP0 - 1; g_es.mask[1] = G.CAP1 - 1;
     g_es.rv[0] = make_view(G.r[0], item);
     if (G.mode != MODE_1D) g_es.rv[1] = make_view(G.r[1], item); else { g_es.rv[1] = g_es.rv[0]; g_es.rv[1].T = 0; }
     char* q = ws;
     g_es.hdr = (NodeHdr*)q; q += sizeof(NodeHdr) * (size_t)G.NP;
-    g_es.win[0] = q; q += 8 * (size_t)Ent::arrays() * G.NP * G.CAP0;
-    g_es.win[1] = q; q += 8 * (size_t)Ent::arrays() * G.NP * G.CAP1;
+    g_es.win[0] = q; q += sizeof(Ent) * (size_t)G.NP * G.CAP0;
+    g_es.win[1] = q; q += sizeof(Ent) * (size_t)G.NP * G.CAP1;
     g_es.freelist = (int32_t*)q; q += 4 * (size_t)G.NP;
     g_es.retq = (int2*)q; q += 8 * (size_t)G.RQ;
     g_es.cum[0] = (double*)q; q += 8 * (size_t)(MODEL == POB_MODEL_CTC ? g_es.rv[0].T : 0);
@@ -923,16 +925,18 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
   int32_t* otop = G.out_top + 4 * (size_t)item;
 
   // ---- init pool and active slots
-  // Pool slots: [0, nbase) go to the root's children, the rest are "virgin" (never used by this item, headers
-  // unwritten) until an allocation finds the FIFO ring of recycled slots empty.
-  for (int s = tid; s < NP; s += NT) slot2e[s] = -1;
+  for (int s = tid; s < NP; s += NT) {
+    hdr[s].order = 0; hdr[s].state = -1;
+    freelist[s] = s;  // FIFO ring of free pool slots
+    slot2e[s] = -1;
+  }
   for (int a = tid; a < EMAX; a += NT) {
     a_slot[a] = -1; a_free[a] = EMAX - 1 - a; key[a] = make_double2(ninf(), 4.5e9);
     a_inbeam[a] = 0; a_needed[a] = 0;
   }
   if (tid == 0) {
     for (int k = 0; k < 32; ++k) sh[k] = 0;
-    sh[SH_FQH] = 0; sh[SH_FQT] = 0; sh[SH_VIRGIN] = 0; sh[SH_AFREE] = EMAX; sh[SH_ORDER] = 1; sh[SH_TID] = 1;
+    sh[SH_FQH] = 0; sh[SH_FQT] = NP; sh[SH_AFREE] = EMAX; sh[SH_ORDER] = 1; sh[SH_TID] = 1;
     sh[SH_DMIN] = 0x7fffffff; sh[SH_FIRSTALIVE] = 0x7fffffff;
     sh[SH_TB0] = 0x7fffffff; sh[SH_TB1] = 0x7fffffff;
   }
@@ -970,7 +974,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     n_updates += (mode != MODE_1D) ? 2 : 1;
   }
   if (tid == 0) {
-    sh[SH_VIRGIN] = nbase; sh[SH_AFREE] = EMAX - nbase; sh[SH_ORDER] = 1 + nbase; sh[SH_NB] = nbase;
+    sh[SH_FQH] = nbase; sh[SH_AFREE] = EMAX - nbase; sh[SH_ORDER] = 1 + nbase; sh[SH_NB] = nbase;
     sh[SH_NUSED] = nbase;
   }
   __syncthreads();
@@ -1067,6 +1071,23 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
       if ((!rset || !cset) && tid == 0) sh[SH_STATUS] |= POB_ST_UNSET_BAND;
       row_end = min(row_end, V); col_end = min(col_end, U);
       if (!have_E) { expand_and_retire(-1, -1); have_E = true; }
+      // The probability rows and envelope entries of the coming steps are pulled towards the SM ahead of time: every
+      // step touches one new row per read, and without this each thread of the sweep waits for it to come from HBM.
+      if (G.prefetch) {
+        if (tid < 4) {
+          const int r = tid & 1;
+          const ReadView& pv = g_es.rv[r];
+          const int t = (r ? row_end : col_end) + ((tid & 2) ? 64 : 6);
+          if (t < pv.T) {
+            const char* q = (const char*)pv.base + (size_t)pv.prow(t) * pv.S * (pv.f64 ? 8 : 4);
+            if (tid & 2) prefetch_l2(q); else prefetch_l1(q);
+          }
+        } else if (tid < 6) {
+          const int ahead = 32;
+          if (tid == 4 && u + ahead < U) prefetch_l1(env + 2 * (u + ahead));
+          if (tid == 5 && v + ahead < V) prefetch_l1(envt + 2 * (v + ahead));
+        }
+      }
       sweep(3, col_start, col_end, row_start, row_end, G.dbg_noreuse != 0, n_updates);
       prune();
       dbg_record(G, nsteps);
@@ -1162,7 +1183,7 @@ extern "C" int pob_debug_trace(pob_ctx* ctx, double* out, int n) {
 namespace {
 
 size_t ws_bytes(int model, int NP, int CAP0, int CAP1, int RQ, int Umax, int Vmax) {
-  const size_t es = model == POB_MODEL_CTC ? 8 : 24;
+  const size_t es = model == POB_MODEL_CTC ? 8 : 32;
   size_t b = sizeof(NodeHdr) * (size_t)NP + es * (size_t)NP * ((size_t)CAP0 + CAP1) + 4 * (size_t)NP + 8 * (size_t)RQ;
   if (model == POB_MODEL_CTC) b += 8 * ((size_t)Umax + Vmax + 2);
   b += 4 * ((size_t)Umax + 2);
@@ -1216,6 +1237,10 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   if (const char* e = getenv("POB_DEBUG_NP")) P.NP = atoi(e);
   if (const char* e = getenv("POB_DEBUG_NORECLAIM")) P.dbg_noreclaim = atoi(e);
   if (const char* e = getenv("POB_DEBUG_NOREUSE")) P.dbg_noreuse = atoi(e);
+  P.inspect_every = 4;
+  if (const char* e = getenv("POB_DEBUG_INSPECT_EVERY")) P.inspect_every = atoi(e) > 0 ? atoi(e) : 1;
+  P.prefetch = 1;
+  if (const char* e = getenv("POB_DEBUG_PREFETCH")) P.prefetch = atoi(e);
   if (getenv("POB_DEBUG_TRACE")) {
     static double* dbg = nullptr;
     if (!dbg) cudaMalloc(&dbg, 200000 * sizeof(double));

@@ -269,9 +269,8 @@ int pob_pair_decode(pob_ctx* ctx, int where, const pob_reads_t* reads1, const po
     cons_off[p] = g1.off[p] + g2.off[p];
   }
   cons_off[n] = g1.off[n] + g2.off[n];
-  const int64_t *d_moff, *d_rboff, *d_alnoff, *d_envoff, *d_consoff;
+  const int64_t *d_rboff, *d_alnoff, *d_envoff, *d_consoff;
   const int32_t *d_skip_c, *d_status_c, *dU, *dV;
-  POB_TRY(upload(ctx, m_off, &d_moff));
   POB_TRY(upload(ctx, rb_off, &d_rboff));
   POB_TRY(upload(ctx, aln_off, &d_alnoff));
   POB_TRY(upload(ctx, env_off, &d_envoff));
@@ -283,16 +282,19 @@ int pob_pair_decode(pob_ctx* ctx, int where, const pob_reads_t* reads1, const po
   int32_t* d_skip = const_cast<int32_t*>(d_skip_c);
   POB_CUDA(cudaMemcpyAsync(d_status, d_status_c, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
   // ---- stage 2: banded alignment of the two basecalls (align.pyx:100-178)
-  int32_t *M, *rowband, *d_alen, *d_matches;
+  int32_t *rowband, *d_alen, *d_matches;
   uint8_t *d_a1, *d_a2;
-  POB_TRY(pob_take(ctx, (size_t)m_off[n] + 1, &M));
   POB_TRY(pob_take(ctx, (size_t)rb_off[n] + 1, &rowband));
   POB_TRY(pob_take(ctx, (size_t)aln_off[n] + 1, &d_a1));
   POB_TRY(pob_take(ctx, (size_t)aln_off[n] + 1, &d_a2));
   POB_TRY(pob_take(ctx, (size_t)n, &d_alen));
   POB_TRY(pob_take(ctx, (size_t)n, &d_matches));
-  POB_TRY(pob_nw_launch(ctx, d_seq1, d1.row_off, d_len1, d_seq2, d2.row_off, d_len2, d_skip, n, band_width, 2, -1, -1,
-                        SZ, d_moff, M, d_rboff, rowband, d_alnoff, d_a1, d_a2, d_alen, d_matches));
+  {
+    std::vector<int64_t> cells(n);
+    for (int p = 0; p < n; ++p) cells[p] = m_off[p + 1] - m_off[p];
+    POB_TRY(nw_run_chunked(ctx, d_seq1, d1.row_off, d_len1, d_seq2, d2.row_off, d_len2, d_skip, n, band_width, 2, -1,
+                           -1, SZ, cells, d_rboff, rowband, d_alnoff, d_a1, d_a2, d_alen, d_matches));
+  }
   identity_skip_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_alen, d_matches, n, d_skip, d_status);
   POB_CUDA(cudaGetLastError());
   // ---- stage 3: alignment columns -> envelope (envelope.py:26-87)

@@ -90,5 +90,39 @@ int upload(pob_ctx* ctx, const std::vector<T>& h, const T** dev) {
   return stage_in(ctx, h.data(), h.size(), dev);
 }
 
+// Banded NW + traceback over n pairs with at most NW_CELL_BUDGET score cells (int32) resident at a time: the
+// anti-diagonal-major matrix of a T~5000 pair is 16 MB, so a 10k-pair batch is aligned in chunks that reuse one
+// scratch matrix (same stream, so a chunk's traceback finishes before the next fill overwrites it).
+// cells[p] = matrix size of pair p (0 = skipped); all other per-pair arrays are device pointers indexed by pair.
+constexpr int64_t NW_CELL_BUDGET = (int64_t)8 << 30;  // 32 GB (the traceback is a latency-bound walk per pair: few, large chunks)
+int nw_run_chunked(pob_ctx* ctx, const uint8_t* s1, const int64_t* off1, const int32_t* len1, const uint8_t* s2,
+                   const int64_t* off2, const int32_t* len2, const int32_t* skip, int n, int band, int match,
+                   int mismatch, int gap, int SZ, const std::vector<int64_t>& cells, const int64_t* d_rboff,
+                   int32_t* rowband, const int64_t* d_alnoff, uint8_t* a1, uint8_t* a2, int32_t* alen,
+                   int32_t* matches) {
+  std::vector<int64_t> m_off((size_t)n + 1);
+  std::vector<int> starts(1, 0);
+  int64_t cur = 0, widest = 0;
+  for (int p = 0; p < n; ++p) {
+    if (cur > 0 && cur + cells[p] > NW_CELL_BUDGET) { starts.push_back(p); cur = 0; }
+    m_off[p] = cur;
+    cur += cells[p];
+    widest = std::max(widest, cur);
+  }
+  m_off[n] = cur;
+  starts.push_back(n);
+  const int64_t* d_moff;
+  POB_TRY(upload(ctx, m_off, &d_moff));
+  int32_t* M;
+  POB_TRY(pob_take(ctx, (size_t)widest + 1, &M));
+  for (size_t c = 0; c + 1 < starts.size(); ++c) {
+    const int p0 = starts[c], cnt = starts[c + 1] - p0;
+    POB_TRY(pob_nw_launch(ctx, s1, off1 + p0, len1 ? len1 + p0 : nullptr, s2, off2 + p0, len2 ? len2 + p0 : nullptr,
+                          skip ? skip + p0 : nullptr, cnt, band, match, mismatch, gap, SZ, d_moff + p0, M,
+                          d_rboff + p0, rowband, d_alnoff + p0, a1, a2, alen ? alen + p0 : nullptr,
+                          matches ? matches + p0 : nullptr));
+  }
+  return POB_OK;
+}
 
 }  // namespace

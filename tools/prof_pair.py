@@ -9,7 +9,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 444
 calls = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 5000
 W = int(sys.argv[4]) if len(sys.argv) > 4 else 25
-uniq = min(n, 64)
+uniq = min(n, int(os.environ.get('POB_PROF_UNIQUE', '64')))
 l1, l2 = [], []
 for k in range(uniq):
     p1, p2, _ = synth.make_pair(k, T)
