@@ -148,7 +148,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "consensus_mbases_per_s": r["bases_per_s"] / 1e6,
-        "config": workload_config(args, n_pairs),
+        "config": workload_config(args, args.pairs_per_gpu),  # the arm's workload; this run's bounded sample is in cpu_baseline
         "cpu_baseline": {"value": r["pairs_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["pairs_per_s"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

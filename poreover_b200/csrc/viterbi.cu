@@ -8,10 +8,11 @@
 //   mapping : timestep of each emitted base                                   pair_decode.py:114-142
 // Compare-only arithmetic, so results are bit-exact by construction.
 //
-// Fast path: one warp per read, float32, 5 states.  A lane owns 4 consecutive rows = 20 floats = five
-// 16-byte loads, so a warp consumes 2560 contiguous bytes per iteration; the next chunk's loads are
-// issued before the current chunk is reduced (2 x 2.5 KB in flight per warp).  HBM-bound: 20 B in per
-// timestep, ~2.4 B out.
+// Fast path: one warp per read, float32, 5 states.  A warp consumes the read in chunks of 128 rows = 2560
+// contiguous bytes.  Chunks are staged with cp.async (16-byte pieces, lane i copies bytes [16 i + 512 k), fully
+// coalesced: every 32-byte sector is requested exactly once) into a per-warp ring of STAGES chunk buffers in
+// shared memory, two chunks ahead of the one being reduced; a lane then reads "its" 4 consecutive rows (20
+// floats, five conflict-free LDS.128 at an 80-byte lane stride).  HBM-bound: 20 B in per timestep, ~2.4 B out.
 #include "common.cuh"
 
 namespace {
@@ -29,13 +30,20 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
   return x - v;
 }
 
-__device__ __forceinline__ float4 ldg_stream(const float4* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int STAGES = 3;            // chunk buffers per warp
+constexpr int CHUNK_FLOATS = 640;    // 32 groups x 4 rows x 5 states
 
 // first-index argmax of one row held in registers; cols are compile-time after inlining
 template <int LAYOUT>
@@ -67,38 +75,61 @@ __device__ __forceinline__ int argmax5(const float* r, bool rc) {
 // One read, one warp.  RC / KIND / PATH are compile-time so the per-row work is a handful of compares and
 // selects; chunks whose 32 groups are all complete take a path without per-row validity tests.
 template <int LAYOUT, bool RC, int KIND, bool PATH>
-__device__ __forceinline__ void viterbi5_read(const float* __restrict__ base, int T, int lane, uint8_t* __restrict__ oseq,
-                                              int32_t* __restrict__ os2s, int8_t* __restrict__ opath, int& nout_o,
-                                              int& pfirst_o, int& plast_o) {
+__device__ __forceinline__ void viterbi5_read(const float* __restrict__ base, int T, int lane, float* __restrict__ ring,
+                                              uint8_t* __restrict__ oseq, int32_t* __restrict__ os2s,
+                                              int8_t* __restrict__ opath, int& nout_o, int& pfirst_o, int& plast_o) {
   const int G = (T + 3) >> 2;          // groups of 4 rows
   const int Gfull = T >> 2;            // complete groups
   const int nch = (G + 31) >> 5;
   const bool aligned = (reinterpret_cast<uintptr_t>(base) & 15) == 0;
-  float cur[20], nxt[20];
-  auto load_group = [&](int c, float* dst) {
-    const int gi = (c << 5) + lane;
-    if (gi >= G) return;
-    const int g = RC ? (G - 1 - gi) : gi;
-    const float* p = base + (size_t)g * 20;
-    if (aligned && g < Gfull) {
-      const float4* q = reinterpret_cast<const float4*>(p);
+  float cur[20];
+  // Stage chunk c (logical groups [32c, 32c+32), a contiguous span of physical groups) into ring slot c % STAGES.
+  // Only bytes of this read are touched: whole 16-byte pieces, then the last 1-3 floats of a partial group.
+  auto stage_chunk = [&](int c) {
+    if (c < nch) {
+      const int ng = min(32, G - (c << 5));                         // groups in this chunk
+      const int gfirst = RC ? (G - (c << 5) - ng) : (c << 5);       // lowest physical group
+      const float* src = base + (size_t)gfirst * 20;
+      float* dst = ring + (c % STAGES) * CHUNK_FLOATS;
+      const int nf = min(ng * 20, T * 5 - gfirst * 20);             // floats of this read in the span
+      if (aligned) {
+        const int npieces = nf >> 2;
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const float4 v = ldg_stream(q + i);
-        dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+        for (int k = 0; k < 5; ++k) {
+          const int i = lane + 32 * k;
+          if (i < npieces) cp_async16(dst + 4 * i, src + 4 * i);
+        }
+        const int i = 4 * npieces + lane;
+        if (i < nf) cp_async4(dst + i, src + i);
+      } else {
+        for (int i = lane; i < nf; i += 32) cp_async4(dst + i, src + i);
       }
-    } else {
-      const int nv = min(20, (T - 4 * g) * 5);
-#pragma unroll
-      for (int i = 0; i < 20; ++i) dst[i] = (i < nv) ? __ldg(p + i) : 0.f;
     }
+    cp_async_commit();  // one group per call (possibly empty) keeps the wait arithmetic uniform
   };
   int carry = -1, nout = 0, pfirst = -1, plast = -1;
-  if (nch > 0) load_group(0, cur);
+#pragma unroll
+  for (int c = 0; c < STAGES - 1; ++c) stage_chunk(c);
   for (int c = 0; c < nch; ++c) {
-    if (c + 1 < nch) load_group(c + 1, nxt);
+    stage_chunk(c + STAGES - 1);
+    cp_async_wait<STAGES - 1>();  // chunk c has landed (this lane's copies; the other lanes' after the warp sync)
+    __syncwarp();
     const int gi = (c << 5) + lane;
     const int g = RC ? (G - 1 - gi) : gi;
+    {
+      // the lane's group inside the staged span
+      const int ng = min(32, G - (c << 5));
+      const int gl = RC ? (ng - 1 - lane) : lane;
+      if (lane < ng) {
+        const float4* q = reinterpret_cast<const float4*>(ring + (c % STAGES) * CHUNK_FLOATS + gl * 20);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const float4 v = q[i];
+          cur[4 * i] = v.x; cur[4 * i + 1] = v.y; cur[4 * i + 2] = v.z; cur[4 * i + 3] = v.w;
+        }
+      }
+    }
+    __syncwarp();  // every lane has read slot c % STAGES before a later iteration refills it
     // the chunk is "full" when all of its 32 groups are complete groups of the read
     const bool full = RC ? ((c << 5) + 31 < G && (G - 1 - (c << 5)) < Gfull) : ((c << 5) + 32 <= Gfull);
     int p[4];
@@ -174,9 +205,8 @@ __device__ __forceinline__ void viterbi5_read(const float* __restrict__ base, in
       }
     }
     nout += total;
-#pragma unroll
-    for (int i = 0; i < 20; ++i) cur[i] = nxt[i];
   }
+  cp_async_wait<0>();
   nout_o = nout;
   pfirst_o = __reduce_max_sync(0xffffffffu, pfirst);
   plast_o = __reduce_max_sync(0xffffffffu, plast);
@@ -188,6 +218,7 @@ viterbi5_f32_kernel(const float* __restrict__ data, const int64_t* __restrict__ 
                     const int32_t* __restrict__ row_len, const uint8_t* __restrict__ rcflag, int n,
                     uint8_t* __restrict__ out_seq, int32_t* __restrict__ out_s2s, int8_t* __restrict__ out_path,
                     int32_t* __restrict__ out_len, int32_t* __restrict__ out_status) {
+  __shared__ __align__(16) float s_ring[WARPS_PER_BLOCK][STAGES * CHUNK_FLOATS];
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= n) return;
@@ -198,9 +229,10 @@ viterbi5_f32_kernel(const float* __restrict__ data, const int64_t* __restrict__ 
   uint8_t* oseq = out_seq + ro;
   int32_t* os2s = out_s2s ? out_s2s + ro : nullptr;
   int8_t* opath = PATH ? out_path + ro : nullptr;
+  float* ring = s_ring[threadIdx.x >> 5];
   int nout, pfirst, plast;
-  if (rc) viterbi5_read<LAYOUT, true, KIND, PATH>(base, T, lane, oseq, os2s, opath, nout, pfirst, plast);
-  else viterbi5_read<LAYOUT, false, KIND, PATH>(base, T, lane, oseq, os2s, opath, nout, pfirst, plast);
+  if (rc) viterbi5_read<LAYOUT, true, KIND, PATH>(base, T, lane, ring, oseq, os2s, opath, nout, pfirst, plast);
+  else viterbi5_read<LAYOUT, false, KIND, PATH>(base, T, lane, ring, oseq, os2s, opath, nout, pfirst, plast);
   if (lane == 0) {
     out_len[r] = nout;
     int st = (T == 0) ? POB_ST_EMPTY : 0;
