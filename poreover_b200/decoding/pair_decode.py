@@ -5,8 +5,11 @@ pair_decode_helper, pair_decode), the argparse Namespace fields, the output file
 (SURVEY.md A.9).  Changed: pairs are not farmed out to a process pool one at a time
 (pair_decode.py:292-297); all pairs of a run go through pob_pair_decode in batches, and with several GPUs
 the batches are pulled from a host work queue by one process per GPU (poreover_b200/multigpu.py).
-Out of scope here, as in SURVEY.md section 2: --method split/align, --skip_matches, --single beam,
---algorithm prefix, --alignment full, --diagonal_envelope (they raise NotImplementedError).
+--alignment full, --diagonal_envelope and --skip_matches run the same kernels stage by
+stage (viterbi -> aligner -> envelope -> one batched search over whole pairs or over the boxes between anchors),
+with the anchor / box bookkeeping of pair_decode.py:412-452 on the host.
+Out of scope here, as in SURVEY.md section 2: --method split/align, --single beam, --algorithm prefix (they raise
+NotImplementedError).
 """
 import logging
 import os
@@ -54,7 +57,6 @@ _UNSUPPORTED = (
     ("method", "envelope", "--method split/align are deprecated in the reference and not on the GPU path"),
     ("single", "viterbi", "--single beam (re-squiggle) is not on the GPU path yet"),
     ("algorithm", "beam", "--algorithm prefix is the legacy search and not on the GPU path"),
-    ("alignment", "banded", "--alignment full is not on the GPU path yet"),
 )
 
 
@@ -62,10 +64,156 @@ def _check_args(args):
     for name, ok, why in _UNSUPPORTED:
         if getattr(args, name, ok) != ok:
             raise NotImplementedError(why)
-    if getattr(args, "skip_matches", False) or getattr(args, "diagonal_envelope", False):
-        raise NotImplementedError("--skip_matches / --diagonal_envelope are not on the GPU path yet")
     if getattr(args, "beam_search_method", "row_col") not in ("row", "row_col"):
         raise NotImplementedError("--beam_search_method grid is marked 'still testing' in the reference; not built")
+
+
+def _staged(args):
+    """True when a flag asks for something the fused pob_pair_decode call does not do."""
+    return (getattr(args, "alignment", "banded") == "full" or getattr(args, "skip_matches", False)
+            or getattr(args, "diagonal_envelope", False))
+
+
+def get_anchors(alignment, matches, indels):
+    """pair_decode.py:53-89: column ranges of long runs of matches / insertions / deletions.
+
+    alignment: 2 x C array of single characters.  Run-length encoding of the column states; a mismatch column
+    always starts a new run (and never forms an anchor), and -- as in the reference -- a run that reaches the
+    last column is never closed, so it yields no anchor."""
+    a1, a2 = np.asarray(alignment[0]), np.asarray(alignment[1])
+    n = len(a1)
+    if n == 0:
+        return [], []
+    state = np.where(a1 == a2, 0, np.where(a1 == '-', 1, np.where(a2 == '-', 2, 3)))  # mat ins del mis
+    new_run = np.ones(n, dtype=bool)
+    new_run[1:] = (state[1:] != state[:-1]) | (state[1:] == 3)
+    starts = np.flatnonzero(new_run)
+    ends = np.append(starts[1:], n)
+    names = ('mat', 'ins', 'del')
+    ranges, types = [], []
+    for s0, e0 in zip(starts[:-1], ends[:-1]):  # the final run is still open when the loop ends
+        st = state[s0]
+        if st == 3:
+            continue
+        if e0 - s0 >= (matches if st == 0 else indels):
+            ranges.append((int(s0), int(e0)))
+            types.append(names[st])
+    return ranges, types
+
+
+def _alignment_to_sequence(alignment):
+    """pair_decode.py:402-410: running count of non-gap characters per row (1-based at the first base)."""
+    return np.cumsum(np.asarray(alignment) != '-', axis=1)
+
+
+def _boxes_and_anchors(alignment, s2s1, s2s2, U, V, skip_threshold):
+    """pair_decode.py:412-452: anchors (start signal index, sequence) and the boxes of signal between them."""
+    a2s = _alignment_to_sequence(alignment)
+    anchor_ranges, anchor_type = get_anchors(alignment, matches=skip_threshold, indels=100)
+    assert len(anchor_ranges) > 0, \
+        'No matches/indels of sufficient length found in alignment. Try decreasing --matches or --indels'
+    anchors, boxes = [], []
+    for i, (cs, ce) in enumerate(anchor_ranges):
+        row = 1 if anchor_type[i] == 'ins' else 0
+        anchors.append((int(s2s1[a2s[0, cs]]), ''.join(alignment[row, cs:ce])))
+        if i > 0:
+            pe = anchor_ranges[i - 1][1]
+            boxes.append((int(s2s1[a2s[0, pe]]), int(s2s1[a2s[0, cs]]), int(s2s2[a2s[1, pe]]), int(s2s2[a2s[1, cs]])))
+        else:
+            boxes.append((0, int(s2s1[a2s[0, cs]]), 0, int(s2s2[a2s[1, cs]])))
+    le = anchor_ranges[-1][1]
+    boxes.append((int(s2s1[a2s[0, le]]), U, int(s2s2[a2s[1, le]]), V))
+    return anchors, boxes
+
+
+def _decode_pairs_staged(args, meta, m1, m2, kind, device):
+    """--alignment full / --diagonal_envelope / --skip_matches: pair_decode.py:357-531 stage by stage."""
+    n = len(meta)
+    rc2 = np.full(n, 1 if args.reverse_complement else 0, dtype=np.uint8)
+    model = decode.MODEL_TYPE[kind]
+    method = args.beam_search_method
+    out = [None] * n
+    U = [len(a) for a in m1]
+    V = [len(a) for a in m2]
+    if getattr(args, "diagonal_envelope", False):
+        # pair_decode.py:497-498; no 1D decoding, the helper returns (consensus fasta, summary) only (:525-527)
+        w = args.diagonal_width
+        envs = []
+        for u_, v_ in zip(U, V):
+            mid = (np.arange(u_) / u_ * v_).astype(int)
+            envs.append(np.stack([np.maximum(mid - w, 0), np.minimum(mid + w, v_)], axis=1))
+        seqs, _, _ = batch.beam_search_2d_batch(m1, m2, envs, args.beam_width, model, method, rc2=rc2, device=device)
+        for k, (in_path, path1, path2, _) in enumerate(meta):
+            out[k] = (fasta_format('consensus;{};{}'.format(args.method, path1.stem, path2.stem), seqs[k]),
+                      {'read1': in_path[0], 'read2': in_path[1]})
+        return out
+    seq1, map1, _, st1 = batch.viterbi_batch(m1, kind, device=device)
+    seq2, map2, _, st2 = batch.viterbi_batch(m2, kind, rc=rc2, device=device)
+    live = []
+    for k, (in_path, path1, path2, _) in enumerate(meta):
+        if (st1[k] | st2[k]) & batch._lib.ST_MAPPING_WRAP:
+            continue  # the reference's assertion (pair_decode.py:379) fires and the pool drops the pair
+        summary = {'read1': in_path[0], 'read2': in_path[1], 'length1': len(seq1[k]), 'length2': len(seq2[k])}
+        if abs(len(seq1[k]) - len(seq2[k])) > 1000:
+            summary['skipped'] = 1
+            out[k] = [summary]
+            continue
+        live.append(k)
+    if not live:
+        return out
+    if getattr(args, "alignment", "banded") == "full":
+        alns = batch.align_global_batch([seq1[k] for k in live], [seq2[k] for k in live], device=device)
+    else:
+        alns = batch.align_banded_batch([seq1[k] for k in live], [seq2[k] for k in live], device=device)
+    todo, arrs = [], {}
+    for k, al in zip(live, alns):
+        in_path = meta[k][0]
+        arr = np.array([list(al[0]), list(al[1])])
+        ident = np.sum(arr[0] == arr[1]) / len(arr[0])
+        summary = {'read1': in_path[0], 'read2': in_path[1], 'length1': len(seq1[k]), 'length2': len(seq2[k]),
+                   'sequence_identity': ident}
+        if ident < 0.5:
+            summary['skipped'] = 1
+            out[k] = [summary]
+            continue
+        summary['skipped'] = 0
+        out[k] = summary
+        arrs[k] = arr
+        todo.append(k)
+    if not todo:
+        return out
+    envs = batch.build_envelope_batch([(''.join(arrs[k][0]), ''.join(arrs[k][1])) for k in todo],
+                                      [map1[k] for k in todo], [map2[k] for k in todo], [U[k] for k in todo],
+                                      [V[k] for k in todo], padding=args.padding, device=device)
+    # one batched search over whole pairs, or over the boxes between anchors (pair_decode.py:512-522)
+    it1, it2, itenv, owner = [], [], [], []
+    pieces = {k: [] for k in todo}
+    for k, env in zip(todo, envs):
+        if not getattr(args, "skip_matches", False):
+            it1.append(m1[k]); it2.append(m2[k]); itenv.append(env); owner.append((k, 0))
+            continue
+        anchors, boxes = _boxes_and_anchors(arrs[k], map1[k], map2[k], U[k], V[k], args.skip_threshold)
+        pieces[k].extend(anchors)
+        y2 = m2[k]
+        for b in boxes:
+            e = env[b[0]:b[1]].copy()
+            if len(e) == 0:
+                raise IndexError("index 0 is out of bounds for axis 0 with size 0")  # pair_decode.py:516 on an empty box
+            v0, v1 = int(e[0, 0]), int(e[-1, 1])
+            # read 2 is a reverse-complement VIEW here: logical rows [v0, v1) are physical rows [V-v1, V-v0)
+            y2_ = y2[V[k] - v1:V[k] - v0] if args.reverse_complement else y2[v0:v1]
+            it1.append(m1[k][b[0]:b[1]]); it2.append(y2_); itenv.append(e - v0); owner.append((k, b[0]))
+    seqs, _, _ = batch.beam_search_2d_batch(it1, it2, itenv, args.beam_width, model, method,
+                                            rc2=np.full(len(it1), 1 if args.reverse_complement else 0, dtype=np.uint8),
+                                            device=device)
+    for (k, start), sq in zip(owner, seqs):
+        pieces[k].append((start, sq))
+    for k in todo:
+        in_path, path1, path2, _ = meta[k]
+        joined = ''.join(x[1] for x in sorted(pieces[k]))  # by first signal index, then sequence (:522)
+        out[k] = (fasta_format(in_path[0], seq1[k]) + fasta_format(in_path[1], seq2[k]),
+                  fasta_format('consensus;{};{}'.format(path1.stem, path2.stem), joined), out[k])
+    return out
 
 
 def _paths(args, in_path):
@@ -95,6 +243,9 @@ def decode_pairs(args, pair_list, device=None, chunk=1024):
         kind = meta[0][3]
         if kind == 'flipflop':
             raise NotImplementedError("flip-flop pair decoding is out of scope (README.md:97 of the reference)")
+        if _staged(args):
+            results[c0:c0 + len(sub)] = _decode_pairs_staged(args, meta, m1, m2, kind, device)
+            continue
         res = batch.pair_decode_batch(m1, m2, kind=kind, beam_width=args.beam_width, padding=args.padding,
                                       method=args.beam_search_method, rc2=bool(args.reverse_complement),
                                       device=device)
@@ -128,7 +279,7 @@ def pair_decode_helper(args):
     r = decode_pairs(args, [in_path])[0]
     if r is None:
         raise AssertionError("len(sequence_to_signal) != len(basecall) (pair_decode.py:379)")
-    return r
+    return r  # 3-tuple, [summary] when skipped, or (consensus fasta, summary) with --diagonal_envelope (:525-527)
 
 
 def write_results(args, results, out_1d_f, out_2d_f, log_f):
@@ -141,6 +292,11 @@ def write_results(args, results, out_1d_f, out_2d_f, log_f):
             print(x[0], file=out_1d_f)
             print(x[1], file=out_2d_f)
             print('\t'.join(map(str, [x[2].get(k, "") for k in keys])), file=log_f)
+        elif len(x) == 2:
+            # --diagonal_envelope: the reference's callback drops this shape silently (pair_decode.py:272-283 only
+            # handles 3 and 1); the consensus is written here because that is what the flag is for
+            print(x[0], file=out_2d_f)
+            print('\t'.join(map(str, [x[1].get(k, "") for k in keys])), file=log_f)
         elif len(x) == 1:
             print('\t'.join(map(str, [x[0].get(k, "") for k in keys])), file=log_f)
 
@@ -172,7 +328,8 @@ def pair_decode(args):
             print('# ' + '\t'.join(["read1", "read2", "length1", "length2", "sequence_identity", "skipped"]), file=lf)
             write_results(args, results, f1, f2, lf)
     else:
-        seqs_1d, seq_2d, summary = pair_decode_helper(args)
+        r = pair_decode_helper(args)
+        seq_2d, summary = (r[1], r[2]) if len(r) == 3 else ((r[0], r[1]) if len(r) == 2 else ("", r[0]))
         print(summary, file=sys.stderr)
         with open(args.out + '.fasta', 'w') as out_fasta:
             print(seq_2d, file=out_fasta)

@@ -1,0 +1,106 @@
+"""Golden fixture for the pair-decode flags of SURVEY.md section 8(f): --skip_matches, --alignment full and
+--diagonal_envelope.  Runs the REAL reference's pair_decode_helper (same scratch build as make_golden.py) on
+synthetic bonito pairs that the tests regenerate from their seeds (poreover_b200.synth.save_pair), and records
+only the outputs in tests/golden/flags.npz.  Run in the build container only."""
+import json
+import os
+import sys
+import tempfile
+from argparse import Namespace
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import make_golden as mg  # noqa: E402
+
+# (name, pair seed, T, beam width, flag overrides)
+CASES = [
+    ("skip_a", 20, 1500, 25, {"skip_matches": True}),
+    ("skip_b", 21, 2500, 5, {"skip_matches": True, "skip_threshold": 6}),
+    ("skip_c", 22, 1000, 25, {"skip_matches": True, "skip_threshold": 15, "padding": 10}),
+    ("skip_d", 27, 1500, 5, {"skip_matches": True}),
+    ("skip_e", 28, 2000, 25, {"skip_matches": True, "skip_threshold": 8}),
+    ("skip_f", 29, 1200, 25, {"skip_matches": True, "skip_threshold": 12}),
+    ("skip_g", 30, 3000, 5, {"skip_matches": True, "skip_threshold": 5}),
+    ("full_a", 23, 600, 25, {"alignment": "full"}),
+    ("full_skip", 24, 800, 5, {"alignment": "full", "skip_matches": True}),
+    ("diag_a", 25, 800, 25, {"diagonal_envelope": True}),
+    ("diag_b", 26, 1200, 5, {"diagonal_envelope": True, "diagonal_width": 30}),
+]
+
+
+# seen to differ between runs of the reference even when three consecutive runs agree (1234 vs 1235 bases)
+KNOWN_UNSTABLE = {"skip_g"}
+
+
+def namespace(f1, f2, d, W, over):
+    base = {"in": [f1, f2], "dir": d, "basecaller": "bonito", "reverse_complement": True, "out": "out", "threads": 1,
+            "method": "envelope", "single": "viterbi", "logging": "info", "debug": False, "algorithm": "beam",
+            "alignment": "banded", "beam_width": W, "debug_envelope": False, "diagonal_envelope": False,
+            "diagonal_width": 50, "padding": 5, "skip_matches": False, "skip_threshold": 10,
+            "beam_search_method": "row_col", "window": 200}
+    base.update(over)
+    return Namespace(**base)
+
+
+def run_case(i, tmp):
+    """One case in THIS process (called in a child: the reference's C++ search has undefined behaviour on some
+    boxed sub-envelopes -- SURVEY.md A.8 -- and takes the interpreter down with it)."""
+    scratch = os.environ.get("POREOVER_REF_SCRATCH", os.path.join(tempfile.gettempdir(), "ref_scratch"))
+    os.makedirs(scratch, exist_ok=True)
+    mg.build_reference(scratch)
+    import warnings
+    warnings.simplefilter("ignore")
+    from poreover.decoding import pair_decode
+    from poreover_b200 import synth
+    name, k, T, W, over = CASES[i]
+    f1, f2 = synth.save_pair(tmp, k, T)
+    r = pair_decode.pair_decode_helper(namespace(f1, f2, tmp, W, over))
+    clean = lambda d: {k_: (float(v) if isinstance(v, (float, np.floating)) else v) for k_, v in d.items()}
+    if len(r) == 3:
+        res = {"len": 3, "fasta1d": r[0], "fasta2d": r[1], "summary": clean(r[2])}
+    elif len(r) == 2:
+        res = {"len": 2, "fasta2d": r[0], "summary": clean(r[1])}
+    else:
+        res = {"len": 1, "summary": clean(r[0])}
+    print("RESULT" + json.dumps(res))
+
+
+def main():
+    import subprocess
+    tmp = tempfile.mkdtemp()
+    G = {"cases": json.dumps(CASES)}
+    for i, (name, k, T, W, over) in enumerate(CASES):
+        runs = []
+        for rep in range(3):  # the reference is not always deterministic here (address-ordered ties, UB): keep stable cases
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", str(i), tmp], capture_output=True,
+                               text=True)
+            lines = [l for l in p.stdout.splitlines() if l.startswith("RESULT")]
+            runs.append(None if (p.returncode != 0 or not lines) else lines[-1][6:])
+        if any(r is None for r in runs):
+            G[name + "_crashed"] = 1
+            print(name, "reference crashed in", sum(r is None for r in runs), "of 3 runs")
+            continue
+        if len(set(runs)) > 1 or name in KNOWN_UNSTABLE:
+            G[name + "_unstable"] = 1
+            print(name, "reference output differs between runs")
+            continue
+        res = json.loads(runs[0])
+        G[name + "_len"] = res["len"]
+        for key in ("fasta1d", "fasta2d"):
+            if key in res:
+                G[name + "_" + key] = res[key]
+        G[name + "_summary"] = json.dumps(res["summary"])
+        print(name, res["len"], len(res.get("fasta2d", "")))
+    out = os.path.join(HERE, "flags.npz")
+    np.savez_compressed(out, **G)
+    print("wrote", out, os.path.getsize(out) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--case":
+        run_case(int(sys.argv[2]), sys.argv[3])
+    else:
+        main()

@@ -125,3 +125,27 @@ def test_work_queue_two_ranks_gloo(tmp_path):
     assert [tuple(x[:2]) for x in r["out"]] == [(i, i * i) for i in range(103)]
     assert sum(r["counts"]) == 103 and all(c > 0 for c in r["counts"])
     assert {x[2] for x in r["out"]} == {0, 1}  # both ranks pulled work from the shared queue
+
+
+def test_get_anchors_matches_reference_loop():
+    """The vectorised get_anchors against a literal transcription of the reference loop's rules on random alignments."""
+    from poreover_b200.decoding.pair_decode import get_anchors
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        n = int(rng.integers(1, 400))
+        a1 = rng.choice(list("ACGT-"), size=n, p=[0.23, 0.23, 0.23, 0.23, 0.08])
+        a2 = np.where(rng.random(n) < 0.8, a1, rng.choice(list("ACGT-"), size=n))
+        both = (a1 == '-') & (a2 == '-')
+        a2[both] = 'A'
+        ranges, types = [], []
+        start, count, prev = 0, 1, 'START'
+        for i in range(n):
+            st = 'mat' if a1[i] == a2[i] else ('ins' if a1[i] == '-' else ('del' if a2[i] == '-' else 'mis'))
+            if prev == st and st != 'mis':
+                count += 1
+            else:
+                if (prev in ('ins', 'del') and count >= 3) or (prev == 'mat' and count >= 4):
+                    ranges.append((start, i)); types.append(prev)
+                prev, count, start = st, 1, i
+        got = get_anchors(np.array([a1, a2]), matches=4, indels=3)
+        assert got == (ranges, types)
