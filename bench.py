@@ -319,8 +319,18 @@ def run_ours(args):
         alg_bytes = float(vb.lens.sum()) * 20 + float(lens.sum()) * 5 + vb.n * 8  # 20T in, L bases + 4L mapping out
         t_ms = vp["ms"] / vp["launches"]
         ach = alg_bytes / (t_ms / 1e3) / 1e9
+        # DRAM traffic of one launch of this kernel on this workload, from the committed ncu --set full capture
+        traffic, traffic_src = None, None
+        try:
+            ns = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01_c.json")))["viterbi5_f32_kernel"]
+            if vb.n == 10000 and args.T == 5000:
+                traffic = ns["dram_traffic_bytes_per_launch"]
+                traffic_src = "profiles/ncu_summary_r01_c.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)"
+        except (OSError, ValueError, KeyError):
+            pass
         roof = {"kernel": "viterbi_ctc (%d reads, T=%d, %.2f GB in)" % (vb.n, args.T, float(vb.lens.sum()) * 20 / 1e9),
-                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "peak_source": peak_src, "ms_per_launch": t_ms}
         bk = prof.get("beam_pair", {"ms": 0.0, "launches": 1})
         tot_ms = sum(v["ms"] for v in prof.values())
