@@ -107,7 +107,7 @@ int pob_memcpy_d2h(pob_ctx* ctx, void* dst, const void* src, size_t bytes); /* a
 /* Per-kernel device timing with CUDA events on the context's stream.  ids: POB_K_* */
 enum {
   POB_K_VITERBI = 0, POB_K_FLIPFLOP = 1, POB_K_NW_FILL = 2, POB_K_NW_TRACE = 3, POB_K_ENVELOPE = 4,
-  POB_K_BEAM_2D = 5, POB_K_BEAM_1D = 6, POB_K_BACKTRACE = 7, POB_K_FORWARD = 8, POB_K_COUNT = 9
+  POB_K_BEAM_2D = 5, POB_K_BEAM_1D = 6, POB_K_BACKTRACE = 7, POB_K_FORWARD = 8, POB_K_ACCEPTOR = 9, POB_K_COUNT = 10
 };
 /* whole-region device timing: CUDA events recorded on the context's stream */
 int pob_timer_start(pob_ctx* ctx);
@@ -195,6 +195,15 @@ int pob_beam_search_2d(pob_ctx* ctx, int where, const pob_reads_t* reads1, const
  * labels: packed base indices 0..3 at lab_off[n+1]. */
 int pob_forward(pob_ctx* ctx, int where, const pob_reads_t* reads, const uint8_t* labels, const int64_t* lab_off,
                 int model, double* out_logp);
+
+/* Banded Viterbi acceptor ("re-squiggle"): best alignment of a known base sequence to a read.
+ * replaces: decoding_cpp.cpp_viterbi_acceptor (decoding_cpp.pyx:69-84) -> viterbi_acceptor_poreover (Forward.h:14-121),
+ *           called by pair-decode --single beam (pair_decode.py:363-370) with band_size = 1000.
+ * labels: packed base indices 0..3 at lab_off[n+1].  out_path: int8 per timestep, packed by reads->row_off:
+ * n_states-1 (blank) or the base index emitted there.  out_status[n]: POB_ST_UNSET_BAND where the reference's
+ * traceback leaves the matrix with labels unplaced (it does not terminate there); POB_ST_EMPTY for empty reads. */
+int pob_viterbi_acceptor(pob_ctx* ctx, int where, const pob_reads_t* reads, const uint8_t* labels,
+                         const int64_t* lab_off, int band_size, int8_t* out_path, int32_t* out_status);
 
 /* ---------------------------------------------------------------------------------------------
  * The whole pair-decode hot path on the device, no host round trip between stages.

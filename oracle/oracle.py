@@ -229,6 +229,23 @@ def forward(y, label, model="ctc", backend="port"):
     return ref().ref_forward(_p(y, c_dp), T, S, label.encode(), model.encode())
 
 
+def viterbi_acceptor(y, label, band_size=1000, backend="port"):
+    """decoding_cpp.cpp_viterbi_acceptor (decoding_cpp.pyx:69-84): int array of length T, 4 = gap."""
+    y = _f64(y)
+    T, S = y.shape
+    path = np.zeros(T, dtype=np.int8)
+    if backend == "port":
+        lab = np.array(["ACGT".index(c) for c in label], dtype=np.uint8)
+        rc = port().orc_viterbi_acceptor(_p(y, c_dp), T, S, int(band_size), _p(lab, c_bp), len(lab),
+                                         path.ctypes.data_as(C.POINTER(C.c_int8)))
+        if rc != 0:
+            raise RuntimeError("traceback leaves the matrix (the reference does not terminate here)")
+    else:
+        ref().ref_viterbi_acceptor(_p(y, c_dp), T, S, int(band_size), label.encode(),
+                                   path.ctypes.data_as(C.POINTER(C.c_int8)))
+    return path.astype(np.int64)
+
+
 # ---------------------------------------------------------------- full pair path (pair_decode.py:305-531)
 def pair_decode(lp1, lp2, kind="bonito", beam_width=25, padding=5, method="row_col", backend="port",
                 band_width=500, with_score=False):

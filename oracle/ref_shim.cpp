@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "BeamSearch.h"
+#include "Forward.h"
 
 namespace {
 
@@ -198,6 +199,15 @@ double ref_forward(const double* y, int T, int S, const char* label, const char*
   auto p = row_ptrs(y, T, S);
   std::string alphabet("ACGT", S - 1);
   return forward(p.data(), T, std::string(label), alphabet, std::string(model));
+}
+
+// decoding_cpp.pyx:69-84 -> Forward.h:14 (prints "Mapping label" on stdout, as the reference does)
+int ref_viterbi_acceptor(const double* y, int T, int S, int band, const char* label, signed char* path_out) {
+  auto p = row_ptrs(y, T, S);
+  std::string alphabet("ACGT", S - 1);
+  std::string path = viterbi_acceptor_poreover(p.data(), T, band, std::string(label), alphabet);
+  for (int t = 0; t < T && t < (int)path.size(); ++t) path_out[t] = (signed char)(path[t] - '0');
+  return 0;
 }
 
 }  // extern "C"

@@ -23,7 +23,7 @@ ST_SHORT_BEAM_SKIP, ST_UNSET_BAND, ST_POOL_OVERFLOW, ST_MAPPING_WRAP = 1, 2, 4, 
 ST_SKIPPED_LENGTH, ST_SKIPPED_IDENTITY, ST_EMPTY = 16, 32, 64
 
 K_NAMES = ["viterbi_ctc", "viterbi_flipflop", "nw_band_fill", "nw_traceback", "envelope", "beam_pair",
-           "beam_single", "backtrace", "forward"]
+           "beam_single", "backtrace", "forward", "acceptor"]
 
 vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
 
@@ -58,6 +58,7 @@ SIGNATURES = {
     "pob_beam_search": (i32, [vp, i32, vp, i32, i32, vp, vp, vp, vp]),
     "pob_beam_search_2d": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "pob_forward": (i32, [vp, i32, vp, vp, vp, i32, vp]),
+    "pob_viterbi_acceptor": (i32, [vp, i32, vp, vp, vp, i32, vp, vp]),
     "pob_pair_decode": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "pob_counters": (i32, [vp, vp]),
 }

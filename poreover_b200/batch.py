@@ -294,6 +294,35 @@ def forward_batch(arrays, labels, model="ctc", rc=None, layout=_lib.BLANK_LAST, 
     return out[:n].copy()
 
 
+def viterbi_acceptor_batch(arrays, labels, band_size=1000, rc=None, layout=_lib.BLANK_LAST, device=None):
+    """Best alignment of each label string to its read.  Returns (paths, status): int64 arrays of length T with
+    4 (n_states-1) for blank or the base index emitted at that timestep.
+
+    replaces decoding_cpp.cpp_viterbi_acceptor (decoding_cpp.pyx:69-84, Forward.h:14-121)."""
+    b = _as_batch(arrays, rc, layout)
+    n = b.n
+    ctx = get_ctx(device)
+    for lab, T in zip(labels, b.lens):
+        if len(lab) == 0:
+            raise IndexError("viterbi_acceptor: empty label (the reference reads label_int[0], Forward.h:51)")
+    idx = [np.frombuffer(l.encode(), dtype=np.uint8) for l in labels]
+    lut = np.full(256, 255, dtype=np.uint8)
+    lut[np.frombuffer(b"ACGT", dtype=np.uint8)] = np.arange(4, dtype=np.uint8)
+    lab_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in idx], out=lab_off[1:])
+    lab = np.zeros(int(lab_off[-1]) + 8, dtype=np.uint8)
+    for x, o in zip(idx, lab_off[:-1]):
+        lab[o:o + len(x)] = lut[x]
+    if (lab[:int(lab_off[-1])] > 3).any():
+        raise KeyError("viterbi_acceptor: label characters must be in ACGT")
+    path = np.zeros(max(b.total_rows, 1) + 4, dtype=np.int8)
+    st = np.zeros(max(n, 1), dtype=np.int32)
+    rs = b.struct()
+    check(lib().pob_viterbi_acceptor(ctx.h, _lib.HOST, C.byref(rs), ptr(lab), ptr(lab_off), int(band_size), ptr(path),
+                                     ptr(st)), "pob_viterbi_acceptor")
+    return [path[o:o + t].astype(np.int64) for o, t in zip(b.row_off[:-1], b.lens)], st[:n].copy()
+
+
 def align_global_batch(seqs1, seqs2, match=2, mismatch=-1, gap_cost=-1, return_dp=False, device=None):
     """Full Needleman-Wunsch for many pairs.  Returns list of (row1, row2, matches[, dp]).
 

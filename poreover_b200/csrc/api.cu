@@ -210,6 +210,60 @@ int pob_forward(pob_ctx* ctx, int where, const pob_reads_t* reads, const uint8_t
   return POB_OK;
 }
 
+int pob_viterbi_acceptor(pob_ctx* ctx, int where, const pob_reads_t* reads, const uint8_t* labels,
+                         const int64_t* lab_off, int band_size, int8_t* out_path, int32_t* out_status) {
+  if (!ctx) return POB_EINVAL;
+  POB_TRY(check_reads(reads, 2, 9));
+  if (reads->dtype != POB_F32 && reads->dtype != POB_F64) return POB_EINVAL;
+  if (band_size < 1) return POB_EINVAL;
+  const int n = reads->n;
+  if (n == 0) return POB_OK;
+  if (!labels || !lab_off || !out_path) return POB_EINVAL;
+  POB_CUDA(cudaSetDevice(ctx->device));
+  POB_TRY(pob_arena_reset(ctx));
+  std::vector<int64_t> off, loff;
+  std::vector<int32_t> len;
+  POB_TRY(fetch_i64(ctx, where, reads->row_off, (size_t)n + 1, off));
+  POB_TRY(fetch_i64(ctx, where, lab_off, (size_t)n + 1, loff));
+  if (reads->row_len) POB_TRY(fetch_i32(ctx, where, reads->row_len, (size_t)n, len));
+  const int SZ = pob_acceptor_slots(band_size);
+  std::vector<int64_t> bp_off(n + 1);
+  bp_off[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    const int64_t T = reads->row_len ? len[i] : off[i + 1] - off[i];
+    const int64_t L = loff[i + 1] - loff[i];
+    if (L > T + 1 && T > 0) return POB_EINVAL;  // more bases than timesteps can never be placed
+    bp_off[i + 1] = bp_off[i] + (T + L + 1) * (SZ / 32);
+  }
+  pob_reads_t d = *reads;
+  const uint8_t* d_lab = labels;
+  const int64_t* d_loff = lab_off;
+  int8_t* d_path = out_path;
+  int32_t* d_status = out_status;
+  if (where == POB_HOST) {
+    POB_TRY(stage_reads(ctx, reads, &d));
+    POB_TRY(stage_in(ctx, labels, (size_t)loff[n], &d_lab, 8));
+    POB_TRY(stage_in(ctx, lab_off, (size_t)n + 1, &d_loff));
+    POB_TRY(stage_out(ctx, out_path, (size_t)off[n] + 4, &d_path));
+    POB_TRY(stage_out(ctx, out_status, (size_t)n, &d_status, true));
+  } else if (!d_status) {
+    POB_TRY(pob_take(ctx, (size_t)n, &d_status));
+  }
+  const int64_t* d_bp_off;
+  POB_TRY(upload(ctx, bp_off, &d_bp_off));
+  uint32_t* bp;
+  double* cum;
+  POB_TRY(pob_take(ctx, (size_t)bp_off[n] + 8, &bp));
+  POB_TRY(pob_take(ctx, (size_t)off[n] + 8, &cum));
+  POB_TRY(pob_acceptor_launch(ctx, d, d_lab, d_loff, band_size, SZ, d_bp_off, bp, cum, d_path, d_status));
+  if (where == POB_HOST) {
+    POB_TRY(copy_back(ctx, out_path, d_path, (size_t)off[n]));
+    POB_TRY(copy_back(ctx, out_status, d_status, (size_t)n));
+  }
+  POB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return POB_OK;
+}
+
 int pob_align_global(pob_ctx* ctx, int where, const uint8_t* seq1, const int64_t* off1, const uint8_t* seq2,
                      const int64_t* off2, int n, int match, int mismatch, int gap, uint8_t* out_a1, uint8_t* out_a2,
                      int32_t* out_alen, int32_t* out_matches, const int64_t* dp_off, int32_t* out_dp) {

@@ -33,6 +33,10 @@ int pob_flipflop_launch(pob_ctx* ctx, const pob_reads& rd, const double* lut, ui
 
 int pob_forward_launch(pob_ctx* ctx, const pob_reads& rd, const uint8_t* labels, const int64_t* lab_off, int model,
                        double* scratch, const int64_t* scr_off, double* out);
+int pob_acceptor_slots(int band);
+int pob_acceptor_launch(pob_ctx* ctx, const pob_reads& rd, const uint8_t* labels, const int64_t* lab_off, int band,
+                        int SZ, const int64_t* bp_off, uint32_t* bp, double* cum, int8_t* out_path,
+                        int32_t* out_status);
 int pob_global_pair_launch(pob_ctx* ctx, const uint8_t* seq1, const int64_t* off1, const uint8_t* seq2,
                            const int64_t* off2, int n, int match, int mismatch, int gap, const int64_t* dp_off,
                            int32_t* dp, const int64_t* aln_off, uint8_t* out_a1, uint8_t* out_a2, int32_t* out_alen,

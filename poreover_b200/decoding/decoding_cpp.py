@@ -48,3 +48,16 @@ def cpp_forward(y_, label_, alphabet_="ACGT", model_="ctc"):
     _check_alphabet(alphabet_, y)
     lab = label_ if alphabet_ == "ACGT" else label_.translate(str.maketrans(alphabet_, "ACGT"))
     return float(batch.forward_batch([y], [lab], model_)[0])
+
+
+def cpp_viterbi_acceptor(y_, label_, band_size=1000, alphabet_="ACGT"):
+    """decoding_cpp.pyx:69-84 -> viterbi_acceptor_poreover (Forward.h:14-121): int array, one entry per timestep,
+    len(alphabet_) for blank or the index of the base emitted there."""
+    y = _prep(y_)
+    _check_alphabet(alphabet_, y)
+    lab = label_ if alphabet_ == "ACGT" else label_.translate(str.maketrans(alphabet_, "ACGT"))
+    paths, st = batch.viterbi_acceptor_batch([y], [lab], band_size)
+    if st[0] & batch._lib.ST_UNSET_BAND:
+        raise RuntimeError("viterbi_acceptor: the label cannot be placed inside the band "
+                           "(the reference's traceback does not terminate here, Forward.h:107-116)")
+    return paths[0]

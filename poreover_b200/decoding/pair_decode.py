@@ -5,10 +5,10 @@ pair_decode_helper, pair_decode), the argparse Namespace fields, the output file
 (SURVEY.md A.9).  Changed: pairs are not farmed out to a process pool one at a time
 (pair_decode.py:292-297); all pairs of a run go through pob_pair_decode in batches, and with several GPUs
 the batches are pulled from a host work queue by one process per GPU (poreover_b200/multigpu.py).
---alignment full, --diagonal_envelope and --skip_matches run the same kernels stage by
+--alignment full, --diagonal_envelope, --skip_matches and --single beam run the same kernels stage by
 stage (viterbi -> aligner -> envelope -> one batched search over whole pairs or over the boxes between anchors),
 with the anchor / box bookkeeping of pair_decode.py:412-452 on the host.
-Out of scope here, as in SURVEY.md section 2: --method split/align, --single beam, --algorithm prefix (they raise
+Out of scope here, as in SURVEY.md section 2: --method split/align, --algorithm prefix (they raise
 NotImplementedError).
 """
 import logging
@@ -55,7 +55,6 @@ def get_sequence_mapping(path, kind):
 
 _UNSUPPORTED = (
     ("method", "envelope", "--method split/align are deprecated in the reference and not on the GPU path"),
-    ("single", "viterbi", "--single beam (re-squiggle) is not on the GPU path yet"),
     ("algorithm", "beam", "--algorithm prefix is the legacy search and not on the GPU path"),
 )
 
@@ -71,7 +70,7 @@ def _check_args(args):
 def _staged(args):
     """True when a flag asks for something the fused pob_pair_decode call does not do."""
     return (getattr(args, "alignment", "banded") == "full" or getattr(args, "skip_matches", False)
-            or getattr(args, "diagonal_envelope", False))
+            or getattr(args, "diagonal_envelope", False) or getattr(args, "single", "viterbi") == "beam")
 
 
 def get_anchors(alignment, matches, indels):
@@ -147,12 +146,29 @@ def _decode_pairs_staged(args, meta, m1, m2, kind, device):
             out[k] = (fasta_format('consensus;{};{}'.format(args.method, path1.stem, path2.stem), seqs[k]),
                       {'read1': in_path[0], 'read2': in_path[1]})
         return out
-    seq1, map1, _, st1 = batch.viterbi_batch(m1, kind, device=device)
-    seq2, map2, _, st2 = batch.viterbi_batch(m2, kind, rc=rc2, device=device)
+    if getattr(args, "single", "viterbi") == "beam":
+        # pair_decode.py:363-370: 1D beam search with cpp_beam_search's DEFAULTS (width 25, model "ctc", whatever
+        # the basecaller), then the banded acceptor turns each basecall into a path; mapping on the host
+        seq1 = batch.beam_search_batch(m1, 25, "ctc", device=device)[0]
+        seq2 = batch.beam_search_batch(m2, 25, "ctc", rc=rc2, device=device)[0]
+        if any(len(x) == 0 for x in seq1 + seq2):
+            raise IndexError("viterbi_acceptor: empty basecall (the reference reads label_int[0], Forward.h:51)")
+        pth1, sa1 = batch.viterbi_acceptor_batch(m1, seq1, 1000, device=device)
+        pth2, sa2 = batch.viterbi_acceptor_batch(m2, seq2, 1000, rc=rc2, device=device)
+        map1 = [np.asarray(get_sequence_mapping(p, kind)[0], dtype=np.int64) for p in pth1]
+        map2 = [np.asarray(get_sequence_mapping(p, kind)[0], dtype=np.int64) for p in pth2]
+        wrap = batch._lib.ST_MAPPING_WRAP
+        st1 = np.array([wrap if (len(m) != len(s) or (a & batch._lib.ST_UNSET_BAND)) else 0
+                        for m, s, a in zip(map1, seq1, sa1)])
+        st2 = np.array([wrap if (len(m) != len(s) or (a & batch._lib.ST_UNSET_BAND)) else 0
+                        for m, s, a in zip(map2, seq2, sa2)])
+    else:
+        seq1, map1, _, st1 = batch.viterbi_batch(m1, kind, device=device)
+        seq2, map2, _, st2 = batch.viterbi_batch(m2, kind, rc=rc2, device=device)
     live = []
     for k, (in_path, path1, path2, _) in enumerate(meta):
         if (st1[k] | st2[k]) & batch._lib.ST_MAPPING_WRAP:
-            continue  # the reference's assertion (pair_decode.py:379) fires and the pool drops the pair
+            continue  # the reference's assertion (pair_decode.py:379 / :382) fires and the pool drops the pair
         summary = {'read1': in_path[0], 'read2': in_path[1], 'length1': len(seq1[k]), 'length2': len(seq2[k])}
         if abs(len(seq1[k]) - len(seq2[k])) > 1000:
             summary['skipped'] = 1

@@ -56,8 +56,12 @@ def make_pair(k, T=5000, density=0.4):
     return p1, p2, seq
 
 
-def save_pair(dirname, k, T=5000):
+def save_pair(dirname, k, T=5000, blank_last=False):
+    """Write the two reads of pair k as .npy probability files: bonito order (blank first, data/bonito022.patch:7-10)
+    or, with blank_last, the PoreOverNet order that `--basecaller poreover` expects (decode.py:108-110)."""
     p1, p2, _ = make_pair(k, T)
+    if blank_last:
+        p1, p2 = np.ascontiguousarray(p1[:, [1, 2, 3, 4, 0]]), np.ascontiguousarray(p2[:, [1, 2, 3, 4, 0]])
     f1, f2 = "pair%05d_1.npy" % k, "pair%05d_2.npy" % k
     np.save(os.path.join(dirname, f1), p1)
     np.save(os.path.join(dirname, f2), p2)

@@ -160,3 +160,17 @@ def test_port_vs_compiled_reference(oracle):
     for model in ("ctc", "ctc_merge_repeats"):
         assert oracle.beam_search_2d(lp1, lp2, None, 10, model, "row", backend="port") == \
             oracle.beam_search_2d(lp1, lp2, None, 10, model, "row", backend="ref")
+
+
+def test_oracle_acceptor_matches_reference_function(oracle):
+    """orc_viterbi_acceptor against the unmodified viterbi_acceptor_poreover (Forward.h:14-121) in oracle/_ref."""
+    O = oracle
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built")
+    for seed, T, band in [(1, 300, 1000), (2, 600, 40), (3, 1500, 100), (4, 1000, 5), (5, 97, 7)]:
+        lp = synth.bonito_log_prob(synth.make_read(seed, T)[0])
+        lab = O.beam_search(lp, 25, "ctc")
+        a = O.viterbi_acceptor(lp, lab, band, "port")
+        b = O.viterbi_acceptor(lp, lab, band, "ref")
+        assert np.array_equal(a, b), (seed, T, band)
+        assert "".join("ACGT"[i] for i in a[a != 4]) == lab
