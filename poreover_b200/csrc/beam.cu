@@ -94,11 +94,12 @@ __device__ __forceinline__ double ninf() { return __longlong_as_double(0xfff0000
 __device__ __forceinline__ double no_nan(double x) { return (x == x) ? x : ninf(); }  // NaN cannot be ranked
 
 // Log.h:27-33 with the bounded term in FP32: max + log1p(exp(min - max))
+// Branch-free (a select at the end) so that two independent evaluations can be interleaved by the scheduler.
 __device__ __forceinline__ double lae(double a, double b) {
   const double m = fmax(a, b);
-  if (m == ninf()) return m;
-  const float d = (float)(fmin(a, b) - m);
-  return m + (double)log1pf(expf(d));
+  const float d = (float)(fmin(a, b) - m);  // NaN when both are -inf: discarded below
+  const double r = m + (double)log1pf(expf(d));
+  return (m == ninf()) ? m : r;
 }
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -436,6 +437,11 @@ struct Engine {
         double pv = ninf();
         if (pstat == PS_INE || pstat == PS_FROZEN) pv = frozen_at(pwb, cs, wmask, plo, phi, same);
         else if (pstat == PS_ROOT) pv = root_prob(r, cs - 1);
+        // merge-repeats: the no-gap chain ng(t) = lae(pv(t) + y, ng(t-1) + y) does not depend on prob(t-1), so ng(t+1)
+        // is evaluated next to prob(t) = lae(prob(t-1) + yblank, ng(t)) -- two independent log-add-exps per
+        // iteration instead of two dependent ones (same operations on the same operands, hence the same values)
+        double ng_cur = ninf();
+        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_cur = lae(pv + yl, ng_prev + yl);
         for (int t = cs; t < limA; ++t) {
           // inputs of the next timestep are requested before this one is evaluated
           double yl_n = 0, yb_n = 0, pv_n = ninf();
@@ -449,12 +455,14 @@ struct Engine {
           double prob;
           Ent* o = wb + ((t + 1) & wmask);
           if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
+            const double ng_nxt = lae(pv_n + yl_n, ng_cur + yl_n);  // for t+1; unused after the last iteration
             const double gp = p_prev + yb;
-            const double ng = lae(pv + yl, ng_prev + yl);
+            const double ng = ng_cur;
             prob = lae(gp, ng);
             double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
             *reinterpret_cast<double4*>(o) = v4;
             ng_prev = ng; g_prev = gp;
+            ng_cur = ng_nxt;
           } else {
             prob = lae(pv + yl, p_prev + yb);
             o->prob = prob;
