@@ -605,8 +605,18 @@ struct Engine {
         key[a] = make_double2(no_nan(a_last0[a] + maxv), (double)a_order[a]);
       }
     }
+    pre_prune();
     __syncthreads();
     PCLK(5);
+  }
+
+  // scalars of the coming prune / sweep, reset by thread 0 BEFORE the barrier that precedes prune()
+  __device__ __forceinline__ void pre_prune() {
+    POB_VIEWS
+    if (threadIdx.x == 0) {
+      sh[SH_NB] = min(sh[SH_NUSED], W); sh[SH_DMIN] = 0x7fffffff;
+      sh[SH_TB0] = 0x7fffffff; sh[SH_TB1] = 0x7fffffff;  // for the next sweep (this sweep read them after its first barrier)
+    }
   }
 
   // ---- Beam::prune (Beam.h:93-108): rank by score desc, exact ties by creation order ----------
@@ -619,10 +629,6 @@ struct Engine {
     const int half = two ? (tid & 1) : 0;
     const bool cand = a < EMAX && a_slot[a] >= 0;
     int rank = 0;
-    if (tid == 0) {
-      sh[SH_NB] = min(sh[SH_NUSED], W); sh[SH_DMIN] = 0x7fffffff;
-      sh[SH_TB0] = 0x7fffffff; sh[SH_TB1] = 0x7fffffff;  // for the next sweep
-    }
     if (cand) {
       const double2 k = key[a];
       const int mid = two ? (EMAX >> 1) : EMAX;
@@ -633,7 +639,8 @@ struct Engine {
       }
     }
     if (two) rank += __shfl_xor_sync(0xffffffffu, rank, 1);
-    __syncthreads();  // SH_DMIN reset is visible before the atomicMin below
+    // no barrier here: the ranking loop only reads key[], the block below only writes other arrays, and the scalars
+    // it updates were reset by pre_prune() before the barrier that precedes this call
     if (a < EMAX && half == 0) {
       a_needed[a] = 0;
       const bool inb = cand && rank < W;
@@ -835,16 +842,15 @@ struct Engine {
           atomicAdd(&sh[SH_NUSED], 1);
         }
       }
+      // the first expansion of a beam node gives it its trace id; its sibling threads took the id from `first` and
+      // fbase above and do not read a_tid[a] in that case, so it can be written in this phase
+      if (xc == 0 && first) {
+        a_tid[a] = my_tid;
+        trace[my_tid] = ((uint32_t)a_ptid[a] << 2) | (uint32_t)a_last[a];
+      }
     }
     __syncthreads();
     PCLK(9);
-    // the first expansion of a beam node gives it its trace id (after every sibling has read the old value)
-    if (xmine && xc == 0 && first) {
-      a_tid[a] = sh[SH_TID] + fbase;
-      trace[a_tid[a]] = ((uint32_t)a_ptid[a] << 2) | (uint32_t)a_last[a];
-    }
-    __syncthreads();
-    PCLK(10);
   }
 
   // ROW traversal while the beam is shorter than W (first row): the reference walks b < beam_width over a
@@ -1023,6 +1029,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
         n_updates++;
         key[tid] = make_double2(no_nan(p), (double)a_order[tid]);  // last_probability(): value at the last t
       }
+      pre_prune();
       __syncthreads();
       prune();
       dbg_record(G, nsteps);
