@@ -80,4 +80,6 @@ def decode_pairs_all_gpus(args, pair_list, chunk=256):
             return 0
 
     cost = [cost_of(p) for p in pair_list]
+    # small runs: at least ~4 chunks per rank so that every GPU gets work; large runs: 256-pair batches
+    chunk = max(8, min(chunk, -(-len(pair_list) // (4 * world))))
     return run_sharded(pair_list, cost, lambda sub: pd.decode_pairs(args, sub, device=local), chunk, group, store)
