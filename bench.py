@@ -176,6 +176,7 @@ def run_ours(args):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = _lib.get_ctx(local)
     L = lib()
