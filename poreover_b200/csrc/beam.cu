@@ -94,6 +94,20 @@ __device__ __forceinline__ double ninf() { return __longlong_as_double(0xfff0000
 __device__ __forceinline__ double no_nan(double x) { return (x == x) ? x : ninf(); }  // NaN cannot be ranked
 
 // Log.h:27-33 with the bounded term in FP32: max + log1p(exp(min - max))
+// Ranking keys are kept as integers: skey(x) is an order-preserving map of a (non-NaN) double onto uint64, so the
+// all-pairs ranking compares with the integer pipe instead of three FP64 compares per pair.  -0.0 is folded into +0.0.
+__device__ __forceinline__ unsigned long long skey(double x) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(x + 0.0);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double skey_inv(unsigned long long k) {
+  const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+  return __longlong_as_double((long long)u);
+}
+__device__ __forceinline__ double2 make_key(double score, double order) {
+  return make_double2(__longlong_as_double((long long)skey(score)), order);
+}
+
 // Branch-free (a select at the end) so that two independent evaluations can be interleaved by the scheduler.
 __device__ __forceinline__ double lae(double a, double b) {
   const double m = fmax(a, b);
@@ -600,9 +614,9 @@ struct Engine {
     const double other = __shfl_xor_sync(0xffffffffu, maxv, 1);
     if (used) {
       if (mode == MODE_ROWCOL) {
-        if (r == 0) key[a] = make_double2(no_nan(maxv + other), (double)a_order[a]);
+        if (r == 0) key[a] = make_key(no_nan(maxv + other), (double)a_order[a]);
       } else if (r == 1) {
-        key[a] = make_double2(no_nan(a_last0[a] + maxv), (double)a_order[a]);
+        key[a] = make_key(no_nan(a_last0[a] + maxv), (double)a_order[a]);
       }
     }
     pre_prune();
@@ -629,16 +643,35 @@ struct Engine {
     const int half = two ? (tid & 1) : 0;
     const bool cand = a < EMAX && a_slot[a] >= 0;
     int rank = 0;
+    const int mid = two ? (EMAX >> 1) : EMAX;
+    const int j0 = half ? mid : 0, j1 = half ? EMAX : mid;
+    const unsigned long long* const k64 = reinterpret_cast<const unsigned long long*>(key);  // [2a] score key, [2a+1] order
+    unsigned long long ks = 0;
+    int eq = 0;
     if (cand) {
-      const double2 k = key[a];
-      const int mid = two ? (EMAX >> 1) : EMAX;
-      const int j0 = half ? mid : 0, j1 = half ? EMAX : mid;
+      // fast pass: integer compares of the score keys only; exact ties are counted and resolved below
+      ks = k64[2 * a];
       for (int j = j0; j < j1; ++j) {
-        const double2 kj = key[j];
-        rank += (kj.x > k.x) || (kj.x == k.x && kj.y < k.y);
+        const unsigned long long kj = k64[2 * j];
+        rank += kj > ks;
+        eq += kj == ks;
       }
     }
-    if (two) rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+    if (two) { rank += __shfl_xor_sync(0xffffffffu, rank, 1); eq += __shfl_xor_sync(0xffffffffu, eq, 1); }
+    // a candidate that could be in the beam and shares its score with another one: rank the tie by creation order
+    // (rare; the whole warp takes the exact pass so that the shuffles stay convergent)
+    if (__any_sync(0xffffffffu, cand && rank < W && eq > 1)) {
+      int tie = 0;
+      if (cand) {
+        const double ko = key[a].y;
+        for (int j = j0; j < j1; ++j) {
+          const double2 kj = key[j];
+          tie += ((unsigned long long)__double_as_longlong(kj.x) == ks) && kj.y < ko;
+        }
+      }
+      if (two) tie += __shfl_xor_sync(0xffffffffu, tie, 1);
+      rank += tie;
+    }
     // no barrier here: the ranking loop only reads key[], the block below only writes other arrays, and the scalars
     // it updates were reset by pre_prune() before the barrier that precedes this call
     if (a < EMAX && half == 0) {
@@ -669,7 +702,7 @@ struct Engine {
     retq[pos % RQ] = make_int2(slot, stamp);
     slot2e[slot] = -1;
     a_slot[a] = -1;
-    key[a] = make_double2(ninf(), 4.5e9);
+    key[a] = make_key(ninf(), 4.5e9);
     a_free[atomicAdd(&sh[SH_AFREE], 1)] = a;
     atomicSub(&sh[SH_NUSED], 1);
   }
@@ -691,7 +724,7 @@ struct Engine {
     a_che[2 * a] = a_che[2 * a + 1] = -1;
     a_last[a] = (uint8_t)last; a_pstat[a] = PS_INE; a_same[a] = (a_last[pa] == last);
     a_inbeam[a] = 0; a_needed[a] = 1;
-    key[a] = make_double2(ninf(), 4.5e9);
+    key[a] = make_key(ninf(), 4.5e9);
     slot2e[slot] = (int16_t)a;
   }
 
@@ -715,7 +748,7 @@ struct Engine {
     a_che[2 * a] = a_che[2 * a + 1] = -1;  // retained entries are stale with respect to the live parent
     a_last[a] = (uint8_t)h.last; a_pstat[a] = PS_INE; a_same[a] = (a_last[pa] == h.last);
     a_inbeam[a] = 0; a_needed[a] = 1;
-    key[a] = make_double2(ninf(), 4.5e9);
+    key[a] = make_key(ninf(), 4.5e9);
     slot2e[slot] = (int16_t)a;
   }
 
@@ -897,7 +930,7 @@ struct Engine {
     if (threadIdx.x == 0 && step < 50000) {
       double sum = 0;
       for (int b = 0; b < sh[SH_NB]; ++b) {
-        const double sc = key[beam[b]].x;
+        const double sc = skey_inv((unsigned long long)__double_as_longlong(key[beam[b]].x));
         if (b == 0) G.dbg_trace[2 * step] = sc;
         if (sc > -1e300) sum += sc;
       }
@@ -945,7 +978,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     slot2e[s] = -1;
   }
   for (int a = tid; a < EMAX; a += NT) {
-    a_slot[a] = -1; a_free[a] = EMAX - 1 - a; key[a] = make_double2(ninf(), 4.5e9);
+    a_slot[a] = -1; a_free[a] = EMAX - 1 - a; key[a] = make_key(ninf(), 4.5e9);
     a_inbeam[a] = 0; a_needed[a] = 0;
   }
   if (tid == 0) {
@@ -994,7 +1027,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
   __syncthreads();
   {
     const double p = update_all(tid < nbase, tid, 0, 0);
-    if (mode == MODE_1D && tid < nbase) key[tid] = make_double2(no_nan(p), (double)a_order[tid]);
+    if (mode == MODE_1D && tid < nbase) key[tid] = make_key(no_nan(p), (double)a_order[tid]);
     if (mode != MODE_1D) update_all(tid < nbase, tid, 1, 0);
   }
 
@@ -1027,7 +1060,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
       const double p = update_all(mine, tid, 0, t);
       if (mine) {
         n_updates++;
-        key[tid] = make_double2(no_nan(p), (double)a_order[tid]);  // last_probability(): value at the last t
+        key[tid] = make_key(no_nan(p), (double)a_order[tid]);  // last_probability(): value at the last t
       }
       pre_prune();
       __syncthreads();
