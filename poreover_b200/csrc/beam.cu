@@ -651,6 +651,7 @@ struct Engine {
     if (cand) {
       // fast pass: integer compares of the score keys only; exact ties are counted and resolved below
       ks = k64[2 * a];
+#pragma unroll 8
       for (int j = j0; j < j1; ++j) {
         const unsigned long long kj = k64[2 * j];
         rank += kj > ks;
@@ -674,15 +675,19 @@ struct Engine {
     }
     // no barrier here: the ranking loop only reads key[], the block below only writes other arrays, and the scalars
     // it updates were reset by pre_prune() before the barrier that precedes this call
+    int dmin_mine = 0x7fffffff;
     if (a < EMAX && half == 0) {
       a_needed[a] = 0;
       const bool inb = cand && rank < W;
       a_inbeam[a] = inb;
       if (inb) {
         beam[rank] = a;
-        atomicMin(&sh[SH_DMIN], a_depth[a]);
+        dmin_mine = a_depth[a];
       }
     }
+    // minimum depth of the new beam: one shared-memory atomic per warp instead of one per beam node
+    dmin_mine = __reduce_min_sync(0xffffffffu, dmin_mine);
+    if ((tid & 31) == 0 && dmin_mine != 0x7fffffff) atomicMin(&sh[SH_DMIN], dmin_mine);
     __syncthreads();
     PCLK(6);
   }
