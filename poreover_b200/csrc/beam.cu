@@ -116,6 +116,13 @@ __device__ __forceinline__ double lae(double a, double b) {
   return (m == ninf()) ? m : r;
 }
 
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -1097,8 +1104,20 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     // BeamSearch.h:295-392
     int u = 0, v = 0;
     bool have_E = false;
+    // The band of row u / column v is read by every thread at the top of every step.  Thread 0 copies the entries
+    // of the next row and the next column into shared memory with cp.async while the current step runs (two slots
+    // each, indexed by parity), so that the next step starts from shared memory instead of a global load.
+    int* const senv = sh + 24;   // [2][2] band of row u  (slot u & 1)
+    int* const senvt = sh + 28;  // [2][2] band of column v (slot v & 1)
+    if (tid == 0) { senv[0] = env[0]; senv[1] = env[1]; senvt[0] = envt[0]; senvt[1] = envt[1]; }
+    __syncthreads();
     while (u <= U - 1 && v <= V - 1) {
-      const int ers = env[2 * u], ere = env[2 * u + 1], ecs = envt[2 * v], ece = envt[2 * v + 1];
+      const int ers = senv[2 * (u & 1)], ere = senv[2 * (u & 1) + 1], ecs = senvt[2 * (v & 1)], ece = senvt[2 * (v & 1) + 1];
+      if (tid == 0) {
+        if (u + 1 < U) cp_async8(senv + 2 * ((u + 1) & 1), env + 2 * (u + 1));
+        if (v + 1 < V) cp_async8(senvt + 2 * ((v + 1) & 1), envt + 2 * (v + 1));
+        cp_async_commit();
+      }
       int row_start = v, row_end = v, col_start = u, col_end = u;
       bool rset = false, cset = false;
       if (v >= ers && v < ere) { row_end = ere; rset = true; }
@@ -1106,6 +1125,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
         const int nb = sh[SH_NB];
         if (nb < W && tid == 0) sh[SH_STATUS] |= POB_ST_SHORT_BEAM_SKIP;
         const bool mine = tid < EMAX && a_slot[tid] >= 0 && a_inbeam[tid];
+        if (tid == 0) cp_async_wait_all();  // visible to everyone after the barriers inside update_all
         update_all(mine, tid, 1, v);
         if (mine) n_updates++;
         ++v; ++nsteps;
@@ -1116,6 +1136,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
         const int nb = sh[SH_NB];
         if (nb < W && tid == 0) sh[SH_STATUS] |= POB_ST_SHORT_BEAM_SKIP;
         const bool mine = tid < EMAX && a_slot[tid] >= 0 && a_inbeam[tid];
+        if (tid == 0) cp_async_wait_all();
         update_all(mine, tid, 0, u);
         if (mine) n_updates++;
         ++u; ++nsteps;
@@ -1144,6 +1165,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
       sweep(3, col_start, col_end, row_start, row_end, G.dbg_noreuse != 0, n_updates);
       prune();
       dbg_record(G, nsteps);
+      if (tid == 0) cp_async_wait_all();  // next row / column bands: visible after the barriers of the expansion
       expand_and_retire(u, v);  // later reads are at t-1 >= u (read 0) and >= v (read 1)
       ++u; ++v; ++nsteps;
     }
