@@ -295,9 +295,10 @@ def run_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        half = max(1, min(P, args.viterbi_reads // 2))
-        reps = max(1, int(np.ceil(args.viterbi_reads / (2.0 * half))))
-        arrays = ((l1[:half] + l2[:half]) * reps)[:args.viterbi_reads]
+        # first reads of the pairs (T rows each), tiled to --viterbi-reads: the same shape as tools/prof_viterbi.py, the
+        # workload of the committed ncu capture that `traffic` comes from
+        reps = max(1, int(np.ceil(args.viterbi_reads / float(P))))
+        arrays = (l1 * reps)[:args.viterbi_reads]
         vb = batch.ReadBatch(arrays)
         dv = dev_reads(vb)
         rows = vb.total_rows
@@ -323,10 +324,10 @@ def run_ours(args):
         # DRAM traffic of one launch of this kernel on this workload, from the committed ncu --set full capture
         traffic, traffic_src = None, None
         try:
-            ns = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01_c.json")))["viterbi5_f32_kernel"]
+            ns = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01_d.json")))["viterbi5_f32_kernel"]
             if vb.n == 10000 and args.T == 5000:
                 traffic = ns["dram_traffic_bytes_per_launch"]
-                traffic_src = "profiles/ncu_summary_r01_c.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)"
+                traffic_src = "profiles/ncu_summary_r01_d.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)"
         except (OSError, ValueError, KeyError):
             pass
         roof = {"kernel": "viterbi_ctc (%d reads, T=%d, %.2f GB in)" % (vb.n, args.T, float(vb.lens.sum()) * 20 / 1e9),
