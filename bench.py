@@ -139,8 +139,8 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_pairs = args.ref_pairs or cores
-    uniq = min(max(n_pairs, 8), 64)
+    n_pairs = args.ref_pairs or 4 * cores  # a subsample of at least 4 x cores pairs
+    uniq = min(max(n_pairs, 8), 256)
     l1, l2 = make_pairs(0, uniq, args.T)
     r = cpu_reference(l1, l2, args.beam_width, n_pairs, args.steps, args.warmup)
     line = {
@@ -344,8 +344,8 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        npairs = min(P, max(cores, 4))
-        r = cpu_reference(l1[:min(P, 64)], l2[:min(P, 64)], args.beam_width, npairs, 1, 0)
+        npairs = min(P, max(4 * cores, 4))  # at least 4 x cores pairs (10-30 s of CPU work)
+        r = cpu_reference(l1[:min(P, 256)], l2[:min(P, 256)], args.beam_width, npairs, 1, 0)
         cpu = {"value": r["pairs_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"],
                "sample": r["sample"], "consensus_mbases_per_s": r["bases_per_s"] / 1e6}
 
@@ -378,7 +378,7 @@ def main():
     ap.add_argument("--T", type=int, default=5000)
     ap.add_argument("--beam-width", type=int, default=25)
     ap.add_argument("--viterbi-reads", type=int, default=10000)
-    ap.add_argument("--ref-pairs", type=int, default=0, help="pairs per step of the reference arm (default: host cores)")
+    ap.add_argument("--ref-pairs", type=int, default=0, help="pairs per step of the reference arm (default: 4 x host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -10,14 +10,16 @@
 // Only FP64 adds and compares are used, in the reference's order, so the result is bit-exact.  The 256
 // possible log((x+1e-7)/(255+1e-7)) values of a uint8 trace come from a host-computed table (decode.py:92-93).
 //
-// One warp per read: lanes 0-7 own the 8 states and exchange v[t-1] by shuffles; the time loop is a
-// dependent chain (latency-bound, FP64 pipe), backpointers are packed 8 x 3 bits per timestep.
+// Four reads per warp: the 8 lanes of a read own its 8 states and exchange v[t-1] by 8-wide shuffles; the time loop
+// is a dependent chain (the kernel is bound by instruction issue, so all 32 lanes do useful work), backpointers are
+// packed 8 x 3 bits per timestep and walked back 8 timesteps per coalesced load.
 #include "common.cuh"
 #include "launch.cuh"
 
 namespace {
 
 constexpr int FF_WARPS = 4;
+constexpr int FF_READS_PER_WARP = 4;
 
 template <bool U8>
 __global__ void __launch_bounds__(FF_WARPS * 32)
@@ -30,17 +32,19 @@ flipflop_kernel(const void* __restrict__ data, const double* __restrict__ lut, c
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut[i];
     __syncthreads();
   }
+  // four reads per warp: lanes 8g..8g+7 own the 8 states of read g; every shuffle below is 8 lanes wide
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * FF_WARPS + (threadIdx.x >> 5);
-  if (r >= n) return;
-  const int64_t ro = row_off[r];
-  const int T = pob_read_len(row_off, row_len, r);
-  if (T <= 0) {
-    if (lane == 0) out_len[r] = 0;
-    return;
-  }
-  const bool rc = rcflag ? rcflag[r] != 0 : false;
-  const int j = lane & 7;
+  const int grp = lane >> 3, j = lane & 7;
+  const int r = (blockIdx.x * FF_WARPS + (threadIdx.x >> 5)) * FF_READS_PER_WARP + grp;
+  const bool valid = r < n;
+  const int64_t ro = valid ? row_off[r] : 0;
+  const int T = valid ? pob_read_len(row_off, row_len, r) : 0;
+  int Tmax = T;
+  Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, 8));
+  Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, 16));
+  if (valid && T <= 0 && j == 0) out_len[r] = 0;
+  if (Tmax <= 0) return;  // warp-uniform
+  const bool rc = (valid && rcflag) ? rcflag[r] != 0 : false;
   // logical state j -> physical column (transducer.py:104-106: [3,2,1,0,7,6,5,4])
   const int pc = rc ? ((j < 4) ? 3 - j : 11 - j) : j;
   auto lp_at = [&](int t) -> double {
@@ -49,9 +53,10 @@ flipflop_kernel(const void* __restrict__ data, const double* __restrict__ lut, c
     return ((const double*)data)[idx];
   };
   uint32_t* mybp = bp + ro;
-  double v = lp_at(0);
+  double v = (T > 0) ? lp_at(0) : 0.0;
   double nxt = (T > 1) ? lp_at(1) : 0.0;
-  for (int t = 1; t < T; ++t) {
+  for (int t = 1; t < Tmax; ++t) {
+    const bool act = t < T;
     const double lp = nxt;
     if (t + 1 < T) nxt = lp_at(t + 1);  // prefetch off the dependent chain
     double best = 0;
@@ -64,12 +69,12 @@ flipflop_kernel(const void* __restrict__ data, const double* __restrict__ lut, c
       const double c = tr + vi;
       if (i == 0 || c > best) { best = c; bi = i; }
     }
-    v = lp + best;
+    if (act) v = lp + best;
     uint32_t pk = (uint32_t)bi << (3 * j);
     pk |= __shfl_xor_sync(0xffffffffu, pk, 1, 8);
     pk |= __shfl_xor_sync(0xffffffffu, pk, 2, 8);
     pk |= __shfl_xor_sync(0xffffffffu, pk, 4, 8);
-    if (lane == 0) mybp[t] = pk;
+    if (j == 0 && act) mybp[t] = pk;
   }
   // argmax of the last row (first index wins), then walk the backpointers
   int state = 0;
@@ -82,34 +87,43 @@ flipflop_kernel(const void* __restrict__ data, const double* __restrict__ lut, c
   }
   __syncwarp();
   int8_t* path = path_buf + ro;
-  if (lane == 0) {
-    path[T - 1] = (int8_t)state;
-    for (int t = T - 1; t >= 1; --t) {
-      state = (mybp[t] >> (3 * state)) & 7;
-      path[t - 1] = (int8_t)state;
+  if (j == 0 && T > 0) path[T - 1] = (int8_t)state;
+  // walk the back-pointers 8 timesteps at a time: one coalesced load of 8 packed words per read, then the dependent
+  // chain runs on shuffles (the 8 lanes of a read follow the same walk; each keeps the state of "its" timestep)
+  for (int c = 0; 1 + 8 * c <= Tmax - 1; ++c) {
+    const int th = T - 1 - 8 * c;   // newest timestep of this chunk for this read (may be < 1: nothing left)
+    const int tm = th - j;
+    const uint32_t w = (tm >= 1) ? mybp[tm] : 0u;
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t wk = __shfl_sync(0xffffffffu, w, k, 8);
+      if (th - k >= 1) state = (wk >> (3 * state)) & 7;
+      if (j == k) mine = state;
     }
+    if (tm >= 1) path[tm - 1] = (int8_t)mine;
   }
   __syncwarp();
   // collapse runs of identical states (A != a), upper-case, record the timestep of each emitted base
   int nout = 0, carry = -1;
   uint8_t* oseq = out_seq + ro;
   int32_t* os2s = out_s2s ? out_s2s + ro : nullptr;
-  for (int t0 = 0; t0 < T; t0 += 32) {
-    const int t = t0 + lane;
+  for (int t0 = 0; t0 < Tmax; t0 += 8) {
+    const int t = t0 + j;
     const int p = (t < T) ? path[t] : -2;
-    int prev = __shfl_up_sync(0xffffffffu, p, 1);
-    if (lane == 0) prev = carry;
-    carry = __shfl_sync(0xffffffffu, p, 31);
+    int prev = __shfl_up_sync(0xffffffffu, p, 1, 8);
+    if (j == 0) prev = carry;
+    carry = __shfl_sync(0xffffffffu, p, 7, 8);
     const bool e = (t < T) && (t == 0 || p != prev);
-    const unsigned m = __ballot_sync(0xffffffffu, e);
+    const unsigned m = (__ballot_sync(0xffffffffu, e) >> (8 * grp)) & 0xffu;
     if (e) {
-      const int off = nout + __popc(m & ((1u << lane) - 1));
+      const int off = nout + __popc(m & ((1u << j) - 1));
       oseq[off] = (uint8_t)("ACGT"[p & 3]);
       if (os2s) os2s[off] = t;
     }
     nout += __popc(m);
   }
-  if (lane == 0) out_len[r] = nout;
+  if (valid && T > 0 && j == 0) out_len[r] = nout;
 }
 
 }  // namespace
@@ -117,7 +131,8 @@ flipflop_kernel(const void* __restrict__ data, const double* __restrict__ lut, c
 int pob_flipflop_launch(pob_ctx* ctx, const pob_reads& rd, const double* lut, uint32_t* bp, int8_t* path,
                         uint8_t* out_seq, int32_t* out_s2s, int32_t* out_len) {
   if (rd.n <= 0) return POB_OK;
-  dim3 block(FF_WARPS * 32), grid((rd.n + FF_WARPS - 1) / FF_WARPS);
+  const int per_block = FF_WARPS * FF_READS_PER_WARP;
+  dim3 block(FF_WARPS * 32), grid((rd.n + per_block - 1) / per_block);
   pob_prof_scope ps(ctx, POB_K_FLIPFLOP);
   if (rd.dtype == POB_U8_TRACE)
     flipflop_kernel<true><<<grid, block, 0, ctx->stream>>>(rd.data, lut, rd.row_off, rd.row_len, rd.rc, rd.n, bp, path,

@@ -56,3 +56,24 @@ def test_acceptor_unplaceable_label_is_flagged():
     assert st[0] & batch._lib.ST_UNSET_BAND
     with pytest.raises(RuntimeError):
         decoding_cpp.cpp_viterbi_acceptor(lp, short, band_size=1)
+
+
+@pytest.mark.parametrize("T,lab,band", [(1, "A", 1000), (5, "ACGTA", 1000), (5, "ACGTA", 1), (6, "ACGTAC", 2),
+                                        (8, "AC", 3), (30, "ACGTTGCA", 2), (30, "A", 1000), (7, "AAAAAAA", 1000),
+                                        (64, "ACGT" * 16, 5), (33, "T" * 5, 40)])
+def test_acceptor_edge_shapes(T, lab, band):
+    """Tiny reads, one label, a base on every timestep, bands wider than the read and 1-wide bands: oracle, the
+    unmodified reference function and the kernel agree entry by entry."""
+    rng = np.random.default_rng(T * 131 + len(lab))
+    lp = np.log(rng.dirichlet(np.ones(5) * 0.5, size=T).astype(np.float32))
+    want = O.viterbi_acceptor(lp, lab, band, "port")
+    if O.have_ref():
+        assert np.array_equal(want, O.viterbi_acceptor(lp, lab, band, "ref"))
+    got, st = batch.viterbi_acceptor_batch([lp], [lab], band)
+    assert not st[0] and np.array_equal(got[0], want)
+
+
+def test_acceptor_rejects_more_bases_than_timesteps():
+    lp = np.log(np.full((4, 5), 0.2, dtype=np.float32))
+    with pytest.raises(Exception):
+        batch.viterbi_acceptor_batch([lp], ["ACGTACGT"], 10)
