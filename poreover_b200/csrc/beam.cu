@@ -636,7 +636,6 @@ struct Engine {
     POB_VIEWS
     if (threadIdx.x == 0) {
       sh[SH_NB] = min(sh[SH_NUSED], W); sh[SH_DMIN] = 0x7fffffff;
-      sh[SH_TB0] = 0x7fffffff; sh[SH_TB1] = 0x7fffffff;  // for the next sweep (this sweep read them after its first barrier)
     }
   }
 
@@ -650,6 +649,10 @@ struct Engine {
     const int half = two ? (tid & 1) : 0;
     const bool cand = a < EMAX && a_slot[a] >= 0;
     int rank = 0;
+    // phase-split bounds of the NEXT sweep: every thread read this sweep's values before the barrier that precedes
+    // this call (they must not be reset earlier: a sweep without a synchronised phase has no barrier between its
+    // readers and its end), and the next sweep's atomicMin comes after the barriers of the expansion
+    if (tid == 0) { sh[SH_TB0] = 0x7fffffff; sh[SH_TB1] = 0x7fffffff; }
     const int mid = two ? (EMAX >> 1) : EMAX;
     const int j0 = half ? mid : 0, j1 = half ? EMAX : mid;
     const unsigned long long* const k64 = reinterpret_cast<const unsigned long long*>(key);  // [2a] score key, [2a+1] order
