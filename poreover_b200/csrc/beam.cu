@@ -24,8 +24,9 @@
 // -2.5e3..-5e4); only the bounded log1p(exp(d)) term, d <= 0, is evaluated in FP32.  No tensor cores:
 // nothing here is a contraction.  Per step the dependent chain is the time-major band sweep: threads own
 // (node, read) items, carry their own t-1 values in registers and exchange parent values through
-// double-buffered shared memory, one block barrier per time sub-step; five more barriers per step cover
-// ranking, expansion, retirement and allocation.
+// double-buffered shared memory, one block barrier per time sub-step; about seven more barriers per step cover
+// the sweep's setup and keys, ranking, expansion, retirement and allocation.  Shared-memory hazards are checked
+// with compute-sanitizer racecheck / synccheck on tools/sanitize_case.py (all traversals, trees and widths).
 #include <stdlib.h>
 
 #include "common.cuh"
