@@ -39,6 +39,7 @@ int pob_viterbi(pob_ctx* ctx, int where, const pob_reads_t* reads, int kind, uin
 int pob_viterbi_flipflop(pob_ctx* ctx, int where, const pob_reads_t* reads, const double* lut, uint8_t* out_seq,
                          int32_t* out_s2s, int8_t* out_path, int32_t* out_len) {
   if (!ctx) return POB_EINVAL;
+  if (reads && reads->n == 0) return POB_OK;  // an empty batch has no geometry to validate
   POB_TRY(check_reads(reads, 8, 8));
   if (reads->dtype != POB_F64 && reads->dtype != POB_U8_TRACE) return POB_EINVAL;
   if (reads->dtype == POB_U8_TRACE && !lut) return POB_EINVAL;
