@@ -393,7 +393,9 @@ struct Engine {
     bool f64 = false, yrc = false;
     int yT = 0;
     long yrowb = 0;
+    PCLK(12);
     deferred_finalize();
+    PCLK(13);
     if (on && te > ts) {
       const int slot = a_slot[a];
       const int last = a_last[a];
@@ -423,6 +425,7 @@ struct Engine {
       } else if (pstat == PS_FROZEN) {
         plo = a_plo[2 * a + r]; phi = a_phi[2 * a + r]; pwb = wbase(a_pslot[a], r);
       }
+      PCLK(14);
       // clean part of the band: only the maximum is needed (independent loads, four in flight)
       {
         const int c0 = max(ts, lo), c1 = min(cs, hi);
@@ -436,6 +439,7 @@ struct Engine {
         }
       }
     }
+    PCLK(15);
     __syncthreads();
     PCLK(1);
     const int Tb0 = sh[SH_TB0], Tb1 = sh[SH_TB1];

@@ -6,7 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "build", "libporeover_b200_clk.so")
 NAMES = {0: "item setup+seed", 1: "sweep: setup + clean-max scan", 2: "sweep: phase A (private)", 3: "sweep: publish + barrier",
          4: "sweep: phase B loop", 5: "sweep: bookkeeping + keys", 6: "prune (rank)", 7: "expand X1 classify",
-         8: "expand X2 retire/inspect", 9: "expand X3 create/revive", 10: "expand X4 trace ids", 11: "single-t update (skip steps)"}
+         8: "expand X2 retire/inspect", 9: "expand X3 create/revive", 10: "expand X4 trace ids", 11: "single-t update (skip steps)", 12: "sweep: call + views", 13: "sweep: deferred_finalize",
+         14: "sweep: per-thread setup", 15: "sweep: clean-max scan (thread 0)"}
 if sys.argv[1] == "build":
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(ROOT, "poreover_b200", "csrc", "*.cu")))
@@ -48,5 +49,5 @@ raw.pob_debug_phase_clocks(clk, 0)
 cnt = ctx.counters()
 tot = float(sum(clk))
 print("beam ms", p["beam_pair"]["ms"], cnt, "steps/pair", cnt["steps"] / n)
-for i in range(12):
+for i in range(16):
     print("%5.1f%%  %8.0f cyc/step  %s" % (100 * clk[i] / tot, clk[i] / cnt["steps"], NAMES[i]))
