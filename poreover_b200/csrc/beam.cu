@@ -113,7 +113,12 @@ __device__ __forceinline__ double2 make_key(double score, double order) {
 __device__ __forceinline__ double lae(double a, double b) {
   const double m = fmax(a, b);
   const float d = (float)(fmin(a, b) - m);  // NaN when both are -inf: discarded below
+#ifdef POB_FAST_LAE
+  // measured: +4 % pairs/s, same strings on 256 pairs, but the ranking score drifts by 1.6e-3 over T = 5000 (bar: 1e-4)
+  const double r = m + (double)__logf(1.0f + __expf(d));
+#else
   const double r = m + (double)log1pf(expf(d));
+#endif
   return (m == ninf()) ? m : r;
 }
 
