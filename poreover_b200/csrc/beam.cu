@@ -38,6 +38,7 @@
 namespace {
 
 enum { MODE_1D = 0, MODE_ROW = 1, MODE_ROWCOL = 2 };
+enum { MIR_DEPTH = 8 };  // newest `prob` values of every (active slot, read) mirrored in shared memory
 enum { PS_ROOT = 0, PS_INE = 1, PS_FROZEN = 2, PS_DEAD = 3 };  // where a node's parent values come from
 enum { KID_ACTIVE = 0, KID_REVIVE = 1, KID_FRESH = 2 };
 
@@ -79,6 +80,7 @@ struct BeamParams {
   int n_items, W, mode, NP, CAP0, CAP1, RQ, EMAX;
   int dbg_noreclaim, dbg_noreuse;
   int inspect_every;        // the retire queue is inspected every this many expansions (its headers are cold)
+  int mir_off;              // shared-memory prob mirror: byte offset, or -1 when it does not fit
   int prefetch;             // pull the probability rows / envelope entries of coming steps towards the SM
   double* dbg_trace;        // optional: [step][2] = (top score, sum of beam scores) after each prune
   char* ws;                 // workspace, one stride per resident CTA
@@ -176,6 +178,7 @@ struct EngState {
                     // build_envelope's repair pass clamps some rows far back, envelope.py:82-85)
   int cap[2], mask[2];
   ReadView rv[2];
+  int mir_off;  // byte offset in pob_smem of the prob mirror (MIR_DEPTH newest values per active slot and read), -1 = off
   uint32_t* trace;
 };
 __shared__ EngState g_es;
@@ -258,6 +261,18 @@ struct Engine {
     return reinterpret_cast<Ent*>(g_es.win[r]) + (size_t)slot * g_es.cap[r];
   }
 
+  // Shared-memory mirror of the newest MIR_DEPTH `prob` values of an active (slot, read): the clean-band maximum
+  // reads them from here instead of the window in global memory (which is served from L2 at best).  Valid for the
+  // time keys [mlo, mhi); every write of a window entry of an active node also writes the mirror.  A node that has
+  // just taken its active slot (a_che < 0: nothing written yet) has an empty mirror whatever the bounds say.
+  __device__ __forceinline__ double* mir_base(int a, int r) const {
+    return reinterpret_cast<double*>(pob_smem + g_es.mir_off) + (size_t)(2 * a + r) * MIR_DEPTH;
+  }
+  __device__ __forceinline__ int* mir_lo() const {
+    return reinterpret_cast<int*>(pob_smem + g_es.mir_off + (size_t)g_es.EMAX * 2 * MIR_DEPTH * 8);
+  }
+  __device__ __forceinline__ int* mir_hi() const { return mir_lo() + 2 * g_es.EMAX; }
+
   // value of the root at time t (parent of depth-1 nodes)
   __device__ __forceinline__ double root_prob(int r, int t) const {
     if (t == -1) return 0.0;
@@ -330,6 +345,15 @@ struct Engine {
       out.prob = prob;
     }
     *(wbase(a_slot[a], r) + ((t + 1) & g_es.mask[r])) = out;
+    if (g_es.mir_off >= 0) {
+      mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
+      int mlo = mir_lo()[2 * a + r], mhi = mir_hi()[2 * a + r];
+      if (a_che[2 * a + r] < 0) mlo = mhi = 0;  // first write since the node took this slot: the bounds are its predecessor's
+      if (mhi > mlo && t == mhi) mhi = t + 1;
+      else if (!(t >= mlo && t < mhi)) { mlo = t; mhi = t + 1; }
+      if (mhi - mlo > MIR_DEPTH) mlo = mhi - MIR_DEPTH;
+      mir_lo()[2 * a + r] = mlo; mir_hi()[2 * a + r] = mhi;
+    }
     int lo = in.lo, hi = in.hi;
     if (t >= hi) { if (t > hi) lo = t; hi = t + 1; }
     else if (t < lo) { lo = t; hi = t + 1; }
@@ -385,7 +409,7 @@ struct Engine {
     const bool used = a < EMAX && a_slot[a] >= 0;
     const bool on = used && ((reads_mask >> r) & 1);
     int lo = 0, hi = 0, plo = 0, phi = 0, pstat = PS_DEAD, pa = 0, cs = 0;
-    bool same = false;
+    bool same = false, was_fresh = true;
     double p_prev = ninf(), ng_prev = ninf(), g_prev = ninf(), maxv = ninf();
     const int ts = r ? s1 : s0, te = r ? e1 : e0;
     Ent* wb = nullptr;
@@ -400,6 +424,7 @@ struct Engine {
     long yrowb = 0;
     PCLK(12);
     deferred_finalize();
+    const bool mirror = g_es.mir_off >= 0;
     PCLK(13);
     if (on && te > ts) {
       const int slot = a_slot[a];
@@ -418,6 +443,7 @@ struct Engine {
         ycol_blank = (long)v.cblank * es;
       }
       const int che = a_che[2 * a + r];
+      was_fresh = che < 0;
       cs = full ? ts : min(max(che, ts), te);
       pstat = a_pstat[a];
       same = a_same[a] != 0;
@@ -434,13 +460,30 @@ struct Engine {
       // clean part of the band: only the maximum is needed (independent loads, four in flight)
       {
         const int c0 = max(ts, lo), c1 = min(cs, hi);
-        for (int t = c0; t < c1; t += 4) {
-          double v0 = ninf(), v1 = ninf(), v2 = ninf(), v3 = ninf();
-          v0 = (wb + ((t + 1) & wmask))->prob;
-          if (t + 1 < c1) v1 = (wb + ((t + 2) & wmask))->prob;
-          if (t + 2 < c1) v2 = (wb + ((t + 3) & wmask))->prob;
-          if (t + 3 < c1) v3 = (wb + ((t + 4) & wmask))->prob;
-          maxv = fmax(fmax(maxv, v0), fmax(fmax(v1, v2), v3));
+        // [c0, g1) from the window, [g1, m1) from the shared-memory mirror, [m1, c1) from the window again (rare)
+        int g1 = c0, m1 = c0;
+        if (mirror && che >= 0) {
+          const int mlo = mir_lo()[2 * a + r], mhi = mir_hi()[2 * a + r];
+          g1 = min(c1, max(c0, mlo));
+          m1 = min(c1, max(g1, mhi));
+          const double* mb = mir_base(a, r);
+#pragma unroll
+          for (int q = 0; q < MIR_DEPTH; ++q) {
+            const int t = g1 + q;
+            if (t < m1) maxv = fmax(maxv, mb[(t + 1) & (MIR_DEPTH - 1)]);
+          }
+        }
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+          const int b0 = part ? m1 : c0, b1 = part ? c1 : g1;
+          for (int t = b0; t < b1; t += 4) {
+            double v0 = ninf(), v1 = ninf(), v2 = ninf(), v3 = ninf();
+            v0 = (wb + ((t + 1) & wmask))->prob;
+            if (t + 1 < b1) v1 = (wb + ((t + 2) & wmask))->prob;
+            if (t + 2 < b1) v2 = (wb + ((t + 3) & wmask))->prob;
+            if (t + 3 < b1) v3 = (wb + ((t + 4) & wmask))->prob;
+            maxv = fmax(fmax(maxv, v0), fmax(fmax(v1, v2), v3));
+          }
         }
       }
     }
@@ -498,6 +541,7 @@ struct Engine {
             prob = lae(pv + yl, p_prev + yb);
             o->prob = prob;
           }
+          if (mirror) mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
           p_prev = prob;
           if (prob > maxv) maxv = prob;
           yl = yl_n; yb = yb_n; pv = pv_n;
@@ -595,6 +639,7 @@ struct Engine {
               o->prob = prob;
               pb.x = prob; pb.y = ninf();
             }
+            if (mirror) mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
             p_prev = prob;
             if (prob > maxv) maxv = prob;
           } else {
@@ -621,6 +666,13 @@ struct Engine {
         if (hi - lo > g_es.cap[r]) lo = hi - g_es.cap[r];
         a_lo[2 * a + r] = lo; a_hi[2 * a + r] = hi;
         a_che[2 * a + r] = te;
+        if (mirror) {
+          // this sweep wrote [cs, te): joined with what the mirror held when the two ranges touch
+          const int mlo = mir_lo()[2 * a + r], mhi = mir_hi()[2 * a + r];
+          int nlo = cs;
+          if (!was_fresh && mhi > mlo && cs >= mlo && cs <= mhi) nlo = mlo;
+          mir_lo()[2 * a + r] = max(nlo, te - MIR_DEPTH); mir_hi()[2 * a + r] = te;
+        }
         a_maxp[2 * a + r] = maxv;  // reset + max over the band
       } else {
         maxv = a_maxp[2 * a + r];  // empty band: max_prob left stale (A.6b)
@@ -977,6 +1029,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
   if (tid == 0) {
     g_es.W = G.W; g_es.NP = G.NP; g_es.RQ = G.RQ; g_es.EMAX = G.EMAX; g_es.mode = G.mode;
     g_es.noreclaim = G.dbg_noreclaim; g_es.inspect_every = G.inspect_every;
+    g_es.mir_off = G.mir_off;
     g_es.cap[0] = G.CAP0; g_es.cap[1] = G.CAP1; g_es.mask[0] = G.CAP0 - 1; g_es.mask[1] = G.CAP1 - 1;
     g_es.rv[0] = make_view(G.r[0], item);
     if (G.mode != MODE_1D) g_es.rv[1] = make_view(G.r[1], item); else { g_es.rv[1] = g_es.rv[0]; g_es.rv[1].T = 0; }
@@ -1343,7 +1396,15 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   int threads = (((mode == MODE_1D ? 1 : 2) * P.EMAX + 31) / 32) * 32;
   if (threads > 1024) return POB_EUNSUPPORTED;
   if (threads < 64) threads = 64;
-  const size_t smem = smem_bytes(W, P.NP, P.EMAX);
+  size_t smem = smem_bytes(W, P.NP, P.EMAX);
+  // prob mirror: 2 * EMAX * MIR_DEPTH doubles + two int bounds per (slot, read); only where it costs no CTA per SM
+  P.mir_off = -1;
+  {
+    const size_t mir = (size_t)P.EMAX * 2 * MIR_DEPTH * 8 + (size_t)P.EMAX * 2 * 2 * 4;
+    bool on = mode != MODE_1D && smem + mir <= 74 * 1024;  // three CTAs per SM share 227 KB
+    if (const char* e = getenv("POB_DEBUG_MIRROR")) on = on && atoi(e) != 0;
+    if (on) { P.mir_off = (int)smem; smem = pob_align_up(smem + mir, 16); }
+  }
   if (smem > 200 * 1024) return POB_EUNSUPPORTED;
   void (*kern)(BeamParams);
   const bool ctc = model == POB_MODEL_CTC;
