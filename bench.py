@@ -324,10 +324,10 @@ def run_ours(args):
         # DRAM traffic of one launch of this kernel on this workload, from the committed ncu --set full capture
         traffic, traffic_src = None, None
         try:
-            ns = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01_d.json")))["viterbi5_f32_kernel"]
+            ns = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01_e.json")))["viterbi5_f32_kernel"]
             if vb.n == 10000 and args.T == 5000:
                 traffic = ns["dram_traffic_bytes_per_launch"]
-                traffic_src = "profiles/ncu_summary_r01_d.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)"
+                traffic_src = "profiles/ncu_summary_r01_e.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)"
         except (OSError, ValueError, KeyError):
             pass
         roof = {"kernel": "viterbi_ctc (%d reads, T=%d, %.2f GB in)" % (vb.n, args.T, float(vb.lens.sum()) * 20 / 1e9),
