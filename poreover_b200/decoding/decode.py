@@ -121,7 +121,7 @@ MODEL_TYPE = {'poreover': 'ctc', 'bonito': 'ctc_merge_repeats', 'guppy': 'ctc_fl
               'flipflop': 'ctc_flipflop'}  # decode.py:172
 
 
-def decode_models(models, algorithm="viterbi", beam_width=25):
+def decode_models(models, algorithm="viterbi", beam_width=25, device=None):
     """Decode a list of transducers in as few GPU calls as possible (one per model kind)."""
     out = [None] * len(models)
     by_kind = {}
@@ -131,13 +131,13 @@ def decode_models(models, algorithm="viterbi", beam_width=25):
         arrays = [models[i].device_array() for i in idx]
         if algorithm == 'viterbi':
             if kind == 'flipflop':
-                seqs = batch.flipflop_viterbi_batch(arrays)[0]
+                seqs = batch.flipflop_viterbi_batch(arrays, device=device)[0]
             else:
-                seqs = batch.viterbi_batch(arrays, kind)[0]
+                seqs = batch.viterbi_batch(arrays, kind, device=device)[0]
         elif algorithm == 'beam':
             if kind == 'flipflop':
                 raise NotImplementedError("flip-flop beam search is out of scope (the reference's own test fails)")
-            seqs = batch.beam_search_batch(arrays, beam_width, MODEL_TYPE[kind])[0]
+            seqs = batch.beam_search_batch(arrays, beam_width, MODEL_TYPE[kind], device=device)[0]
         else:
             raise NotImplementedError("--algorithm prefix is the reference's legacy O(T^2) search; not on the GPU path")
         for i, s in zip(idx, seqs):
@@ -163,8 +163,12 @@ def decode(args):
     if len(in_files) > 1:
         logger.info("found {} reads to decode".format(len(in_files)))
         logger.info("writing sequences to {0}.fasta".format(args.out))
-    models = [model_from_trace(p, args.basecaller) for p in in_files]
-    seqs = decode_models(models, args.algorithm, args.beam_width)
+    # the reference farms files out to a process pool (decode.py:158-162); here they go through the GPU in chunks,
+    # and under `torchrun` every rank decodes the chunks it pulls from a host work queue on its own GPU
+    from .. import multigpu
+    seqs = multigpu.decode_files_all_gpus(args, in_files)
+    if seqs is None:
+        return  # non-zero ranks of a multi-process launch
     with open(args.out + '.fasta', 'w') as out_fasta:
         for p, sq in zip(in_files, seqs):
             print(fasta_format(Path(p).stem, sq), file=out_fasta)

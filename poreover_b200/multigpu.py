@@ -59,6 +59,38 @@ def run_sharded(items, cost, process_chunk, chunk=256, group=None, store=None):
     return out
 
 
+def _host_group():
+    """(world, local rank, store, group) of the host-side (gloo) process group; single process: (1, local, None, None)."""
+    rank, world, local = dist_info()
+    if world == 1:
+        return world, local, None, None
+    import datetime
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", timeout=datetime.timedelta(hours=4))
+    return world, local, dist.distributed_c10d._get_default_store(), dist.group.WORLD
+
+
+def decode_files_all_gpus(args, in_files, chunk=1024):
+    """`decode` CLI path (decode.py:114-167): files are independent, every rank loads and decodes the chunks it pulls
+    on its own GPU; rank 0 gets the sequences in input order (None elsewhere)."""
+    from .decoding import decode as dec
+    world, local, store, group = _host_group()
+
+    def size_of(p):
+        try:
+            return os.path.getsize(p)
+        except OSError:
+            return 0
+
+    def work(paths):
+        models = [dec.model_from_trace(p, args.basecaller) for p in paths]
+        return dec.decode_models(models, args.algorithm, args.beam_width, device=local)
+
+    chunk = max(8, min(chunk, -(-len(in_files) // (4 * world))))
+    return run_sharded(in_files, [size_of(p) for p in in_files], work, chunk, group, store)
+
+
 def decode_pairs_all_gpus(args, pair_list, chunk=256):
     """CLI path: every rank decodes the chunks it pulls on its own GPU (LOCAL_RANK)."""
     from .decoding import pair_decode as pd
