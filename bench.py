@@ -340,6 +340,22 @@ def run_ours(args):
                 "cell_updates_per_launch": counters["cell_updates"], "ms_per_launch": bk["ms"] / max(1, bk["launches"]),
                 "cell_updates_per_s": counters["cell_updates"] / max(1e-9, bk["ms"] / max(1, bk["launches"]) / 1e3),
                 "share_of_step": bk["ms"] / tot_ms if tot_ms else None}
+        # the same kernel in the HBM frame, for comparison: minimal bytes a pair needs (20 (U+V) in, 8 U of
+        # envelope, the consensus out) against the measured peak, and its DRAM traffic from the committed ncu capture
+        # (444 pairs per launch there, scaled per pair): the traffic is the engine's per-node windows streaming
+        # through L2, not re-reads of the input
+        beam_ms = bk["ms"] / max(1, bk["launches"])
+        alg = 20.0 * (rows1 + rows2) + 8.0 * rows1 + bases
+        beam["hbm_frame"] = {"algorithmic_bytes_per_launch": alg, "achieved": alg / max(1e-9, beam_ms / 1e3) / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": alg / max(1e-9, beam_ms / 1e3) / 1e9 / peak}
+        try:
+            nb = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01_e.json")))["beam_kernel"]
+            per_pair = (nb["dram_read"] + nb["dram_write"]) * 1e9 / nb["grid"]
+            beam["hbm_frame"]["traffic"] = per_pair * P
+            beam["hbm_frame"]["traffic_source"] = ("profiles/ncu_summary_r01_e.json: (dram__bytes_read.sum + "
+                                                   "dram__bytes_write.sum) / 444 pairs x pairs per launch")
+        except (OSError, ValueError, KeyError):
+            beam["hbm_frame"]["traffic"] = None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
