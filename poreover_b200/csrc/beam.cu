@@ -1378,7 +1378,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   if (const char* e = getenv("POB_DEBUG_NP")) P.NP = atoi(e);
   if (const char* e = getenv("POB_DEBUG_NORECLAIM")) P.dbg_noreclaim = atoi(e);
   if (const char* e = getenv("POB_DEBUG_NOREUSE")) P.dbg_noreuse = atoi(e);
-  P.inspect_every = 4;
+  P.inspect_every = 0;  // set below, once the block size is known
   if (const char* e = getenv("POB_DEBUG_INSPECT_EVERY")) P.inspect_every = atoi(e) > 0 ? atoi(e) : 1;
   P.prefetch = 1;
   if (const char* e = getenv("POB_DEBUG_PREFETCH")) P.prefetch = atoi(e);
@@ -1396,6 +1396,13 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   int threads = (((mode == MODE_1D ? 1 : 2) * P.EMAX + 31) / 32) * 32;
   if (threads > 1024) return POB_EUNSUPPORTED;
   if (threads < 64) threads = 64;
+  if (P.inspect_every == 0) {
+    // about W nodes retire per step and one inspection looks at up to `threads` queue entries: keep the interval
+    // below threads / W so that the queue does not back up (a short pool falls back to every step anyway)
+    P.inspect_every = threads / (W + 8);
+    if (P.inspect_every > 8) P.inspect_every = 8;
+    if (P.inspect_every < 1) P.inspect_every = 1;
+  }
   size_t smem = smem_bytes(W, P.NP, P.EMAX);
   // prob mirror: 2 * EMAX * MIR_DEPTH doubles + two int bounds per (slot, read); only where it costs no CTA per SM
   P.mir_off = -1;
