@@ -516,15 +516,24 @@ struct Engine {
         // iteration instead of two dependent ones (same operations on the same operands, hence the same values)
         double ng_cur = ninf();
         if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_cur = lae(pv + yl, ng_prev + yl);
+        // inputs are requested two timesteps ahead: those of t+1 were loaded during iteration t-1 (or just below),
+        // so the no-gap chain of t+1 never waits for a load issued in the same iteration
+        double yl_n = 0, yb_n = 0, pv_n = ninf();
+        ylast_p += ystep; yblank_p += ystep;
+        if (cs + 1 < limA) {
+          if (f64) { yl_n = __ldg((const double*)ylast_p); yb_n = __ldg((const double*)yblank_p); }
+          else { yl_n = (double)__ldg((const float*)ylast_p); yb_n = (double)__ldg((const float*)yblank_p); }
+          if (pstat == PS_INE || pstat == PS_FROZEN) pv_n = frozen_at(pwb, cs + 1, wmask, plo, phi, same);
+          else if (pstat == PS_ROOT) pv_n = root_prob(r, cs);
+        }
         for (int t = cs; t < limA; ++t) {
-          // inputs of the next timestep are requested before this one is evaluated
-          double yl_n = 0, yb_n = 0, pv_n = ninf();
+          double yl_n2 = 0, yb_n2 = 0, pv_n2 = ninf();
           ylast_p += ystep; yblank_p += ystep;
-          if (t + 1 < limA) {
-            if (f64) { yl_n = __ldg((const double*)ylast_p); yb_n = __ldg((const double*)yblank_p); }
-            else { yl_n = (double)__ldg((const float*)ylast_p); yb_n = (double)__ldg((const float*)yblank_p); }
-            if (pstat == PS_INE || pstat == PS_FROZEN) pv_n = frozen_at(pwb, t + 1, wmask, plo, phi, same);
-            else if (pstat == PS_ROOT) pv_n = root_prob(r, t);
+          if (t + 2 < limA) {
+            if (f64) { yl_n2 = __ldg((const double*)ylast_p); yb_n2 = __ldg((const double*)yblank_p); }
+            else { yl_n2 = (double)__ldg((const float*)ylast_p); yb_n2 = (double)__ldg((const float*)yblank_p); }
+            if (pstat == PS_INE || pstat == PS_FROZEN) pv_n2 = frozen_at(pwb, t + 2, wmask, plo, phi, same);
+            else if (pstat == PS_ROOT) pv_n2 = root_prob(r, t + 1);
           }
           double prob;
           Ent* o = wb + ((t + 1) & wmask);
@@ -545,6 +554,7 @@ struct Engine {
           p_prev = prob;
           if (prob > maxv) maxv = prob;
           yl = yl_n; yb = yb_n; pv = pv_n;
+          yl_n = yl_n2; yb_n = yb_n2; pv_n = pv_n2;
         }
       }
     }
