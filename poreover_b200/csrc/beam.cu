@@ -1187,9 +1187,12 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     int* const senvt = sh + 28;  // [2][2] band of column v (slot v & 1)
     if (tid == 0) { senv[0] = env[0]; senv[1] = env[1]; senvt[0] = envt[0]; senvt[1] = envt[1]; }
     __syncthreads();
+    // the staging and prefetching below is done by the last threads of the block: they own no (node, read) item, so
+    // the extra instructions stay off the warps whose work the step's barriers wait for
+    const int aux = NT - 1;
     while (u <= U - 1 && v <= V - 1) {
       const int ers = senv[2 * (u & 1)], ere = senv[2 * (u & 1) + 1], ecs = senvt[2 * (v & 1)], ece = senvt[2 * (v & 1) + 1];
-      if (tid == 0) {
+      if (tid == aux) {
         if (u + 1 < U) cp_async8(senv + 2 * ((u + 1) & 1), env + 2 * (u + 1));
         if (v + 1 < V) cp_async8(senvt + 2 * ((v + 1) & 1), envt + 2 * (v + 1));
         cp_async_commit();
@@ -1201,7 +1204,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
         const int nb = sh[SH_NB];
         if (nb < W && tid == 0) sh[SH_STATUS] |= POB_ST_SHORT_BEAM_SKIP;
         const bool mine = tid < EMAX && a_slot[tid] >= 0 && a_inbeam[tid];
-        if (tid == 0) cp_async_wait_all();  // visible to everyone after the barriers inside update_all
+        if (tid == aux) cp_async_wait_all();  // visible to everyone after the barriers inside update_all
         update_all(mine, tid, 1, v);
         if (mine) n_updates++;
         ++v; ++nsteps;
@@ -1212,7 +1215,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
         const int nb = sh[SH_NB];
         if (nb < W && tid == 0) sh[SH_STATUS] |= POB_ST_SHORT_BEAM_SKIP;
         const bool mine = tid < EMAX && a_slot[tid] >= 0 && a_inbeam[tid];
-        if (tid == 0) cp_async_wait_all();
+        if (tid == aux) cp_async_wait_all();
         update_all(mine, tid, 0, u);
         if (mine) n_updates++;
         ++u; ++nsteps;
@@ -1224,24 +1227,25 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
       // The probability rows and envelope entries of the coming steps are pulled towards the SM ahead of time: every
       // step touches one new row per read, and without this each thread of the sweep waits for it to come from HBM.
       if (G.prefetch) {
-        if (tid < 4) {
-          const int r = tid & 1;
+        const int k = tid - (NT - 8);  // threads NT-8 .. NT-3
+        if (k >= 0 && k < 4) {
+          const int r = k & 1;
           const ReadView& pv = g_es.rv[r];
-          const int t = (r ? row_end : col_end) + ((tid & 2) ? 64 : 6);
+          const int t = (r ? row_end : col_end) + ((k & 2) ? 64 : 6);
           if (t < pv.T) {
             const char* q = (const char*)pv.base + (size_t)pv.prow(t) * pv.S * (pv.f64 ? 8 : 4);
-            if (tid & 2) prefetch_l2(q); else prefetch_l1(q);
+            if (k & 2) prefetch_l2(q); else prefetch_l1(q);
           }
-        } else if (tid < 6) {
+        } else if (k >= 4 && k < 6) {
           const int ahead = 32;
-          if (tid == 4 && u + ahead < U) prefetch_l1(env + 2 * (u + ahead));
-          if (tid == 5 && v + ahead < V) prefetch_l1(envt + 2 * (v + ahead));
+          if (k == 4 && u + ahead < U) prefetch_l1(env + 2 * (u + ahead));
+          if (k == 5 && v + ahead < V) prefetch_l1(envt + 2 * (v + ahead));
         }
       }
       sweep(3, col_start, col_end, row_start, row_end, G.dbg_noreuse != 0, n_updates);
       prune();
       dbg_record(G, nsteps);
-      if (tid == 0) cp_async_wait_all();  // next row / column bands: visible after the barriers of the expansion
+      if (tid == aux) cp_async_wait_all();  // next row / column bands: visible after the barriers of the expansion
       expand_and_retire(u, v);  // later reads are at t-1 >= u (read 0) and >= v (read 1)
       ++u; ++v; ++nsteps;
     }
