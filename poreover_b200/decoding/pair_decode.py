@@ -241,49 +241,82 @@ def _paths(args, in_path):
     return path1, path2
 
 
-def decode_pairs(args, pair_list, device=None, chunk=1024):
-    """Decode [(name1, name2), ...] -> list of pair_decode_helper-style results, in input order."""
+def load_pairs(args, sub):
+    """Host stage of a chunk of pairs: the files of both reads -> packed log-probability batches (or, for the staged
+    flags, per-read arrays).  No GPU work; runs on the loader threads while the previous chunk is being decoded."""
+    from .. import ingest
+    meta, files1, files2 = [], [], []
+    for in_path in sub:
+        path1, path2 = _paths(args, in_path)
+        files1.append(os.path.join(args.dir, path1))
+        files2.append(os.path.join(args.dir, path2))
+        meta.append((in_path, path1, path2))
+    if _staged(args):
+        models = ingest.load_models(files1 + files2, args.basecaller)
+        a, b = models[:len(sub)], models[len(sub):]
+        for x, y in zip(a, b):
+            assert x.kind == y.kind
+        kind = a[0].kind if a else None
+        meta = [m + (kind,) for m in meta]
+        return meta, [x.device_array() for x in a], [y.device_array() for y in b], kind
+    try:
+        b1 = ingest.load_reads(files1, args.basecaller)
+        b2 = ingest.load_reads(files2, args.basecaller, rc=1 if args.reverse_complement else 0)
+    except NotImplementedError:
+        raise NotImplementedError("flip-flop pair decoding is out of scope (README.md:97 of the reference)")
+    for x, y in zip(b1.kinds, b2.kinds):
+        assert x == y
+    kind = b1.kinds[0] if b1.kinds else None
+    return [m + (kind,) for m in meta], b1, b2, kind
+
+
+def decode_loaded(args, payload, device=None):
+    """GPU stage of a chunk: load_pairs' payload -> pair_decode_helper-style results, in the chunk's order."""
+    meta, m1, m2, kind = payload
+    n = len(meta)
+    if n == 0:
+        return []
+    if kind == 'flipflop':
+        raise NotImplementedError("flip-flop pair decoding is out of scope (README.md:97 of the reference)")
+    if _staged(args):
+        return _decode_pairs_staged(args, meta, m1, m2, kind, device)
+    results = [None] * n
+    res = batch.pair_decode_batch(m1, m2, kind=kind, beam_width=args.beam_width, padding=args.padding,
+                                  method=args.beam_search_method, device=device)  # rc and layout travel in the batches
+    for k, (r, (in_path, path1, path2, _)) in enumerate(zip(res, meta)):
+        if r["status"] & (batch._lib.ST_MAPPING_WRAP | batch._lib.ST_EMPTY):
+            continue  # the reference's assertion fires and the pool drops the pair silently
+        summary = {'read1': in_path[0], 'read2': in_path[1], 'length1': r["length1"], 'length2': r["length2"]}
+        if r["status"] & batch._lib.ST_SKIPPED_LENGTH:
+            summary['skipped'] = 1
+            results[k] = [summary]
+            continue
+        summary['sequence_identity'] = r["identity"]
+        if r["skipped"]:
+            summary['skipped'] = 1
+            results[k] = [summary]
+            continue
+        summary['skipped'] = 0
+        results[k] = (
+            fasta_format(in_path[0], r["basecall1"]) + fasta_format(in_path[1], r["basecall2"]),
+            fasta_format('consensus;{};{}'.format(path1.stem, path2.stem), r["consensus"]),
+            summary)
+    return results
+
+
+def decode_pairs(args, pair_list, device=None, chunk=2048):
+    """Decode [(name1, name2), ...] -> list of pair_decode_helper-style results, in input order.
+
+    Chunks of pairs go through a two-stage pipeline: the files of chunk k+1 are loaded (ingest.py) while the GPU
+    decodes chunk k."""
+    from .. import ingest
     _check_args(args)
     results = [None] * len(pair_list)
-    for c0 in range(0, len(pair_list), chunk):
-        sub = pair_list[c0:c0 + chunk]
-        m1, m2, meta = [], [], []
-        for in_path in sub:
-            path1, path2 = _paths(args, in_path)
-            a = decode.model_from_trace(os.path.join(args.dir, path1), args.basecaller)
-            b = decode.model_from_trace(os.path.join(args.dir, path2), args.basecaller)
-            assert a.kind == b.kind
-            m1.append(a.device_array())
-            m2.append(b.device_array())
-            meta.append((in_path, path1, path2, a.kind))
-        kind = meta[0][3]
-        if kind == 'flipflop':
-            raise NotImplementedError("flip-flop pair decoding is out of scope (README.md:97 of the reference)")
-        if _staged(args):
-            results[c0:c0 + len(sub)] = _decode_pairs_staged(args, meta, m1, m2, kind, device)
-            continue
-        res = batch.pair_decode_batch(m1, m2, kind=kind, beam_width=args.beam_width, padding=args.padding,
-                                      method=args.beam_search_method, rc2=bool(args.reverse_complement),
-                                      device=device)
-        for k, (r, (in_path, path1, path2, _)) in enumerate(zip(res, meta)):
-            if r["status"] & (batch._lib.ST_MAPPING_WRAP | batch._lib.ST_EMPTY):
-                results[c0 + k] = None  # the reference's assertion fires and the pool drops the pair silently
-                continue
-            summary = {'read1': in_path[0], 'read2': in_path[1], 'length1': r["length1"], 'length2': r["length2"]}
-            if r["status"] & batch._lib.ST_SKIPPED_LENGTH:
-                summary['skipped'] = 1
-                results[c0 + k] = [summary]
-                continue
-            summary['sequence_identity'] = r["identity"]
-            if r["skipped"]:
-                summary['skipped'] = 1
-                results[c0 + k] = [summary]
-                continue
-            summary['skipped'] = 0
-            results[c0 + k] = (
-                fasta_format(in_path[0], r["basecall1"]) + fasta_format(in_path[1], r["basecall2"]),
-                fasta_format('consensus;{};{}'.format(path1.stem, path2.stem), r["consensus"]),
-                summary)
+    starts = iter(range(0, len(pair_list), chunk))
+    for c0, payload in ingest.Lookahead(lambda: next(starts, None),
+                                        lambda c0: load_pairs(args, pair_list[c0:c0 + chunk])):
+        res = decode_loaded(args, payload, device)
+        results[c0:c0 + len(res)] = res
     return results
 
 

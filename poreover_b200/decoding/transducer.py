@@ -21,29 +21,54 @@ class transducer:
     def __init__(self, log_prob, kind, alphabet):
         log_prob = np.asarray(log_prob)
         # The reference widens to float64 (transducer.py:16).  float32 input widens exactly, so the
-        # float32 original is kept for the device (half the bytes, identical results).
+        # float32 original is kept for the device (half the bytes, identical results); the float64 copy and the
+        # all-ones transition table (transducer.py:22) are built on first access -- the batch drivers never read
+        # them, and at a few thousand reads per second their allocation was most of the loader's time.
         self._f32 = np.ascontiguousarray(log_prob) if log_prob.dtype == np.float32 else None
-        self.log_prob = log_prob.astype(np.float64)
+        self._lp64 = None if self._f32 is not None else log_prob.astype(np.float64)
+        self._transition = None
         self.t_max = len(log_prob)
         self.alphabet = alphabet
         self.num_states = len(alphabet)
         self.kind = kind
-        assert (self.num_states == len(self.log_prob[0]))
-        self.transition = np.ones((self.t_max, self.num_states))
+        assert (self.num_states == (log_prob.shape[1] if log_prob.ndim > 1 else len(log_prob[0])))
+
+    @property
+    def log_prob(self):
+        if self._lp64 is None:
+            self._lp64 = self._f32.astype(np.float64)
+        return self._lp64
+
+    @log_prob.setter
+    def log_prob(self, value):
+        self._lp64 = value
+        self._f32 = None  # an assigned table replaces the loader's float32 original
+
+    @property
+    def transition(self):
+        if self._transition is None:
+            self._transition = np.ones((self.t_max, self.num_states))
+        return self._transition
+
+    @transition.setter
+    def transition(self, value):
+        self._transition = value
 
     def __getitem__(self, i):
         return self.log_prob.__getitem__(i)
 
     def device_array(self):
         """The array handed to the C ABI: float32 when that is exact, else float64."""
-        if self._f32 is not None and self._f32.shape == self.log_prob.shape:
+        if self._f32 is not None:
             return self._f32
         return np.ascontiguousarray(self.log_prob)
 
     def _reverse(self, perm):
-        self.log_prob = self.log_prob[::-1, perm]
         if self._f32 is not None:
             self._f32 = np.ascontiguousarray(self._f32[::-1, perm])
+            self._lp64 = None
+        else:
+            self.log_prob = self.log_prob[::-1, perm]
 
     def argmax_decode(self, return_path=False):
         """transducer.py:27-33 (repeats kept, blanks dropped: the 'poreover' rule)"""

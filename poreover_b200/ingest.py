@@ -1,0 +1,212 @@
+"""Batched ingest of basecaller output files for the command-line drivers.
+
+The reference loads one file per pool task (decode.py:41-51, :67-112, pair_decode.py:321-356).  With the search on
+the GPU the loader is what a `pair-decode` run waits for: np.load's header machinery, the float64 copy and the
+all-ones transition table of every transducer object, the column permutation and the packing copy cost more host
+time per pair than the GPU needs to decode it.  Here the files of a chunk are read by a thread pool (file reads and
+numpy's ufunc loops release the GIL) and the logarithm is written straight into the packed buffer that crosses the
+C ABI:
+
+  * the arithmetic is still numpy's, on the same C-contiguous float32 array, so every value is bit-identical to what
+    decode.load_logits returns (a CUDA logf would not be, and Viterbi ties would move: DESIGN.md section 1);
+  * bonito files stay in file order (blank first): the kernels resolve the layout in their address computation
+    (POB_BLANK_FIRST), which replaces the permutation copy of decode.py:79;
+  * anything that is not a plain 2-D probability table (.csv, 3-D logits, float64 files, .hdf5/.fast5) goes through
+    decode.model_from_trace unchanged and is copied into the batch.
+"""
+import os
+import re
+import threading
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from . import _lib
+from .batch import ALIGN_ROWS, ReadBatch
+
+_pool = None
+_pool_lock = threading.Lock()
+
+
+def n_threads():
+    env = os.environ.get("POREOVER_B200_LOADER_THREADS")
+    if env:
+        return max(1, int(env))
+    return max(1, min(32, os.cpu_count() or 4))
+
+
+def pool():
+    """The loader's thread pool (created on first use, shared by all chunks of a run)."""
+    global _pool
+    with _pool_lock:
+        if _pool is None:
+            _pool = ThreadPoolExecutor(max_workers=n_threads(), thread_name_prefix="pob-load")
+        return _pool
+
+
+_HDR = re.compile(r"^\{'descr': '([<|=]?[fiu]\d)', 'fortran_order': False, 'shape': \((\d*(?:, ?\d+)*),?\), \}\s*$")
+
+
+def read_npy(path):
+    """np.load(path) for the plain little-endian C-order arrays bonito and PoreOverNet write, without the Python-level
+    header parsing (most of np.load's time on a 100 KB file).  Anything unusual falls back to np.load."""
+    with open(path, 'rb') as f:
+        buf = f.read()
+    if buf[:6] == b'\x93NUMPY' and len(buf) >= 12:
+        major = buf[6]
+        if major == 1:
+            hlen, start = int.from_bytes(buf[8:10], 'little'), 10
+        elif major in (2, 3):
+            hlen, start = int.from_bytes(buf[8:12], 'little'), 12
+        else:
+            return np.load(path)
+        m = _HDR.match(buf[start:start + hlen].decode('latin1'))
+        if m:
+            dtype = np.dtype(m.group(1))
+            shape = tuple(int(x) for x in m.group(2).replace(' ', '').split(',') if x)
+            count = int(np.prod(shape)) if shape else 1
+            if len(buf) - start - hlen >= count * dtype.itemsize:
+                return np.frombuffer(buf, dtype=dtype, count=count, offset=start + hlen).reshape(shape)
+    return np.load(path)
+
+
+def _is_probability_row(row):
+    """np.isclose(np.sum(row), 1) of decode.py:43, deciding the clear cases without numpy's array machinery."""
+    s = np.sum(row)
+    d = abs(float(s) - 1.0)
+    if d < 5e-6:
+        return True
+    if d > 2e-5 or d != d:  # the test is |s - 1| <= 1e-8 + 1e-5; NaN is never close
+        return False
+    return bool(np.isclose(s, 1))
+
+
+class _Raw:
+    """What pass 1 learned about one file."""
+    __slots__ = ("arr", "direct", "T", "dtype", "kind")
+
+
+def _stage1(path, basecaller):
+    from .decoding import decode
+    r = _Raw()
+    ext = os.path.splitext(path)[1]
+    if ext == '.npy' and basecaller in ('poreover', 'bonito'):
+        raw = read_npy(path)
+        if raw.ndim == 2 and raw.dtype == np.float32 and raw.flags.c_contiguous and _is_probability_row(raw[0]):
+            assert raw.shape[1] == 5  # transducer.py:21
+            r.arr, r.direct, r.T, r.dtype, r.kind = raw, True, raw.shape[0], np.dtype(np.float32), basecaller
+            return r
+    # everything else: the reference's loader path, then the model's own array (blank last)
+    m = decode.model_from_trace(path, basecaller)
+    a = m.device_array()
+    r.arr, r.direct, r.T, r.dtype, r.kind = a, False, a.shape[0], a.dtype, m.kind
+    return r
+
+
+def _chunks(n, parts):
+    step = max(1, -(-n // max(1, parts)))
+    return [(i, min(n, i + step)) for i in range(0, n, step)]
+
+
+def load_reads(paths, basecaller, rc=None, alloc=None):
+    """Load many files of one basecaller into one packed ReadBatch (host memory).
+
+    Equivalent to ReadBatch([decode.model_from_trace(p, basecaller).device_array() for p in paths], rc=rc) up to the
+    column layout: when every file is a plain bonito probability table the batch keeps the file order and says so
+    (layout BLANK_FIRST).  alloc(shape, dtype) may supply the packed buffer (e.g. pinned memory); it must be zeroed.
+    The batch also carries .kinds, the transducer kind of every read."""
+    paths = list(paths)
+    n = len(paths)
+    ex = pool()
+    parts = _chunks(n, 4 * n_threads())
+    raws = [None] * n
+
+    def s1(lohi):
+        for i in range(*lohi):
+            raws[i] = _stage1(paths[i], basecaller)
+
+    list(ex.map(s1, parts))
+    all_direct = n > 0 and all(r.direct for r in raws)
+    first_blank = all_direct and basecaller == 'bonito'
+    f32 = n > 0 and all(r.dtype == np.float32 for r in raws)
+    b = ReadBatch.__new__(ReadBatch)
+    b.np_dtype = np.dtype(np.float32 if f32 else np.float64)
+    b.dtype = _lib.F32 if f32 else _lib.F64
+    b.n = n
+    b.n_states = 5
+    b.kinds = [r.kind for r in raws]  # transducer.kind of every read ('poreover' / 'bonito' / 'flipflop')
+    if 'flipflop' in b.kinds:
+        raise NotImplementedError("flip-flop traces do not go through the packed 5-state loader")
+    for r in raws:
+        if r.arr.ndim != 2 or r.arr.shape[1] != 5:
+            raise ValueError("all reads of a batch must have the same number of states")
+    b.layout = _lib.BLANK_FIRST if first_blank else _lib.BLANK_LAST
+    b.lens = np.array([r.T for r in raws], dtype=np.int32)
+    padded = (b.lens.astype(np.int64) + ALIGN_ROWS - 1) // ALIGN_ROWS * ALIGN_ROWS
+    b.row_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(padded, out=b.row_off[1:])
+    b.total_rows = int(b.row_off[-1])
+    b.data = (alloc or np.zeros)((b.total_rows, 5), b.np_dtype)
+    data, off = b.data, b.row_off
+
+    def s2(lohi):
+        with np.errstate(divide="ignore"):
+            for i in range(*lohi):
+                r = raws[i]
+                dst = data[off[i]:off[i] + r.T]
+                if r.direct and first_blank:
+                    np.log(r.arr, out=dst)  # decode.py:45, written where the kernels read it
+                elif r.direct:
+                    if basecaller == 'bonito':  # mixed batch: permute like decode.py:79
+                        lg = np.log(r.arr)
+                        dst[:, :4] = lg[:, 1:]
+                        dst[:, 4] = lg[:, 0]
+                    else:
+                        np.log(r.arr, out=dst)
+                else:
+                    dst[...] = r.arr  # float32 -> float64 widening is exact
+                raws[i] = None
+
+    list(ex.map(s2, parts))
+    b.rc = None if rc is None else np.ascontiguousarray(np.broadcast_to(np.asarray(rc, dtype=np.uint8), (n,)))
+    return b
+
+
+def load_models(paths, basecaller):
+    """[decode.model_from_trace(p, basecaller) for p in paths] on the loader's thread pool."""
+    from .decoding import decode
+    paths = list(paths)
+    out = [None] * len(paths)
+
+    def work(lohi):
+        for i in range(*lohi):
+            out[i] = decode.model_from_trace(paths[i], basecaller)
+
+    list(pool().map(work, _chunks(len(paths), 4 * n_threads())))
+    return out
+
+
+class Lookahead:
+    """Two-stage pipeline over a stream of chunks: while the caller consumes chunk k (GPU call + result formatting)
+    one background thread runs load(chunk k+1).  Chunks are pulled from `source` (a callable returning the next
+    chunk or None) on the CALLER's thread, so a distributed work queue is only ever touched from there."""
+
+    def __init__(self, source, load):
+        self._source, self._load = source, load
+        self._ex = ThreadPoolExecutor(max_workers=1, thread_name_prefix="pob-prefetch")
+        self._next = self._submit()
+
+    def _submit(self):
+        c = self._source()
+        if c is None:
+            return None
+        return c, self._ex.submit(self._load, c)
+
+    def __iter__(self):
+        try:
+            while self._next is not None:
+                c, fut = self._next
+                self._next = self._submit()  # the load of the following chunk starts before this one is consumed
+                yield c, fut.result()
+        finally:
+            self._ex.shutdown(wait=True)

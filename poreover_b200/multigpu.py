@@ -31,19 +31,21 @@ class WorkQueue:
         return lo, min(self.n, lo + self.chunk)
 
 
-def run_sharded(items, cost, process_chunk, chunk=256, group=None, store=None):
+def run_sharded(items, cost, process_chunk, chunk=256, group=None, store=None, load_chunk=None):
     """Process `items` across all ranks.  cost[i] orders the queue (descending).  process_chunk(list) ->
-    list of results.  Returns the full result list in input order on rank 0, None elsewhere."""
+    list of results.  With load_chunk, a chunk goes through two stages -- payload = load_chunk(list) on a host
+    thread, then process_chunk(payload) -- and the load of the next chunk overlaps the processing of the current
+    one (the queue itself is only touched from the calling thread).  Returns the full result list in input order
+    on rank 0, None elsewhere."""
+    from .ingest import Lookahead
     rank, world, _ = dist_info()
     order = sorted(range(len(items)), key=lambda i: -cost[i])
     q = WorkQueue(len(order), chunk, store if world > 1 else None)
     mine = {}
-    while True:
-        c = q.next()
-        if c is None:
-            break
-        idx = order[c[0]:c[1]]
-        for i, r in zip(idx, process_chunk([items[i] for i in idx])):
+    if load_chunk is None:
+        load_chunk = lambda sub: sub
+    for c, payload in Lookahead(q.next, lambda c: load_chunk([items[i] for i in order[c[0]:c[1]]])):
+        for i, r in zip(order[c[0]:c[1]], process_chunk(payload)):
             mine[i] = r
     if world == 1:
         return [mine.get(i) for i in range(len(items))]
@@ -71,7 +73,7 @@ def _host_group():
     return world, local, dist.distributed_c10d._get_default_store(), dist.group.WORLD
 
 
-def decode_files_all_gpus(args, in_files, chunk=1024):
+def decode_files_all_gpus(args, in_files, chunk=4096):
     """`decode` CLI path (decode.py:114-167): files are independent, every rank loads and decodes the chunks it pulls
     on its own GPU; rank 0 gets the sequences in input order (None elsewhere)."""
     from .decoding import decode as dec
@@ -83,15 +85,26 @@ def decode_files_all_gpus(args, in_files, chunk=1024):
         except OSError:
             return 0
 
-    def work(paths):
-        models = [dec.model_from_trace(p, args.basecaller) for p in paths]
-        return dec.decode_models(models, args.algorithm, args.beam_width, device=local)
+    def load(paths):
+        from . import ingest
+        npy = args.basecaller in ('poreover', 'bonito') and all(os.path.splitext(p)[1] == '.npy' for p in paths)
+        if npy and args.algorithm in ('viterbi', 'beam'):
+            return ingest.load_reads(paths, args.basecaller)  # one packed batch of a single model kind
+        return ingest.load_models(paths, args.basecaller)
+
+    def work(payload):
+        from . import batch
+        if isinstance(payload, batch.ReadBatch):
+            if args.algorithm == 'viterbi':
+                return batch.viterbi_batch(payload, args.basecaller, device=local)[0]
+            return batch.beam_search_batch(payload, args.beam_width, dec.MODEL_TYPE[args.basecaller], device=local)[0]
+        return dec.decode_models(payload, args.algorithm, args.beam_width, device=local)
 
     chunk = max(8, min(chunk, -(-len(in_files) // (4 * world))))
-    return run_sharded(in_files, [size_of(p) for p in in_files], work, chunk, group, store)
+    return run_sharded(in_files, [size_of(p) for p in in_files], work, chunk, group, store, load_chunk=load)
 
 
-def decode_pairs_all_gpus(args, pair_list, chunk=256):
+def decode_pairs_all_gpus(args, pair_list, chunk=2048):
     """CLI path: every rank decodes the chunks it pulls on its own GPU (LOCAL_RANK)."""
     from .decoding import pair_decode as pd
     rank, world, local = dist_info()
@@ -112,6 +125,9 @@ def decode_pairs_all_gpus(args, pair_list, chunk=256):
             return 0
 
     cost = [cost_of(p) for p in pair_list]
-    # small runs: at least ~4 chunks per rank so that every GPU gets work; large runs: 256-pair batches
+    # small runs: at least ~4 chunks per rank so that every GPU gets work; large runs: 2048-pair batches (a B200 holds
+    # 444 pairs in flight, so a batch should be several waves; the next batch is loaded while this one is decoded)
+    pd._check_args(args)
     chunk = max(8, min(chunk, -(-len(pair_list) // (4 * world))))
-    return run_sharded(pair_list, cost, lambda sub: pd.decode_pairs(args, sub, device=local), chunk, group, store)
+    return run_sharded(pair_list, cost, lambda payload: pd.decode_loaded(args, payload, device=local), chunk, group,
+                       store, load_chunk=lambda sub: pd.load_pairs(args, sub))

@@ -24,7 +24,13 @@ def work(chunk):
     return [(x, x * x, rank) for x in chunk]
 
 
-out = multigpu.run_sharded(items, cost, work, chunk=7, group=dist.group.WORLD, store=store)
+def load(chunk):
+    # host stage of the two-stage pipeline: runs one chunk ahead on the prefetch thread
+    time.sleep(0.001 * len(chunk))
+    return list(chunk)
+
+
+out = multigpu.run_sharded(items, cost, work, chunk=7, group=dist.group.WORLD, store=store, load_chunk=load)
 counts = [None, None]
 dist.all_gather_object(counts, len(seen))
 if rank == 0:

@@ -1,0 +1,197 @@
+"""CPU: the batched file ingest of the command-line drivers (poreover_b200/ingest.py).
+Every array that reaches the C ABI must be bit-identical to what the reference's loader path
+(decode.model_from_trace -> transducer) produces; only the column order of plain bonito tables may differ, and the
+batch says so."""
+import os
+import threading
+import time
+
+import numpy as np
+import pytest
+
+from poreover_b200 import _lib, batch, ingest, synth
+from poreover_b200.decoding import decode as gdecode
+from poreover_b200.decoding import transducer
+
+
+def _reference_arrays(paths, basecaller):
+    return [gdecode.model_from_trace(p, basecaller).device_array() for p in paths]
+
+
+def _rows(b, i):
+    return b.data[b.row_off[i]:b.row_off[i] + b.lens[i]]
+
+
+def test_bonito_tables_keep_file_order_and_values(tmp_path):
+    paths = []
+    for k in range(6):
+        f1, f2 = synth.save_pair(str(tmp_path), k, 200 + 17 * k)
+        paths += [str(tmp_path / f1), str(tmp_path / f2)]
+    ref = _reference_arrays(paths, "bonito")
+    b = ingest.load_reads(paths, "bonito", rc=1)
+    assert b.layout == _lib.BLANK_FIRST and b.dtype == _lib.F32 and b.n == len(paths)
+    assert b.kinds == ["bonito"] * len(paths) and b.rc.tolist() == [1] * len(paths)
+    assert all(o % batch.ALIGN_ROWS == 0 for o in b.row_off)
+    for i, a in enumerate(ref):
+        got = _rows(b, i)[:, [1, 2, 3, 4, 0]]  # decode.py:79 applied to the file-order rows
+        assert got.dtype == a.dtype and np.array_equal(got, a)
+    # padding rows stay zero, like ReadBatch
+    same = batch.ReadBatch([a[:, [4, 0, 1, 2, 3]] for a in ref])
+    assert np.array_equal(same.data, b.data) and np.array_equal(same.row_off, b.row_off)
+
+
+def test_poreover_tables_and_exact_zero_probabilities(tmp_path):
+    rng = np.random.default_rng(3)
+    paths = []
+    for k in range(4):
+        p = rng.dirichlet(np.ones(5), size=50 + k).astype(np.float32)
+        p[3, 2] = 0.0  # log(0) = -inf must come through without a warning turning into an error
+        np.save(tmp_path / ("p%d.npy" % k), p)
+        paths.append(str(tmp_path / ("p%d.npy" % k)))
+    ref = _reference_arrays(paths, "poreover")
+    b = ingest.load_reads(paths, "poreover")
+    assert b.layout == _lib.BLANK_LAST and b.kinds == ["poreover"] * 4
+    for i, a in enumerate(ref):
+        assert np.array_equal(_rows(b, i), a)
+        assert np.isneginf(_rows(b, i)[3, 2])
+
+
+def test_unusual_files_take_the_reference_loader_path(tmp_path):
+    rng = np.random.default_rng(4)
+    plain = rng.dirichlet(np.ones(5), size=40).astype(np.float32)
+    f64 = rng.dirichlet(np.ones(5), size=33)                               # float64 probabilities
+    logits3d = rng.normal(size=(3, 20, 5)).astype(np.float32)              # windows x time x states, not normalised
+    fortran = np.asfortranarray(rng.dirichlet(np.ones(5), size=25).astype(np.float32))
+    names = {"a.npy": plain, "b.npy": f64, "c.npy": logits3d, "d.npy": fortran}
+    paths = []
+    for n, a in names.items():
+        np.save(tmp_path / n, a)
+        paths.append(str(tmp_path / n))
+    for basecaller in ("bonito", "poreover"):
+        ref = _reference_arrays(paths, basecaller)
+        b = ingest.load_reads(paths, basecaller)
+        assert b.layout == _lib.BLANK_LAST and b.dtype == _lib.F64  # a mixed batch is widened, exactly
+        assert b.lens.tolist() == [40, 33, 60, 25]
+        for i, a in enumerate(ref):
+            assert np.array_equal(_rows(b, i), a.astype(np.float64)), (basecaller, i)
+    # the same batch through ReadBatch gives the same bytes
+    rb = batch.ReadBatch(_reference_arrays(paths, "bonito"))
+    assert np.array_equal(rb.data, ingest.load_reads(paths, "bonito").data)
+
+
+def test_csv_and_flipflop(tmp_path):
+    rng = np.random.default_rng(6)
+    p5 = rng.dirichlet(np.ones(5), size=12)
+    np.savetxt(tmp_path / "x.csv", p5, delimiter=",", header="a,c,g,t,b")
+    b = ingest.load_reads([str(tmp_path / "x.csv")], "poreover")
+    assert b.kinds == ["poreover"] and np.array_equal(_rows(b, 0), np.log(p5))
+    p8 = rng.dirichlet(np.ones(8), size=12)
+    np.savetxt(tmp_path / "y.csv", p8, delimiter=",", header="A,C,G,T,a,c,g,t")
+    with pytest.raises(NotImplementedError):
+        ingest.load_reads([str(tmp_path / "y.csv")], "poreover")
+    ms = ingest.load_models([str(tmp_path / "x.csv"), str(tmp_path / "y.csv")], "")
+    assert [m.kind for m in ms] == ["poreover", "flipflop"]
+
+
+def test_read_npy_equals_np_load(tmp_path):
+    rng = np.random.default_rng(7)
+    cases = [rng.random((7, 5)).astype(np.float32), rng.random((4, 3, 5)), rng.integers(0, 255, (9, 8)).astype(np.uint8),
+             np.zeros((0, 5), np.float32), rng.random(6).astype(np.float32), np.float32(3.5),
+             np.asfortranarray(rng.random((4, 5))), rng.random((3, 5)).astype(">f4"),
+             np.zeros(3, dtype=[("a", "<f4"), ("b", "<i4")])]
+    for i, a in enumerate(cases):
+        f = tmp_path / ("c%d.npy" % i)
+        np.save(f, a)
+        got, want = ingest.read_npy(str(f)), np.load(f)
+        assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want), i
+    # numpy's other header versions
+    f = tmp_path / "v2.npy"
+    with open(f, "wb") as fh:
+        np.lib.format.write_array(fh, cases[0], version=(2, 0))
+    assert np.array_equal(ingest.read_npy(str(f)), cases[0])
+    # a truncated payload is left to np.load (which raises)
+    raw = open(tmp_path / "c0.npy", "rb").read()
+    open(tmp_path / "short.npy", "wb").write(raw[:-8])
+    with pytest.raises(Exception):
+        ingest.read_npy(str(tmp_path / "short.npy"))
+
+
+def test_probability_row_rule_is_np_isclose():
+    for s in (1.0, 1 + 4e-6, 1 - 9.9e-6, 1 + 1.0005e-5, 1 + 1.002e-5, 1 + 3e-5, 0.0, -7.25, np.nan, np.inf):
+        row = np.array([s, 0, 0, 0, 0], dtype=np.float64)
+        assert ingest._is_probability_row(row) == bool(np.isclose(np.sum(row), 1)), s
+        row32 = row.astype(np.float32)
+        assert ingest._is_probability_row(row32) == bool(np.isclose(np.sum(row32), 1)), s
+
+
+def test_lookahead_overlaps_and_keeps_order():
+    chunks = iter(range(6))
+    log, main = [], threading.get_ident()
+    src_threads = set()
+
+    def source():
+        src_threads.add(threading.get_ident())
+        return next(chunks, None)
+
+    def load(c):
+        log.append(("load", c))
+        assert threading.get_ident() != main
+        time.sleep(0.01)
+        return c * 10
+
+    seen = []
+    for c, payload in ingest.Lookahead(source, load):
+        log.append(("use", c))
+        seen.append((c, payload))
+        time.sleep(0.02)
+    assert seen == [(c, c * 10) for c in range(6)]
+    assert src_threads == {main}  # the (possibly distributed) queue is only touched by the caller
+    for c in range(5):
+        assert log.index(("load", c + 1)) < log.index(("use", c + 1))
+        assert log.index(("load", c + 1)) > log.index(("load", c))
+    # chunk k+1 is being loaded while chunk k is in use
+    assert log.index(("load", 2)) < log.index(("use", 2))
+
+    def bad(c):
+        raise RuntimeError("loader failed on %d" % c)
+
+    chunks2 = iter(range(3))
+    with pytest.raises(RuntimeError, match="loader failed on 0"):
+        for _ in ingest.Lookahead(lambda: next(chunks2, None), bad):
+            pass
+    assert list(ingest.Lookahead(lambda: None, load)) == []
+
+
+def test_transducer_builds_float64_and_transition_on_demand():
+    x = np.log(np.random.default_rng(8).random((10, 5)).astype(np.float32))
+    m = transducer.bonito(x)
+    assert m._lp64 is None and m._transition is None  # nothing allocated until somebody asks (transducer.py:16, :22)
+    assert m.device_array() is m._f32
+    assert m.log_prob.dtype == np.float64 and np.array_equal(m.log_prob, x.astype(np.float64))
+    assert m.transition.shape == (10, 5) and (m.transition == 1).all()
+    assert np.array_equal(m[3], m.log_prob[3]) and m.t_max == 10 and m.num_states == 5
+    m.reverse_complement()
+    assert np.array_equal(m.log_prob, x.astype(np.float64)[::-1, [3, 2, 1, 0, 4]])
+    assert np.array_equal(m.device_array(), x[::-1, [3, 2, 1, 0, 4]])
+    m.log_prob = np.zeros((3, 5))  # an assigned table replaces the float32 original
+    assert m.device_array().dtype == np.float64 and m.device_array().shape == (3, 5)
+    f = transducer.flipflop(np.zeros((4, 8)))
+    assert f.transition.shape == (8, 8) and f.log_prob.dtype == np.float64
+    with pytest.raises(AssertionError):
+        transducer.bonito(np.zeros((4, 6), np.float32))
+
+
+def test_load_pairs_host_stage(tmp_path):
+    from argparse import Namespace
+    from poreover_b200.decoding import pair_decode as gpd
+    pairs = [list(synth.save_pair(str(tmp_path), k, 150 + 10 * k)) for k in range(3)]
+    args = Namespace(dir=str(tmp_path), basecaller="bonito", reverse_complement=True, alignment="banded",
+                     skip_matches=False, diagonal_envelope=False, single="viterbi")
+    meta, b1, b2, kind = gpd.load_pairs(args, pairs)
+    assert kind == "bonito" and b1.n == b2.n == 3 and b1.rc is None and b2.rc.tolist() == [1, 1, 1]
+    assert b1.layout == b2.layout == _lib.BLANK_FIRST
+    assert [m[0] for m in meta] == pairs and meta[0][3] == "bonito"
+    args.skip_matches = True  # staged flags: per-read arrays in the reference's column order
+    meta, m1, m2, kind = gpd.load_pairs(args, pairs)
+    ref = _reference_arrays([os.path.join(str(tmp_path), p[0]) for p in pairs], "bonito")
+    assert all(np.array_equal(a, b) for a, b in zip(m1, ref)) and len(m2) == 3
