@@ -18,14 +18,8 @@ from .. import batch
 
 
 def fasta_format(name, seq, width=60):
-    """decode.py:20-27"""
-    fasta = '>' + name + '\n'
-    window = 0
-    while window + width < len(seq):
-        fasta += (seq[window:window + width] + '\n')
-        window += width
-    fasta += (seq[window:] + '\n')
-    return fasta
+    """decode.py:20-27: header line, the sequence in lines of `width`, no empty last line unless seq is empty."""
+    return '>' + name + '\n' + '\n'.join([seq[i:i + width] for i in range(0, len(seq), width)]) + '\n'
 
 
 def _logsumexp(a, axis):

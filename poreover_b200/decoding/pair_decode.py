@@ -260,8 +260,9 @@ def load_pairs(args, sub):
         meta = [m + (kind,) for m in meta]
         return meta, [x.device_array() for x in a], [y.device_array() for y in b], kind
     try:
-        b1 = ingest.load_reads(files1, args.basecaller)
-        b2 = ingest.load_reads(files2, args.basecaller, rc=1 if args.reverse_complement else 0)
+        alloc = ingest.packed_alloc()
+        b1 = ingest.load_reads(files1, args.basecaller, alloc=alloc)
+        b2 = ingest.load_reads(files2, args.basecaller, rc=1 if args.reverse_complement else 0, alloc=alloc)
     except NotImplementedError:
         raise NotImplementedError("flip-flop pair decoding is out of scope (README.md:97 of the reference)")
     for x, y in zip(b1.kinds, b2.kinds):
@@ -270,19 +271,32 @@ def load_pairs(args, sub):
     return [m + (kind,) for m in meta], b1, b2, kind
 
 
-def decode_loaded(args, payload, device=None):
-    """GPU stage of a chunk: load_pairs' payload -> pair_decode_helper-style results, in the chunk's order."""
+def decode_loaded(args, payload, device=None, fmt=True):
+    """GPU stage of a chunk: load_pairs' payload -> pair_decode_helper-style results, in the chunk's order.
+    With fmt=False the records are returned raw, for format_decoded on another thread."""
     meta, m1, m2, kind = payload
-    n = len(meta)
-    if n == 0:
+    if len(meta) == 0:
         return []
     if kind == 'flipflop':
         raise NotImplementedError("flip-flop pair decoding is out of scope (README.md:97 of the reference)")
     if _staged(args):
-        return _decode_pairs_staged(args, meta, m1, m2, kind, device)
-    results = [None] * n
+        done = _decode_pairs_staged(args, meta, m1, m2, kind, device)
+        return done if fmt else ("done", done)
     res = batch.pair_decode_batch(m1, m2, kind=kind, beam_width=args.beam_width, padding=args.padding,
                                   method=args.beam_search_method, device=device)  # rc and layout travel in the batches
+    raw = ("raw", meta, res)
+    return format_decoded(args, raw) if fmt else raw
+
+
+def format_decoded(args, raw):
+    """Host stage after the GPU: pob_pair_decode's records -> the tuples pair_decode_helper returns
+    (pair_decode.py:383-398, :525-531)."""
+    if not raw:
+        return []
+    if raw[0] == "done":
+        return raw[1]
+    _, meta, res = raw
+    results = [None] * len(meta)
     for k, (r, (in_path, path1, path2, _)) in enumerate(zip(res, meta)):
         if r["status"] & (batch._lib.ST_MAPPING_WRAP | batch._lib.ST_EMPTY):
             continue  # the reference's assertion fires and the pool drops the pair silently
@@ -307,16 +321,16 @@ def decode_loaded(args, payload, device=None):
 def decode_pairs(args, pair_list, device=None, chunk=2048):
     """Decode [(name1, name2), ...] -> list of pair_decode_helper-style results, in input order.
 
-    Chunks of pairs go through a two-stage pipeline: the files of chunk k+1 are loaded (ingest.py) while the GPU
-    decodes chunk k."""
-    from .. import ingest
+    Chunks of pairs go through a three-stage pipeline: the files of chunk k+2 are loaded (ingest.py) and the GPU
+    decodes chunk k+1 while the records of chunk k are formatted."""
+    from .. import ingest, multigpu
     _check_args(args)
     results = [None] * len(pair_list)
-    starts = iter(range(0, len(pair_list), chunk))
-    for c0, payload in ingest.Lookahead(lambda: next(starts, None),
-                                        lambda c0: load_pairs(args, pair_list[c0:c0 + chunk])):
-        res = decode_loaded(args, payload, device)
-        results[c0:c0 + len(res)] = res
+    q = multigpu.WorkQueue(len(pair_list), chunk, ramp=1)
+    for c, raw in ingest.Lookahead(q.next, lambda c: load_pairs(args, pair_list[c[0]:c[1]]),
+                                   lambda payload: decode_loaded(args, payload, device, fmt=False)):
+        res = format_decoded(args, raw)
+        results[c[0]:c[0] + len(res)] = res
     return results
 
 

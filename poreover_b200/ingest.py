@@ -14,6 +14,7 @@ C ABI:
   * anything that is not a plain 2-D probability table (.csv, 3-D logits, float64 files, .hdf5/.fast5) goes through
     decode.model_from_trace unchanged and is copied into the batch.
 """
+import ctypes as C
 import os
 import re
 import threading
@@ -113,7 +114,7 @@ def load_reads(paths, basecaller, rc=None, alloc=None):
 
     Equivalent to ReadBatch([decode.model_from_trace(p, basecaller).device_array() for p in paths], rc=rc) up to the
     column layout: when every file is a plain bonito probability table the batch keeps the file order and says so
-    (layout BLANK_FIRST).  alloc(shape, dtype) may supply the packed buffer (e.g. pinned memory); it must be zeroed.
+    (layout BLANK_FIRST).  alloc(shape, dtype) may supply the packed buffer (e.g. pinned memory, any contents).
     The batch also carries .kinds, the transducer kind of every read."""
     paths = list(paths)
     n = len(paths)
@@ -165,6 +166,7 @@ def load_reads(paths, basecaller, rc=None, alloc=None):
                         np.log(r.arr, out=dst)
                 else:
                     dst[...] = r.arr  # float32 -> float64 widening is exact
+                data[off[i] + r.T:off[i + 1]] = 0  # alignment rows between reads
                 raws[i] = None
 
     list(ex.map(s2, parts))
@@ -187,26 +189,97 @@ def load_models(paths, basecaller):
 
 
 class Lookahead:
-    """Two-stage pipeline over a stream of chunks: while the caller consumes chunk k (GPU call + result formatting)
-    one background thread runs load(chunk k+1).  Chunks are pulled from `source` (a callable returning the next
-    chunk or None) on the CALLER's thread, so a distributed work queue is only ever touched from there."""
+    """Pipeline over a stream of chunks: while the caller consumes chunk k (result formatting, file output), one
+    background thread runs load(chunk k+1 ..) and, when `work` is given, a second one runs work(load's payload) --
+    the GPU call, which releases the GIL -- in chunk order.  Chunks are pulled from `source` (a callable returning
+    the next chunk or None) on the CALLER's thread, so a distributed work queue is only ever touched from there.
+    Yields (chunk, work(load(chunk))), or (chunk, load(chunk)) without a work stage."""
 
-    def __init__(self, source, load):
-        self._source, self._load = source, load
-        self._ex = ThreadPoolExecutor(max_workers=1, thread_name_prefix="pob-prefetch")
-        self._next = self._submit()
+    def __init__(self, source, load, work=None):
+        self._source, self._load, self._work = source, load, work
+        self._ex_load = ThreadPoolExecutor(max_workers=1, thread_name_prefix="pob-prefetch")
+        self._ex_work = ThreadPoolExecutor(max_workers=1, thread_name_prefix="pob-gpu") if work else None
+        self._depth = 2 if work else 1  # chunks in flight behind the one being consumed
+        self._pending = []
+        self._fill()
 
-    def _submit(self):
-        c = self._source()
-        if c is None:
-            return None
-        return c, self._ex.submit(self._load, c)
+    def _fill(self):
+        while len(self._pending) < self._depth:
+            c = self._source()
+            if c is None:
+                return
+            fut = self._ex_load.submit(self._load, c)
+            if self._ex_work is not None:
+                fut = self._ex_work.submit(lambda f=fut: self._work(f.result()))
+            self._pending.append((c, fut))
 
     def __iter__(self):
         try:
-            while self._next is not None:
-                c, fut = self._next
-                self._next = self._submit()  # the load of the following chunk starts before this one is consumed
+            while self._pending:
+                c, fut = self._pending.pop(0)
+                self._fill()  # the following chunks are under way before this one is consumed
                 yield c, fut.result()
+                self._fill()
         finally:
-            self._ex.shutdown(wait=True)
+            for _, fut in self._pending:
+                fut.cancel()
+            self._ex_load.shutdown(wait=True)
+            if self._ex_work is not None:
+                self._ex_work.shutdown(wait=True)
+
+
+class PinnedPool:
+    """Page-locked host buffers (pob_malloc_host) for the packed batches, reused from chunk to chunk: pinning costs
+    more than the copy it speeds up, so a buffer goes back to the pool when the last numpy view of it dies."""
+
+    def __init__(self, keep=8):
+        self._free, self._lock, self._keep = [], threading.Lock(), keep
+
+    def _give(self, cap, addr):
+        with self._lock:
+            if len(self._free) < self._keep:
+                self._free.append((cap, addr))
+                return
+        _lib.lib().pob_free_host(C.c_void_p(addr))
+
+    def empty(self, shape, dtype):
+        """np.empty(shape, dtype) in pinned memory, or None when no pinned memory can be had (no GPU)."""
+        import weakref
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        if nbytes == 0:
+            return np.zeros(shape, dtype)
+        addr = cap = None
+        with self._lock:
+            fit = [x for x in self._free if x[0] >= nbytes]
+            if fit:
+                cap, addr = min(fit)
+                self._free.remove((cap, addr))
+        fresh = addr is None
+        if fresh:
+            cap = (nbytes * 5 // 4 + 4095) & ~4095  # headroom: chunks of a run differ a little in size
+            h = C.c_void_p()
+            if _lib.lib().pob_malloc_host(C.c_size_t(cap), C.byref(h)) != 0 or not h.value:
+                return None
+            addr = h.value
+        cbuf = (C.c_char * cap).from_address(addr)
+        weakref.finalize(cbuf, self._give, cap, addr)
+        return np.frombuffer(cbuf, dtype=np.uint8, count=nbytes).view(dtype).reshape(shape)
+
+
+_pinned = None
+
+
+def packed_alloc():
+    """Allocator of load_reads' packed buffers: pinned when POREOVER_B200_PINNED=1, else numpy's."""
+    global _pinned
+    if os.environ.get("POREOVER_B200_PINNED", "0") != "1":
+        return None
+    if _pinned is None:
+        _pinned = PinnedPool()
+
+    def alloc(shape, dtype):
+        a = _pinned.empty(shape, dtype)
+        return a if a is not None else np.zeros(shape, dtype)
+
+    return alloc

@@ -13,11 +13,16 @@ def dist_info():
 
 
 class WorkQueue:
-    """Chunked dynamic queue over range(n_items) shared by all ranks of a torch.distributed job."""
+    """Chunked dynamic queue over range(n_items) shared by all ranks of a torch.distributed job.  The first `ramp`
+    chunks are a quarter of the size: a pipelined consumer starts its first GPU call sooner."""
 
-    def __init__(self, n_items, chunk, store=None, key="poreover_b200_queue"):
+    def __init__(self, n_items, chunk, store=None, key="poreover_b200_queue", ramp=0):
         self.n, self.chunk, self.store, self.key = n_items, max(1, chunk), store, key
         self._local = 0
+        self.bounds = [0]  # the same on every rank: chunk k = [bounds[k], bounds[k+1])
+        while self.bounds[-1] < n_items:
+            step = max(1, self.chunk // 4) if len(self.bounds) - 1 < ramp else self.chunk
+            self.bounds.append(min(n_items, self.bounds[-1] + step))
 
     def next(self):
         if self.store is None:
@@ -25,27 +30,31 @@ class WorkQueue:
             self._local += 1
         else:
             k = self.store.add(self.key, 1) - 1  # atomic on the store's host
-        lo = k * self.chunk
-        if lo >= self.n:
+        if k + 1 >= len(self.bounds):
             return None
-        return lo, min(self.n, lo + self.chunk)
+        return self.bounds[k], self.bounds[k + 1]
 
 
-def run_sharded(items, cost, process_chunk, chunk=256, group=None, store=None, load_chunk=None):
+def run_sharded(items, cost, process_chunk, chunk=256, group=None, store=None, load_chunk=None, finish_chunk=None):
     """Process `items` across all ranks.  cost[i] orders the queue (descending).  process_chunk(list) ->
-    list of results.  With load_chunk, a chunk goes through two stages -- payload = load_chunk(list) on a host
-    thread, then process_chunk(payload) -- and the load of the next chunk overlaps the processing of the current
-    one (the queue itself is only touched from the calling thread).  Returns the full result list in input order
-    on rank 0, None elsewhere."""
+    list of results.  With load_chunk, a chunk goes through a pipeline -- payload = load_chunk(list) on a host
+    thread, process_chunk(payload) on a second thread (the GPU call), then finish_chunk(its result) -> list of
+    results on the calling thread -- so that loading chunk k+2, decoding chunk k+1 and formatting chunk k overlap
+    (the queue itself is only touched from the calling thread).  Returns the full result list in input order on
+    rank 0, None elsewhere."""
     from .ingest import Lookahead
     rank, world, _ = dist_info()
     order = sorted(range(len(items)), key=lambda i: -cost[i])
-    q = WorkQueue(len(order), chunk, store if world > 1 else None)
+    q = WorkQueue(len(order), chunk, store if world > 1 else None, ramp=world if load_chunk else 0)
     mine = {}
     if load_chunk is None:
-        load_chunk = lambda sub: sub
-    for c, payload in Lookahead(q.next, lambda c: load_chunk([items[i] for i in order[c[0]:c[1]]])):
-        for i, r in zip(order[c[0]:c[1]], process_chunk(payload)):
+        stream = ((c, process_chunk([items[i] for i in order[c[0]:c[1]]])) for c in iter(q.next, None))
+    else:
+        stream = Lookahead(q.next, lambda c: load_chunk([items[i] for i in order[c[0]:c[1]]]), process_chunk)
+    for c, res in stream:
+        if finish_chunk is not None:
+            res = finish_chunk(res)
+        for i, r in zip(order[c[0]:c[1]], res):
             mine[i] = r
     if world == 1:
         return [mine.get(i) for i in range(len(items))]
@@ -129,5 +138,6 @@ def decode_pairs_all_gpus(args, pair_list, chunk=2048):
     # 444 pairs in flight, so a batch should be several waves; the next batch is loaded while this one is decoded)
     pd._check_args(args)
     chunk = max(8, min(chunk, -(-len(pair_list) // (4 * world))))
-    return run_sharded(pair_list, cost, lambda payload: pd.decode_loaded(args, payload, device=local), chunk, group,
-                       store, load_chunk=lambda sub: pd.load_pairs(args, sub))
+    return run_sharded(pair_list, cost, lambda payload: pd.decode_loaded(args, payload, device=local, fmt=False), chunk,
+                       group, store, load_chunk=lambda sub: pd.load_pairs(args, sub),
+                       finish_chunk=lambda raw: pd.format_decoded(args, raw))

@@ -162,6 +162,64 @@ def test_lookahead_overlaps_and_keeps_order():
     assert list(ingest.Lookahead(lambda: None, load)) == []
 
 
+def test_three_stage_pipeline():
+    """load (thread A) -> work (thread B, the GPU call) -> the caller, all three busy at once, results in order."""
+    chunks = iter(range(8))
+    busy, peak, lock = set(), [0], threading.Lock()
+    threads = {"load": set(), "work": set()}
+
+    def stage(name, dt):
+        def f(x):
+            threads[name].add(threading.get_ident())
+            with lock:
+                busy.add(name)
+                peak[0] = max(peak[0], len(busy))
+            time.sleep(dt)
+            with lock:
+                busy.discard(name)
+            return x + (name,) if isinstance(x, tuple) else (x, name)
+        return f
+
+    out = []
+    for c, r in ingest.Lookahead(lambda: next(chunks, None), stage("load", 0.01), stage("work", 0.02)):
+        with lock:
+            busy.add("use")
+            peak[0] = max(peak[0], len(busy))
+        time.sleep(0.02)
+        with lock:
+            busy.discard("use")
+        out.append((c, r))
+    assert out == [(c, (c, "load", "work")) for c in range(8)]
+    assert peak[0] == 3
+    assert len(threads["load"]) == 1 and len(threads["work"]) == 1 and threads["load"] != threads["work"]
+
+    def bad(x):
+        raise ValueError("gpu stage failed")
+
+    chunks2 = iter(range(4))
+    with pytest.raises(ValueError, match="gpu stage failed"):
+        for _ in ingest.Lookahead(lambda: next(chunks2, None), stage("load", 0.0), bad):
+            pass
+
+
+def test_ramped_queue_and_pinned_fallback(monkeypatch):
+    from poreover_b200 import multigpu
+    q = multigpu.WorkQueue(1000, 256, ramp=2)
+    got = list(iter(q.next, None))
+    assert got == [(0, 64), (64, 128), (128, 384), (384, 640), (640, 896), (896, 1000)]
+    assert list(iter(multigpu.WorkQueue(10, 4).next, None)) == [(0, 4), (4, 8), (8, 10)]
+    assert list(iter(multigpu.WorkQueue(0, 4, ramp=1).next, None)) == []
+    out = multigpu.run_sharded(list(range(40)), [i % 5 for i in range(40)], lambda p: [x * 2 for x in p], chunk=8,
+                               load_chunk=lambda sub: [x + 1 for x in sub], finish_chunk=lambda r: [x - 2 for x in r])
+    assert out == [2 * i for i in range(40)]
+    assert ingest.packed_alloc() is None
+    monkeypatch.setenv("POREOVER_B200_PINNED", "1")
+    alloc = ingest.packed_alloc()  # no GPU here: cudaMallocHost fails and numpy's memory is used
+    a = alloc((16, 5), np.float32)
+    assert a.shape == (16, 5) and a.dtype == np.float32
+    assert alloc((0, 5), np.float32).shape == (0, 5)
+
+
 def test_transducer_builds_float64_and_transition_on_demand():
     x = np.log(np.random.default_rng(8).random((10, 5)).astype(np.float32))
     m = transducer.bonito(x)

@@ -16,7 +16,8 @@ import tempfile
 import time
 from concurrent.futures import ProcessPoolExecutor
 
-sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+# POB_TREE=<dir> times another checkout of the package (e.g. an older commit unpacked under build/)
+sys.path.insert(0, os.environ.get("POB_TREE") or os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 
 
 def _gen(job):
@@ -32,8 +33,9 @@ def main():
     ap.add_argument("--T", type=int, default=5000)
     ap.add_argument("--beam_width", type=int, default=25)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--whole-only", action="store_true", help="only the whole-run figure (works on older trees)")
     a = ap.parse_args()
-    from poreover_b200 import ingest, multigpu
+    from poreover_b200 import multigpu
     from poreover_b200.__main__ import build_parser
     from poreover_b200.decoding import pair_decode as pd
 
@@ -64,6 +66,15 @@ def main():
     done = sum(1 for r in res if r is not None and len(r) == 3)
     bases = sum(len(r[1].split("\n", 1)[1].replace("\n", "")) for r in res if r is not None and len(r) == 3)
 
+    if a.whole_only:
+        out = {"metric": "pair_decode_cli_pairs_per_s", "value": a.pairs / t_run, "unit": "pairs/s", "pairs": a.pairs,
+               "decoded": done, "wall_s": t_run, "tree": os.environ.get("POB_TREE", "this checkout")}
+        print(json.dumps(out))
+        if a.out:
+            with open(a.out, "w") as f:
+                f.write(json.dumps(out) + "\n")
+        return
+    from poreover_b200 import ingest
     # the stages on their own, same chunking as the run
     chunk = max(8, min(2048, -(-len(pair_list) // 4)))
     subs = [pair_list[i:i + chunk] for i in range(0, len(pair_list), chunk)]
@@ -87,6 +98,7 @@ def main():
            "pairs": a.pairs, "unique_pairs": a.unique, "T": a.T, "beam_width": a.beam_width, "decoded": done,
            "consensus_mbases_per_s": bases / t_run / 1e6, "wall_s": t_run, "chunk": chunk,
            "loader_threads": ingest.n_threads(), "host_cores": os.cpu_count(),
+           "pinned_batches": os.environ.get("POREOVER_B200_PINNED", "0") == "1",
            "host_stage_pairs_per_s": 1.0 / t_load, "gpu_stage_pairs_per_s": 1.0 / t_gpu,
            "reference_style_loader_pairs_per_s_1thread": 1.0 / t_ref_loader, "synth_s": t_gen,
            "what": "files on disk (page cache) -> .1d.fasta/.2d.fasta/.log, one process, one GPU, wall clock"}
