@@ -183,7 +183,9 @@ class Context:
 
 
 def get_ctx(device=None):
-    """Process-wide context for `device` (default: $LOCAL_RANK or 0)."""
+    """Process-wide context for `device` (default: $LOCAL_RANK or 0); a Context passes through."""
+    if isinstance(device, Context):
+        return device
     if device is None:
         device = int(os.environ.get("POREOVER_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
     with _lock:
@@ -197,6 +199,37 @@ def get_ctx(device=None):
         with _lock:
             _ctxs[device] = c
     return c
+
+
+_free_ctxs = {}  # device -> contexts not in use by a borrow_ctx() block
+
+
+class borrow_ctx:
+    """`with borrow_ctx(device) as ctx:` -- a context (stream + scratch arena) nobody else is using right now.  The
+    command-line pipeline runs two GPU threads per device so that consecutive batches overlap; each call borrows
+    a context for its duration.  The process-wide context of get_ctx() is the first one handed out, further ones are
+    created on demand and kept for the life of the process."""
+
+    def __init__(self, device=None):
+        if device is None:
+            device = int(os.environ.get("POREOVER_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        self.device, self.ctx = device, None
+
+    def __enter__(self):
+        first = get_ctx(self.device)
+        with _lock:
+            free = _free_ctxs.setdefault(self.device, [first])
+            if free:
+                self.ctx = free.pop()
+        if self.ctx is None:
+            self.ctx = Context(self.device)
+        return self.ctx
+
+    def __exit__(self, *exc):
+        with _lock:
+            _free_ctxs[self.device].append(self.ctx)
+        self.ctx = None
+        return False
 
 
 def ptr(a):

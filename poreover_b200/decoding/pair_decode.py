@@ -321,14 +321,19 @@ def format_decoded(args, raw):
 def decode_pairs(args, pair_list, device=None, chunk=2048):
     """Decode [(name1, name2), ...] -> list of pair_decode_helper-style results, in input order.
 
-    Chunks of pairs go through a three-stage pipeline: the files of chunk k+2 are loaded (ingest.py) and the GPU
-    decodes chunk k+1 while the records of chunk k are formatted."""
+    Chunks of pairs go through a three-stage pipeline: files are loaded a chunk ahead (ingest.py), two GPU calls are
+    in flight on two contexts (the second fills the SMs the first one's last wave leaves idle), and the records of
+    the oldest chunk are formatted meanwhile."""
     from .. import ingest, multigpu
     _check_args(args)
     results = [None] * len(pair_list)
     q = multigpu.WorkQueue(len(pair_list), chunk, ramp=1)
-    for c, raw in ingest.Lookahead(q.next, lambda c: load_pairs(args, pair_list[c[0]:c[1]]),
-                                   lambda payload: decode_loaded(args, payload, device, fmt=False)):
+
+    def gpu_stage(payload):
+        with batch._lib.borrow_ctx(device) as ctx:  # two of these run at a time, each on its own stream and arena
+            return decode_loaded(args, payload, ctx, fmt=False)
+
+    for c, raw in ingest.Lookahead(q.next, lambda c: load_pairs(args, pair_list[c[0]:c[1]]), gpu_stage):
         res = format_decoded(args, raw)
         results[c[0]:c[0] + len(res)] = res
     return results

@@ -190,16 +190,20 @@ def load_models(paths, basecaller):
 
 class Lookahead:
     """Pipeline over a stream of chunks: while the caller consumes chunk k (result formatting, file output), one
-    background thread runs load(chunk k+1 ..) and, when `work` is given, a second one runs work(load's payload) --
-    the GPU call, which releases the GIL -- in chunk order.  Chunks are pulled from `source` (a callable returning
-    the next chunk or None) on the CALLER's thread, so a distributed work queue is only ever touched from there.
-    Yields (chunk, work(load(chunk))), or (chunk, load(chunk)) without a work stage."""
+    background thread runs load(..) a chunk ahead and, when `work` is given, `workers` more threads run
+    work(load's payload) -- the GPU call, which releases the GIL.  With two workers (each on its own context and
+    stream, _lib.thread_ctx) the kernels of chunk k+1 fill the SMs that the draining last wave of chunk k leaves idle.
+    Chunks are pulled from `source` (a callable returning the next chunk or None) on the CALLER's thread, so a
+    distributed work queue is only ever touched from there, and results are yielded in chunk order:
+    (chunk, work(load(chunk))), or (chunk, load(chunk)) without a work stage."""
 
-    def __init__(self, source, load, work=None):
+    def __init__(self, source, load, work=None, workers=None):
+        if workers is None:
+            workers = int(os.environ.get("POREOVER_B200_GPU_LANES", "2"))
         self._source, self._load, self._work = source, load, work
         self._ex_load = ThreadPoolExecutor(max_workers=1, thread_name_prefix="pob-prefetch")
-        self._ex_work = ThreadPoolExecutor(max_workers=1, thread_name_prefix="pob-gpu") if work else None
-        self._depth = 2 if work else 1  # chunks in flight behind the one being consumed
+        self._ex_work = ThreadPoolExecutor(max_workers=max(1, workers), thread_name_prefix="pob-gpu") if work else None
+        self._depth = (1 + max(1, workers)) if work else 1  # chunks in flight behind the one being consumed
         self._pending = []
         self._fill()
 

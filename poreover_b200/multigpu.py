@@ -102,12 +102,13 @@ def decode_files_all_gpus(args, in_files, chunk=4096):
         return ingest.load_models(paths, args.basecaller)
 
     def work(payload):
-        from . import batch
-        if isinstance(payload, batch.ReadBatch):
-            if args.algorithm == 'viterbi':
-                return batch.viterbi_batch(payload, args.basecaller, device=local)[0]
-            return batch.beam_search_batch(payload, args.beam_width, dec.MODEL_TYPE[args.basecaller], device=local)[0]
-        return dec.decode_models(payload, args.algorithm, args.beam_width, device=local)
+        from . import _lib, batch
+        with _lib.borrow_ctx(local) as ctx:  # two of these run at a time, each on its own stream and arena
+            if isinstance(payload, batch.ReadBatch):
+                if args.algorithm == 'viterbi':
+                    return batch.viterbi_batch(payload, args.basecaller, device=ctx)[0]
+                return batch.beam_search_batch(payload, args.beam_width, dec.MODEL_TYPE[args.basecaller], device=ctx)[0]
+            return dec.decode_models(payload, args.algorithm, args.beam_width, device=ctx)
 
     chunk = max(8, min(chunk, -(-len(in_files) // (4 * world))))
     return run_sharded(in_files, [size_of(p) for p in in_files], work, chunk, group, store, load_chunk=load)
@@ -138,6 +139,11 @@ def decode_pairs_all_gpus(args, pair_list, chunk=2048):
     # 444 pairs in flight, so a batch should be several waves; the next batch is loaded while this one is decoded)
     pd._check_args(args)
     chunk = max(8, min(chunk, -(-len(pair_list) // (4 * world))))
-    return run_sharded(pair_list, cost, lambda payload: pd.decode_loaded(args, payload, device=local, fmt=False), chunk,
-                       group, store, load_chunk=lambda sub: pd.load_pairs(args, sub),
+    from . import _lib
+
+    def gpu_stage(payload):
+        with _lib.borrow_ctx(local) as ctx:  # two of these run at a time, each on its own stream and arena
+            return pd.decode_loaded(args, payload, device=ctx, fmt=False)
+
+    return run_sharded(pair_list, cost, gpu_stage, chunk, group, store, load_chunk=lambda sub: pd.load_pairs(args, sub),
                        finish_chunk=lambda raw: pd.format_decoded(args, raw))

@@ -191,7 +191,15 @@ def test_three_stage_pipeline():
         out.append((c, r))
     assert out == [(c, (c, "load", "work")) for c in range(8)]
     assert peak[0] == 3
-    assert len(threads["load"]) == 1 and len(threads["work"]) == 1 and threads["load"] != threads["work"]
+    assert len(threads["load"]) == 1 and 1 <= len(threads["work"]) <= 2 and not (threads["load"] & threads["work"])
+    # two GPU workers, uneven durations: results still come back in chunk order
+    chunks3 = iter(range(9))
+    got = list(ingest.Lookahead(lambda: next(chunks3, None), lambda c: c,
+                                lambda c: (time.sleep(0.02 if c % 2 == 0 else 0.001), c * c)[1], workers=2))
+    assert got == [(c, c * c) for c in range(9)]
+    chunks4 = iter(range(4))
+    one = list(ingest.Lookahead(lambda: next(chunks4, None), lambda c: c, lambda c: -c, workers=1))
+    assert one == [(c, -c) for c in range(4)]
 
     def bad(x):
         raise ValueError("gpu stage failed")

@@ -99,6 +99,7 @@ def main():
            "consensus_mbases_per_s": bases / t_run / 1e6, "wall_s": t_run, "chunk": chunk,
            "loader_threads": ingest.n_threads(), "host_cores": os.cpu_count(),
            "pinned_batches": os.environ.get("POREOVER_B200_PINNED", "0") == "1",
+           "gpu_lanes": int(os.environ.get("POREOVER_B200_GPU_LANES", "2")),
            "host_stage_pairs_per_s": 1.0 / t_load, "gpu_stage_pairs_per_s": 1.0 / t_gpu,
            "reference_style_loader_pairs_per_s_1thread": 1.0 / t_ref_loader, "synth_s": t_gen,
            "what": "files on disk (page cache) -> .1d.fasta/.2d.fasta/.log, one process, one GPU, wall clock"}
