@@ -48,24 +48,28 @@ def _unpack(buf, offs, lens):
     return [buf[o:o + l] for o, l in zip(offs, lens)]
 
 
-def viterbi_batch(arrays, kind, rc=None, layout=_lib.BLANK_LAST, return_path=False, device=None):
-    """Best-path decode of many reads.  Returns (sequences, s2s lists, paths or None, status array).
+def viterbi_batch(arrays, kind, rc=None, layout=_lib.BLANK_LAST, return_path=False, device=None, return_maps=True):
+    """Best-path decode of many reads.  Returns (sequences, s2s lists or None, paths or None, status array).
 
-    replaces transducer.{poreover,bonito}.viterbi_decode + get_sequence_mapping (see include/poreover_b200.h)."""
+    replaces transducer.{poreover,bonito}.viterbi_decode + get_sequence_mapping (see include/poreover_b200.h).
+    return_maps=False (the `decode` command line only wants the sequences) skips the mapping's device-to-host copy
+    and its per-read arrays."""
     b = arrays if isinstance(arrays, ReadBatch) else ReadBatch(arrays, rc=rc, layout=layout)
     ctx = get_ctx(device)
     rows = max(b.total_rows, 1)
     seq = np.zeros(rows, dtype=np.uint8)
-    s2s = np.zeros(rows, dtype=np.int32)
+    s2s = np.zeros(rows, dtype=np.int32) if return_maps else None
     path = np.zeros(rows, dtype=np.int8) if return_path else None
     ln = np.zeros(max(b.n, 1), dtype=np.int32)
     st = np.zeros(max(b.n, 1), dtype=np.int32)
     rs = b.struct()
     check(lib().pob_viterbi(ctx.h, _lib.HOST, C.byref(rs), _lib.KIND[kind], ptr(seq), ptr(s2s), ptr(path), ptr(ln),
                             ptr(st)), "pob_viterbi")
-    offs = b.row_off[:-1]
-    seqs = [seq[o:o + l].tobytes().decode() for o, l in zip(offs, ln[:b.n])]
-    maps = [s2s[o:o + l].astype(np.int64) for o, l in zip(offs, ln[:b.n])]
+    offs = b.row_off[:-1].tolist()
+    lens = ln[:b.n].tolist()
+    text = seq.tobytes().decode("latin1")  # one decode, then string slices (offsets are byte offsets)
+    seqs = [text[o:o + l] for o, l in zip(offs, lens)]
+    maps = [s2s[o:o + l].astype(np.int64) for o, l in zip(offs, lens)] if return_maps else None
     paths = [path[o:o + t].astype(np.int64) for o, t in zip(offs, b.lens)] if return_path else None
     return seqs, maps, paths, st[:b.n].copy()
 
@@ -221,15 +225,19 @@ def pair_decode_batch(arrays1, arrays2, kind="bonito", beam_width=25, padding=5,
                                 ptr(l2), ptr(cons), ptr(lc), ptr(sc), ptr(stats), ptr(st)), "pob_pair_decode")
     out = []
     skip_mask = _lib.ST_SKIPPED_LENGTH | _lib.ST_SKIPPED_IDENTITY | _lib.ST_MAPPING_WRAP | _lib.ST_EMPTY
+    # one decode per buffer, then string slices (offsets are byte offsets); plain python ints in the loop
+    t1, t2, tc = (x.tobytes().decode("latin1") for x in (seq1, seq2, cons))
+    off1, off2 = b1.row_off.tolist(), b2.row_off.tolist()
+    len1, len2, lenc, stl, scl = l1.tolist(), l2.tolist(), lc.tolist(), st.tolist(), sc.tolist()
     for p in range(n):
-        o1, o2 = int(b1.row_off[p]), int(b2.row_off[p])
-        r = {"basecall1": seq1[o1:o1 + l1[p]].tobytes().decode(), "basecall2": seq2[o2:o2 + l2[p]].tobytes().decode(),
-             "status": int(st[p]), "skipped": 1 if (st[p] & skip_mask) else 0, "length1": int(l1[p]), "length2": int(l2[p])}
+        o1, o2, s_ = off1[p], off2[p], stl[p]
+        r = {"basecall1": t1[o1:o1 + len1[p]], "basecall2": t2[o2:o2 + len2[p]],
+             "status": s_, "skipped": 1 if (s_ & skip_mask) else 0, "length1": len1[p], "length2": len2[p]}
         if stats[p, 3] > 0:
             r["identity"] = stats[p, 2] / stats[p, 3]  # np.sum(a0 == a1) / len(a0)  (pair_decode.py:391)
         if not r["skipped"]:
-            r["consensus"] = cons[o1 + o2:o1 + o2 + lc[p]].tobytes().decode()
-            r["score"] = float(sc[p])
+            r["consensus"] = tc[o1 + o2:o1 + o2 + lenc[p]]
+            r["score"] = scl[p]
         out.append(r)
     return out
 
@@ -246,9 +254,9 @@ def flipflop_lut():
     return FLIPFLOP_LUT
 
 
-def flipflop_viterbi_batch(arrays, rc=None, return_path=False, device=None):
+def flipflop_viterbi_batch(arrays, rc=None, return_path=False, device=None, return_maps=True):
     """Flip-flop Viterbi over many reads.  arrays: T x 8 float64 log-probabilities, or T x 8 uint8 traces
-    (decoded through the host-computed table).  Returns (sequences, s2s lists, paths or None).
+    (decoded through the host-computed table).  Returns (sequences, s2s lists or None, paths or None).
 
     replaces transducer.viterbi_decode for kind 'flipflop' (transducer.py:35-59, :94-103)."""
     arrays = [np.asarray(a) for a in arrays]
@@ -259,16 +267,18 @@ def flipflop_viterbi_batch(arrays, rc=None, return_path=False, device=None):
     ctx = get_ctx(device)
     rows = max(b.total_rows, 1)
     seq = np.zeros(rows + 4, dtype=np.uint8)
-    s2s = np.zeros(rows + 4, dtype=np.int32)
-    path = np.zeros(rows + 4, dtype=np.int8)
+    s2s = np.zeros(rows + 4, dtype=np.int32) if return_maps else None
+    path = np.zeros(rows + 4, dtype=np.int8) if return_path else None
     ln = np.zeros(max(b.n, 1), dtype=np.int32)
     lut = flipflop_lut() if u8 else None
     rs = b.struct()
     check(lib().pob_viterbi_flipflop(ctx.h, _lib.HOST, C.byref(rs), ptr(lut), ptr(seq), ptr(s2s), ptr(path), ptr(ln)),
           "pob_viterbi_flipflop")
-    offs = b.row_off[:-1]
-    seqs = [seq[o:o + l].tobytes().decode() for o, l in zip(offs, ln[:b.n])]
-    maps = [s2s[o:o + l].astype(np.int64) for o, l in zip(offs, ln[:b.n])]
+    offs = b.row_off[:-1].tolist()
+    lens = ln[:b.n].tolist()
+    text = seq.tobytes().decode("latin1")  # one decode, then string slices (offsets are byte offsets)
+    seqs = [text[o:o + l] for o, l in zip(offs, lens)]
+    maps = [s2s[o:o + l].astype(np.int64) for o, l in zip(offs, lens)] if return_maps else None
     paths = [path[o:o + t].astype(np.int64) for o, t in zip(offs, b.lens)] if return_path else None
     return seqs, maps, paths
 

@@ -125,9 +125,9 @@ def decode_models(models, algorithm="viterbi", beam_width=25, device=None):
         arrays = [models[i].device_array() for i in idx]
         if algorithm == 'viterbi':
             if kind == 'flipflop':
-                seqs = batch.flipflop_viterbi_batch(arrays, device=device)[0]
+                seqs = batch.flipflop_viterbi_batch(arrays, device=device, return_maps=False)[0]
             else:
-                seqs = batch.viterbi_batch(arrays, kind, device=device)[0]
+                seqs = batch.viterbi_batch(arrays, kind, device=device, return_maps=False)[0]
         elif algorithm == 'beam':
             if kind == 'flipflop':
                 raise NotImplementedError("flip-flop beam search is out of scope (the reference's own test fails)")

@@ -106,7 +106,7 @@ def decode_files_all_gpus(args, in_files, chunk=4096):
         with _lib.borrow_ctx(local) as ctx:  # two of these run at a time, each on its own stream and arena
             if isinstance(payload, batch.ReadBatch):
                 if args.algorithm == 'viterbi':
-                    return batch.viterbi_batch(payload, args.basecaller, device=ctx)[0]
+                    return batch.viterbi_batch(payload, args.basecaller, device=ctx, return_maps=False)[0]
                 return batch.beam_search_batch(payload, args.beam_width, dec.MODEL_TYPE[args.basecaller], device=ctx)[0]
             return dec.decode_models(payload, args.algorithm, args.beam_width, device=ctx)
 

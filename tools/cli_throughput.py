@@ -26,6 +26,47 @@ def _gen(job):
     return synth.save_pair(d, k, T)
 
 
+def decode_mode(a, d, names):
+    """`python -m poreover_b200 decode DIR --basecaller bonito --algorithm ...` on a directory of 2 x pairs reads
+    (symbolic links to the unique files): multigpu.decode_files_all_gpus + the FASTA output of decode.decode."""
+    from pathlib import Path
+
+    from poreover_b200 import multigpu
+    from poreover_b200.__main__ import build_parser
+    from poreover_b200.decoding import decode as dec
+    uniq = [n for pair in names for n in pair]
+    rd = os.path.join(d, "reads")
+    os.mkdir(rd)
+    files = []
+    for i in range(2 * a.pairs):
+        f = os.path.join(rd, "read%06d.npy" % i)
+        os.symlink(os.path.join(d, uniq[i % len(uniq)]), f)
+        files.append(f)
+    args = build_parser().parse_args(["decode", rd, "--basecaller", "bonito", "--algorithm", a.decode, "--beam_width",
+                                      str(a.beam_width), "--out", os.path.join(d, "dec")])
+
+    def whole_run(fs):
+        seqs = multigpu.decode_files_all_gpus(args, fs)
+        with open(args.out + '.fasta', 'w') as out_fasta:
+            for p, sq in zip(fs, seqs):
+                print(dec.fasta_format(Path(p).stem, sq), file=out_fasta)
+        return seqs
+
+    whole_run(files[:min(len(files), 4096)])
+    t0 = time.perf_counter()
+    seqs = whole_run(files)
+    t_run = time.perf_counter() - t0
+    out = {"metric": "decode_cli_reads_per_s", "algorithm": a.decode, "value": len(files) / t_run, "unit": "reads/s",
+           "reads": len(files), "T": a.T, "beam_width": a.beam_width if a.decode == "beam" else None,
+           "mbases_per_s": sum(len(s) for s in seqs) / t_run / 1e6, "wall_s": t_run, "host_cores": os.cpu_count(),
+           "tree": os.environ.get("POB_TREE", "this checkout"),
+           "what": "files on disk (page cache) -> .fasta, one process, one GPU, wall clock"}
+    print(json.dumps(out))
+    if a.out:
+        with open(a.out, "w") as f:
+            f.write(json.dumps(out) + "\n")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pairs", type=int, default=8192)
@@ -34,6 +75,8 @@ def main():
     ap.add_argument("--beam_width", type=int, default=25)
     ap.add_argument("--out", default=None)
     ap.add_argument("--whole-only", action="store_true", help="only the whole-run figure (works on older trees)")
+    ap.add_argument("--decode", choices=["viterbi", "beam"], default=None,
+                    help="time the single-read `decode` command line on 2 x --pairs reads instead of pair-decode")
     a = ap.parse_args()
     from poreover_b200 import multigpu
     from poreover_b200.__main__ import build_parser
@@ -44,6 +87,8 @@ def main():
     with ProcessPoolExecutor() as ex:
         names = list(ex.map(_gen, [(d, k, a.T) for k in range(a.unique)], chunksize=8))
     t_gen = time.perf_counter() - t0
+    if a.decode:
+        return decode_mode(a, d, names)
     pair_list = [list(names[i % a.unique]) for i in range(a.pairs)]
     with open(os.path.join(d, "pairs.txt"), "w") as f:
         for p in pair_list:
