@@ -12,6 +12,8 @@
 // memory (slot = row & (SZ-1)); every computed cell is also streamed to global memory in
 // anti-diagonal-major order (coalesced) for the recompute-style traceback.  Integer pipe + shared memory
 // bound; algorithmic work = sum_i (end_i - start_i) cells.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "launch.cuh"
 
@@ -83,6 +85,95 @@ nw_fill_kernel(const uint8_t* __restrict__ seq1, const int64_t* __restrict__ off
       int v = max(max(dg + sc, up + gap), lf + gap);
       cur[i & mask] = v;
       Mp[(size_t)d * SZ + (i & mask)] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// Fill, row-owner variant (the one that runs whenever SZ <= 1024, i.e. band <= 511): thread t owns the rows
+// i = t, t + NT, t + 2 NT, ... (NT == SZ).  The active rows of an anti-diagonal are a contiguous range of fewer than
+// SZ rows (i + start_i and i + end_i both increase strictly with i and a row is active for at most 2 band + 1
+// diagonals), so a thread has at most one active row per diagonal and stays on a row for its whole band:
+//   * the band of rows i and i-1 and the character of row i live in registers (recomputed when the thread moves on),
+//   * the left neighbour M(i, j-1) is the thread's own previous value, the diagonal neighbour M(i-1, j-1) is the
+//     `up` value it read one diagonal earlier,
+// which leaves one shared-memory read (M(i-1, j) from the row above), one character of read 2, one shared and one
+// global store per cell, and no per-diagonal search for the active range.  Same cells, same values, same layout of M
+// as nw_fill_kernel below (kept for wider bands).
+template <int NT>
+__global__ void __launch_bounds__(NT, 2048 / NT)
+nw_fill_rows_kernel(const uint8_t* __restrict__ seq1, const int64_t* __restrict__ off1,
+                    const int32_t* __restrict__ len1, const uint8_t* __restrict__ seq2,
+                    const int64_t* __restrict__ off2, const int32_t* __restrict__ len2,
+                    const int32_t* __restrict__ skip, int band, int match, int mismatch, int gap,
+                    const int64_t* __restrict__ m_off, int32_t* __restrict__ M, const int64_t* __restrict__ rb_off,
+                    int32_t* __restrict__ rowband) {
+  extern __shared__ int32_t sm[];
+  constexpr int SZ = NT, mask = NT - 1;
+  const int p = blockIdx.x;
+  if (skip && skip[p]) return;
+  const int l1 = len1 ? len1[p] : (int)(off1[p + 1] - off1[p]);
+  const int l2 = len2 ? len2[p] : (int)(off2[p + 1] - off2[p]);
+  if (l1 <= 0) return;
+  const uint8_t* s1 = seq1 + off1[p];
+  const uint8_t* s2 = seq2 + off2[p];
+  int32_t* Mp = M + m_off[p];
+  int32_t* rs = rowband + rb_off[p];  // [l1] start, then [l1] end: read by the traceback
+  int32_t* re = rs + l1;
+  const int t = threadIdx.x;
+  for (int i = t; i < l1; i += NT) {
+    int s, e;
+    row_band(i, l1, l2, band, s, e);
+    rs[i] = s;
+    re[i] = e;
+  }
+  for (int k = t; k < 3 * SZ; k += NT) sm[k] = 0;
+  __syncthreads();
+  if (l2 <= 0) return;
+  // state of the row this thread is on
+  int i = t, si = 0, ei = -1, sp = 0, ep = -1;
+  uint8_t ch = 0;
+  bool fresh = true;        // no `up` value of the previous diagonal yet (first diagonal on this row)
+  int dg_next = 0, v_prev = 0;
+  if (i < l1) {
+    row_band(i, l1, l2, band, si, ei);
+    if (i > 0) row_band(i - 1, l1, l2, band, sp, ep);
+    ch = wrap_char(s1, l1, i - 1);
+  }
+  const int D = l1 + l2 - 1;
+  const int slot = t;       // (i & mask) == t for every row this thread owns
+  const int slot_up = (t + NT - 1) & mask;
+  for (int d = 0; d < D; ++d) {
+    // row finished (or empty and passed): move on to the next row of this thread
+    while (i < l1 && d - i >= ei) {
+      i += NT;
+      fresh = true;
+      if (i < l1) {
+        row_band(i, l1, l2, band, si, ei);
+        row_band(i - 1, l1, l2, band, sp, ep);
+        ch = wrap_char(s1, l1, i - 1);
+      }
+    }
+    int32_t* cur = sm + (d % 3) * SZ;
+    const int32_t* p1 = sm + ((d + 2) % 3) * SZ;  // d-1
+    const int32_t* p2 = sm + ((d + 1) % 3) * SZ;  // d-2
+    if (i < l1) {
+      const int j = d - i;
+      // M(i-1, j): read on every diagonal once the row is in sight, it is the next diagonal's M(i-1, j-1)
+      const int up = (i > 0 && j >= sp && j < ep) ? p1[slot_up] : 0;
+      if (j >= si && j < ei) {
+        int dg;
+        if (fresh) dg = (i > 0 && j - 1 >= sp && j - 1 < ep) ? p2[slot_up] : 0;
+        else dg = dg_next;
+        const int sc = (ch == wrap_char(s2, l2, j - 1)) ? match : mismatch;
+        const int lf = (j - 1 >= si) ? v_prev : 0;
+        const int v = max(max(dg + sc, up + gap), lf + gap);
+        cur[slot] = v;
+        Mp[(size_t)d * SZ + slot] = v;
+        v_prev = v;
+      }
+      dg_next = up;
+      fresh = false;
     }
     __syncthreads();
   }
@@ -321,8 +412,20 @@ int pob_nw_launch(pob_ctx* ctx, const uint8_t* seq1, const int64_t* off1, const 
     POB_CUDA(cudaFuncSetAttribute(nw_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   {
     pob_prof_scope ps(ctx, POB_K_NW_FILL);
-    nw_fill_kernel<<<n, NW_THREADS, smem, ctx->stream>>>(seq1, off1, len1, seq2, off2, len2, skip, band, match,
-                                                         mismatch, gap, SZ, m_off, M, rb_off, rowband);
+    static const bool generic = getenv("POB_DEBUG_NW_GENERIC") != nullptr;
+#define POB_NW_ROWS(NT)                                                                                          \
+  nw_fill_rows_kernel<NT><<<n, NT, smem, ctx->stream>>>(seq1, off1, len1, seq2, off2, len2, skip, band, match, \
+                                                        mismatch, gap, m_off, M, rb_off, rowband)
+    if (generic || SZ > 1024) {
+      nw_fill_kernel<<<n, NW_THREADS, smem, ctx->stream>>>(seq1, off1, len1, seq2, off2, len2, skip, band, match,
+                                                           mismatch, gap, SZ, m_off, M, rb_off, rowband);
+    } else if (SZ == 1024) POB_NW_ROWS(1024);
+    else if (SZ == 512) POB_NW_ROWS(512);
+    else if (SZ == 256) POB_NW_ROWS(256);
+    else if (SZ == 128) POB_NW_ROWS(128);
+    else if (SZ == 64) POB_NW_ROWS(64);
+    else return POB_EINVAL;
+#undef POB_NW_ROWS
   }
   POB_CUDA(cudaGetLastError());
   {
