@@ -141,41 +141,48 @@ nw_fill_rows_kernel(const uint8_t* __restrict__ seq1, const int64_t* __restrict_
     ch = wrap_char(s1, l1, i - 1);
   }
   const int D = l1 + l2 - 1;
-  const int slot = t;       // (i & mask) == t for every row this thread owns
-  const int slot_up = (t + NT - 1) & mask;
-  for (int d = 0; d < D; ++d) {
-    // row finished (or empty and passed): move on to the next row of this thread
-    while (i < l1 && d - i >= ei) {
-      i += NT;
-      fresh = true;
-      if (i < l1) {
-        row_band(i, l1, l2, band, si, ei);
-        row_band(i - 1, l1, l2, band, sp, ep);
-        ch = wrap_char(s1, l1, i - 1);
-      }
-    }
-    int32_t* cur = sm + (d % 3) * SZ;
-    const int32_t* p1 = sm + ((d + 2) % 3) * SZ;  // d-1
-    const int32_t* p2 = sm + ((d + 1) % 3) * SZ;  // d-2
+  const int slot_up = (t + NT - 1) & mask;  // (i & mask) == t for every row this thread owns
+  int32_t* cur = sm;                        // diagonal d; p1 = d-1, p2 = d-2 (rotated at the end of every iteration)
+  const int32_t* p1 = sm + 2 * SZ;
+  const int32_t* p2 = sm + SZ;
+  int32_t* mrow = Mp + t;                   // &M[d][t]
+  for (int d = 0; d < D; ++d, mrow += SZ) {
     if (i < l1) {
-      const int j = d - i;
-      // M(i-1, j): read on every diagonal once the row is in sight, it is the next diagonal's M(i-1, j-1)
-      const int up = (i > 0 && j >= sp && j < ep) ? p1[slot_up] : 0;
-      if (j >= si && j < ei) {
-        int dg;
-        if (fresh) dg = (i > 0 && j - 1 >= sp && j - 1 < ep) ? p2[slot_up] : 0;
-        else dg = dg_next;
-        const int sc = (ch == wrap_char(s2, l2, j - 1)) ? match : mismatch;
-        const int lf = (j - 1 >= si) ? v_prev : 0;
-        const int v = max(max(dg + sc, up + gap), lf + gap);
-        cur[slot] = v;
-        Mp[(size_t)d * SZ + slot] = v;
-        v_prev = v;
+      int j = d - i;
+      if (j >= ei) {
+        // row finished (or empty and passed): move on to the next row of this thread
+        do {
+          i += NT;
+          if (i < l1) {
+            row_band(i, l1, l2, band, si, ei);
+            row_band(i - 1, l1, l2, band, sp, ep);
+            ch = wrap_char(s1, l1, i - 1);
+          }
+        } while (i < l1 && d - i >= ei);
+        fresh = true;
+        j = d - i;
       }
-      dg_next = up;
-      fresh = false;
+      if (i < l1 && j >= si - 1) {
+        // M(i-1, j): read from the diagonal before the row's first cell on, it is the next diagonal's M(i-1, j-1)
+        const int up = (i > 0 && j >= sp && j < ep) ? p1[slot_up] : 0;
+        if (j >= si) {
+          int dg;
+          if (fresh) dg = (i > 0 && j - 1 >= sp && j - 1 < ep) ? p2[slot_up] : 0;
+          else dg = dg_next;
+          const int sc = (ch == wrap_char(s2, l2, j - 1)) ? match : mismatch;
+          const int lf = (j - 1 >= si) ? v_prev : 0;
+          const int v = max(max(dg + sc, up + gap), lf + gap);
+          cur[t] = v;
+          *mrow = v;
+          v_prev = v;
+        }
+        dg_next = up;
+        fresh = false;
+      }
     }
     __syncthreads();
+    int32_t* const nxt = const_cast<int32_t*>(p2);
+    p2 = p1; p1 = cur; cur = nxt;
   }
 }
 
