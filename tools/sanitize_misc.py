@@ -26,4 +26,14 @@ w = O.pair_decode(synth.bonito_log_prob(p1), O.reverse_complement(synth.bonito_l
 bad += r["consensus"] != w["consensus"]
 g = batch.align_global_batch([r["basecall1"]], [r["basecall2"]])[0]
 bad += (g[0], g[1]) != tuple("".join(x) for x in O.global_pair(r["basecall1"], r["basecall2"])[:2])
+# banded NW, row-owner fill kernel at several slot counts (band 1/3/10 -> 64 slots, 40 -> 128, 500 -> 1024), uneven
+# lengths (several rows of a thread in one pair) and a band wider than the kernel's 1024 threads (generic kernel)
+rng = np.random.default_rng(11)
+for n1, n2, band in ((90, 100, 1), (300, 120, 3), (57, 211, 10), (400, 380, 40), (700, 650, 500), (150, 140, 600)):
+    a = "".join(rng.choice(list("ACGT"), size=n1))
+    b = "".join(rng.choice(list("ACGT"), size=n2))
+    got = batch.align_banded_batch([a, b], [b, a], band_width=band)
+    for (x, y), gt in zip(((a, b), (b, a)), got):
+        want = O.global_pair_banded(x, y, band)
+        bad += (gt[0], gt[1]) != ("".join(want[0]), "".join(want[1]))
 print("done, mismatches:", bad)
