@@ -1408,10 +1408,6 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   P.RQ = P.NP * 2;
   // the band sweep wants one thread per (node, read); the single-read search one per node
   int threads = (((mode == MODE_1D ? 1 : 2) * P.EMAX + 31) / 32) * 32;
-  // wide single-read beams: the all-pairs ranking is the largest phase (EMAX candidates per thread); two threads per
-  // candidate halve its loop and double the warps that hide its shared-memory latency (one CTA per SM either way)
-  static const int wide_1d = getenv("POB_DEBUG_1D_WIDE") ? atoi(getenv("POB_DEBUG_1D_WIDE")) : 0;
-  if (mode == MODE_1D && wide_1d && P.EMAX > 256 && 2 * P.EMAX <= 1024) threads = ((2 * P.EMAX + 31) / 32) * 32;
   if (threads > 1024) return POB_EUNSUPPORTED;
   if (threads < 64) threads = 64;
   if (P.inspect_every == 0) {
