@@ -76,6 +76,7 @@ class PoreoverB200Error(RuntimeError):
 
 _lib = None
 _lock = threading.Lock()
+_ctx_lock = threading.Lock()
 _ctxs = {}
 
 
@@ -188,16 +189,15 @@ def get_ctx(device=None):
         return device
     if device is None:
         device = int(os.environ.get("POREOVER_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
-    with _lock:
+    lib()  # loaded before _ctx_lock is taken (lib() has its own lock)
+    with _ctx_lock:  # creation is atomic: the command-line pipeline asks from two GPU threads at once
         c = _ctxs.get(device)
-    if c is None:
-        if device_count() <= device:
-            raise PoreoverB200Error(
-                "no CUDA device %d visible: poreover_b200 has no CPU fallback (%s)"
-                % (device, lib().pob_last_cuda_error().decode()))
-        c = Context(device)
-        with _lock:
-            _ctxs[device] = c
+        if c is None:
+            if device_count() <= device:
+                raise PoreoverB200Error(
+                    "no CUDA device %d visible: poreover_b200 has no CPU fallback (%s)"
+                    % (device, lib().pob_last_cuda_error().decode()))
+            c = _ctxs[device] = Context(device)
     return c
 
 
