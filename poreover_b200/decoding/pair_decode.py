@@ -318,7 +318,7 @@ def format_decoded(args, raw):
     return results
 
 
-def decode_pairs(args, pair_list, device=None, chunk=2048):
+def decode_pairs(args, pair_list, device=None, chunk=4096):
     """Decode [(name1, name2), ...] -> list of pair_decode_helper-style results, in input order.
 
     Chunks of pairs go through a three-stage pipeline: files are loaded a chunk ahead (ingest.py), two GPU calls are

@@ -114,7 +114,7 @@ def decode_files_all_gpus(args, in_files, chunk=4096):
     return run_sharded(in_files, [size_of(p) for p in in_files], work, chunk, group, store, load_chunk=load)
 
 
-def decode_pairs_all_gpus(args, pair_list, chunk=2048):
+def decode_pairs_all_gpus(args, pair_list, chunk=4096):
     """CLI path: every rank decodes the chunks it pulls on its own GPU (LOCAL_RANK)."""
     from .decoding import pair_decode as pd
     rank, world, local = dist_info()
@@ -135,7 +135,7 @@ def decode_pairs_all_gpus(args, pair_list, chunk=2048):
             return 0
 
     cost = [cost_of(p) for p in pair_list]
-    # small runs: at least ~4 chunks per rank so that every GPU gets work; large runs: 2048-pair batches (a B200 holds
+    # small runs: at least ~4 chunks per rank so that every GPU gets work; large runs: 4096-pair batches (a B200 holds
     # 444 pairs in flight, so a batch should be several waves; the next batch is loaded while this one is decoded)
     pd._check_args(args)
     chunk = max(8, min(chunk, -(-len(pair_list) // (4 * world))))

@@ -121,7 +121,7 @@ def main():
         return
     from poreover_b200 import ingest
     # the stages on their own, same chunking as the run
-    chunk = max(8, min(2048, -(-len(pair_list) // 4)))
+    chunk = max(8, min(4096, -(-len(pair_list) // 4)))
     subs = [pair_list[i:i + chunk] for i in range(0, len(pair_list), chunk)]
     t0 = time.perf_counter()
     payloads = [pd.load_pairs(args, s) for s in subs[:2]]
