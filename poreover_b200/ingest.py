@@ -233,39 +233,64 @@ class Lookahead:
 
 
 class PinnedPool:
-    """Page-locked host buffers (pob_malloc_host) for the packed batches, reused from chunk to chunk: pinning costs
-    more than the copy it speeds up, so a buffer goes back to the pool when the last numpy view of it dies."""
+    """Page-locked host buffers (pob_malloc_host) for the packed batches, reused from chunk to chunk: a buffer goes
+    back to the pool when the last numpy view of it dies.  Pinning costs more than the copy it speeds up (0.2 s per
+    GB), so nothing ever waits for it: a request that finds no free buffer gets None (the caller uses pageable
+    memory for this chunk) and a background thread pins one more buffer of that size for the chunks to come."""
 
     def __init__(self, keep=8):
         self._free, self._lock, self._keep = [], threading.Lock(), keep
+        self._owned = 0            # buffers pinned so far (free or in use)
+        self._wanted = []          # sizes the background thread still has to pin
+        self._thread = None
+        self._closed = False
 
     def _give(self, cap, addr):
         with self._lock:
-            if len(self._free) < self._keep:
-                self._free.append((cap, addr))
-                return
-        _lib.lib().pob_free_host(C.c_void_p(addr))
+            self._free.append((cap, addr))
+
+    def _pin_loop(self):
+        while True:
+            with self._lock:
+                if not self._wanted or self._closed:
+                    self._thread = None
+                    return
+                cap = self._wanted.pop(0)
+            h = C.c_void_p()
+            ok = _lib.lib().pob_malloc_host(C.c_size_t(cap), C.byref(h)) == 0 and h.value
+            with self._lock:
+                if ok:
+                    self._free.append((cap, h.value))
+                else:
+                    self._owned -= 1   # no pinned memory to be had (no GPU): stay on pageable buffers
+
+    def close(self):
+        """Stop pinning (interpreter exit): wait for the allocation in flight, leave the rest to the OS."""
+        with self._lock:
+            self._closed = True
+            t = self._thread
+        if t is not None:
+            t.join(timeout=5)
 
     def empty(self, shape, dtype):
-        """np.empty(shape, dtype) in pinned memory, or None when no pinned memory can be had (no GPU)."""
+        """np.empty(shape, dtype) in pinned memory, or None when no pinned buffer of that size is free right now."""
         import weakref
         dtype = np.dtype(dtype)
         nbytes = int(np.prod(shape)) * dtype.itemsize
         if nbytes == 0:
             return np.zeros(shape, dtype)
-        addr = cap = None
         with self._lock:
             fit = [x for x in self._free if x[0] >= nbytes]
-            if fit:
-                cap, addr = min(fit)
-                self._free.remove((cap, addr))
-        fresh = addr is None
-        if fresh:
-            cap = (nbytes * 5 // 4 + 4095) & ~4095  # headroom: chunks of a run differ a little in size
-            h = C.c_void_p()
-            if _lib.lib().pob_malloc_host(C.c_size_t(cap), C.byref(h)) != 0 or not h.value:
+            if not fit:
+                if self._owned < self._keep and not self._closed:
+                    self._owned += 1
+                    self._wanted.append((nbytes * 5 // 4 + 4095) & ~4095)  # headroom: chunks differ a little in size
+                    if self._thread is None:
+                        self._thread = threading.Thread(target=self._pin_loop, name="pob-pin", daemon=True)
+                        self._thread.start()
                 return None
-            addr = h.value
+            cap, addr = min(fit)
+            self._free.remove((cap, addr))
         cbuf = (C.c_char * cap).from_address(addr)
         weakref.finalize(cbuf, self._give, cap, addr)
         return np.frombuffer(cbuf, dtype=np.uint8, count=nbytes).view(dtype).reshape(shape)
@@ -275,12 +300,15 @@ _pinned = None
 
 
 def packed_alloc():
-    """Allocator of load_reads' packed buffers: pinned when POREOVER_B200_PINNED=1, else numpy's."""
+    """Allocator of load_reads' packed buffers: the pinned pool when POREOVER_B200_PINNED=1, else numpy's."""
     global _pinned
     if os.environ.get("POREOVER_B200_PINNED", "0") != "1":
         return None
-    if _pinned is None:
-        _pinned = PinnedPool()
+    with _pool_lock:
+        if _pinned is None:
+            import atexit
+            _pinned = PinnedPool()
+            atexit.register(_pinned.close)
 
     def alloc(shape, dtype):
         a = _pinned.empty(shape, dtype)
