@@ -186,78 +186,66 @@ nw_fill_rows_kernel(const uint8_t* __restrict__ seq1, const int64_t* __restrict_
   }
 }
 
-// M(i, j) as the reference's SparseMatrix returns it; the row's band is recomputed (same function as the fill) rather
-// than loaded, which takes a dependent L2 round trip out of every traceback step
-__device__ __forceinline__ int m_get_rb(const int32_t* Mp, int l1, int l2, int band, int SZ, int i, int j) {
+__device__ __forceinline__ int m_get(const int32_t* Mp, const int32_t* rs, const int32_t* re, int l1, int SZ, int i,
+                                     int j) {
   if (i < 0 || i >= l1) return 0;
-  int s, e;
-  row_band(i, l1, l2, band, s, e);
-  if (j < s || j >= e) return 0;  // column `end` itself is in range of get() but holds 0
+  if (j < rs[i] || j >= re[i]) return 0;  // column `end` itself is in range of get() but holds 0
   return Mp[(size_t)(i + j) * SZ + (i & (SZ - 1))];
 }
 
-// Traceback, step 1: one THREAD per pair walks the path (a chain of dependent reads of M from L2 / HBM: the lanes of
-// a warp keep 32 such chains in flight) and writes the gapped rows backwards from the end of the pair's output slot.
-__global__ void __launch_bounds__(32)
-nw_traceback_walk_kernel(const uint8_t* __restrict__ seq1, const int64_t* __restrict__ off1,
-                         const int32_t* __restrict__ len1, const uint8_t* __restrict__ seq2,
-                         const int64_t* __restrict__ off2, const int32_t* __restrict__ len2,
-                         const int32_t* __restrict__ skip, int n, int band, int gap, int SZ,
-                         const int64_t* __restrict__ m_off, const int32_t* __restrict__ M,
-                         const int64_t* __restrict__ aln_off, uint8_t* __restrict__ out_a1,
-                         uint8_t* __restrict__ out_a2, int32_t* __restrict__ out_alen,
-                         int32_t* __restrict__ out_matches) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per pair: lane 0 walks the path (writing the gapped rows backwards from the end of the
+// pair's output slot), then the warp moves them to the front and counts equal columns.
+__global__ void __launch_bounds__(128)
+nw_traceback_kernel(const uint8_t* __restrict__ seq1, const int64_t* __restrict__ off1,
+                    const int32_t* __restrict__ len1, const uint8_t* __restrict__ seq2,
+                    const int64_t* __restrict__ off2, const int32_t* __restrict__ len2,
+                    const int32_t* __restrict__ skip, int n, int gap, int SZ, const int64_t* __restrict__ m_off,
+                    const int32_t* __restrict__ M, const int64_t* __restrict__ rb_off,
+                    const int32_t* __restrict__ rowband, const int64_t* __restrict__ aln_off,
+                    uint8_t* __restrict__ out_a1, uint8_t* __restrict__ out_a2, int32_t* __restrict__ out_alen,
+                    int32_t* __restrict__ out_matches) {
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (p >= n) return;
   if (skip && skip[p]) {
-    out_alen[p] = 0;
-    if (out_matches) out_matches[p] = 0;
+    if (lane == 0) { out_alen[p] = 0; if (out_matches) out_matches[p] = 0; }
     return;
   }
   const int l1 = len1 ? len1[p] : (int)(off1[p + 1] - off1[p]);
   const int l2 = len2 ? len2[p] : (int)(off2[p + 1] - off2[p]);
   if (l1 <= 0) {  // ZeroDivisionError in the reference (align.pyx:122)
-    out_alen[p] = -1;
-    if (out_matches) out_matches[p] = 0;
+    if (lane == 0) { out_alen[p] = -1; if (out_matches) out_matches[p] = 0; }
     return;
   }
   const uint8_t* s1 = seq1 + off1[p];
   const uint8_t* s2 = seq2 + off2[p];
   const int32_t* Mp = M + m_off[p];
+  const int32_t* rs = rowband + rb_off[p];
+  const int32_t* re = rs + l1;
   uint8_t* a1 = out_a1 + aln_off[p];
   uint8_t* a2 = out_a2 + aln_off[p];
   const int cap = (int)(aln_off[p + 1] - aln_off[p]);
-  int i = l1, j = l2, w = cap;  // write position moves down from cap
-  while (i > 0 && j > 0) {
-    const int sc = (wrap_char(s1, l1, i - 1) == wrap_char(s2, l2, j - 1)) ? 2 : -1;
-    const int c0 = m_get_rb(Mp, l1, l2, band, SZ, i - 1, j - 1) + sc;
-    const int c1 = m_get_rb(Mp, l1, l2, band, SZ, i - 1, j) + gap;
-    const int c2 = m_get_rb(Mp, l1, l2, band, SZ, i, j - 1) + gap;
-    const int mx = max(c0, max(c1, c2));
-    if (c0 == mx) { --i; --j; --w; a1[w] = wrap_char(s1, l1, i); a2[w] = wrap_char(s2, l2, j); }
-    if (c1 == mx) { --i; --w; a1[w] = wrap_char(s1, l1, i); a2[w] = '-'; }
-    if (c2 == mx) { --j; --w; a1[w] = '-'; a2[w] = wrap_char(s2, l2, j); }
+  int n_col = 0;
+  if (lane == 0) {
+    int i = l1, j = l2, w = cap;  // write position moves down from cap
+    while (i > 0 && j > 0) {
+      const int sc = (wrap_char(s1, l1, i - 1) == wrap_char(s2, l2, j - 1)) ? 2 : -1;
+      const int c0 = m_get(Mp, rs, re, l1, SZ, i - 1, j - 1) + sc;
+      const int c1 = m_get(Mp, rs, re, l1, SZ, i - 1, j) + gap;
+      const int c2 = m_get(Mp, rs, re, l1, SZ, i, j - 1) + gap;
+      const int mx = max(c0, max(c1, c2));
+      if (c0 == mx) { --i; --j; --w; a1[w] = wrap_char(s1, l1, i); a2[w] = wrap_char(s2, l2, j); }
+      if (c1 == mx) { --i; --w; a1[w] = wrap_char(s1, l1, i); a2[w] = '-'; }
+      if (c2 == mx) { --j; --w; a1[w] = '-'; a2[w] = wrap_char(s2, l2, j); }
+    }
+    while (i > 0 || j > 0) {
+      if (i > 0) { --i; --w; a1[w] = wrap_char(s1, l1, i); a2[w] = '-'; }
+      else { --j; --w; a1[w] = '-'; a2[w] = wrap_char(s2, l2, j); }
+    }
+    n_col = cap - w;
   }
-  while (i > 0 || j > 0) {
-    if (i > 0) { --i; --w; a1[w] = wrap_char(s1, l1, i); a2[w] = '-'; }
-    else { --j; --w; a1[w] = '-'; a2[w] = wrap_char(s2, l2, j); }
-  }
-  out_alen[p] = cap - w;
-}
-
-// Traceback, step 2: one warp per pair moves the rows to the front of the slot and counts equal columns.
-__global__ void __launch_bounds__(128)
-nw_traceback_pack_kernel(int n, const int64_t* __restrict__ aln_off, uint8_t* __restrict__ out_a1,
-                         uint8_t* __restrict__ out_a2, const int32_t* __restrict__ out_alen,
-                         int32_t* __restrict__ out_matches) {
-  const int lane = threadIdx.x & 31;
-  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (p >= n) return;
-  const int n_col = out_alen[p];
-  if (n_col <= 0) return;  // skipped pair or empty read 1: the walk wrote the counts
-  uint8_t* a1 = out_a1 + aln_off[p];
-  uint8_t* a2 = out_a2 + aln_off[p];
-  const int cap = (int)(aln_off[p + 1] - aln_off[p]);
+  n_col = __shfl_sync(0xffffffffu, n_col, 0);
+  __syncwarp();
   const int src = cap - n_col;
   int matches = 0;
   for (int c0 = 0; c0 < n_col; c0 += 32) {  // ascending chunks: safe forward move of overlapping ranges
@@ -272,7 +260,10 @@ nw_traceback_pack_kernel(int n, const int64_t* __restrict__ aln_off, uint8_t* __
     __syncwarp();
   }
   matches = __reduce_add_sync(0xffffffffu, matches);
-  if (lane == 0 && out_matches) out_matches[p] = matches;
+  if (lane == 0) {
+    out_alen[p] = n_col;
+    if (out_matches) out_matches[p] = matches;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -446,10 +437,9 @@ int pob_nw_launch(pob_ctx* ctx, const uint8_t* seq1, const int64_t* off1, const 
   POB_CUDA(cudaGetLastError());
   {
     pob_prof_scope ps(ctx, POB_K_NW_TRACE);
-    nw_traceback_walk_kernel<<<(n + 31) / 32, 32, 0, ctx->stream>>>(seq1, off1, len1, seq2, off2, len2, skip, n, band, gap,
-                                                                   SZ, m_off, M, aln_off, out_a1, out_a2, out_alen,
-                                                                   out_matches);
-    nw_traceback_pack_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(n, aln_off, out_a1, out_a2, out_alen, out_matches);
+    nw_traceback_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(seq1, off1, len1, seq2, off2, len2, skip, n, gap, SZ,
+                                                              m_off, M, rb_off, rowband, aln_off, out_a1, out_a2,
+                                                              out_alen, out_matches);
   }
   POB_CUDA(cudaGetLastError());
   return POB_OK;
