@@ -327,13 +327,22 @@ def decode_pairs(args, pair_list, device=None, chunk=4096):
     from .. import ingest, multigpu
     _check_args(args)
     results = [None] * len(pair_list)
-    q = multigpu.WorkQueue(len(pair_list), chunk, ramp=1)
+
+    def size_of(in_path):
+        try:
+            return os.path.getsize(os.path.join(args.dir, _paths(args, in_path)[0]))
+        except (OSError, IndexError):
+            return 0
+
+    cost = [size_of(p) for p in pair_list]  # chunks of long reads are cut by bytes, and get one GPU call at a time
+    q = multigpu.WorkQueue(len(pair_list), chunk, ramp=1, weights=cost, weight_budget=multigpu.CHUNK_BYTES)
 
     def gpu_stage(payload):
         with batch._lib.borrow_ctx(device) as ctx:  # two of these run at a time, each on its own stream and arena
             return decode_loaded(args, payload, ctx, fmt=False)
 
-    for c, raw in ingest.Lookahead(q.next, lambda c: load_pairs(args, pair_list[c[0]:c[1]]), gpu_stage):
+    for c, raw in ingest.Lookahead(q.next, lambda c: load_pairs(args, pair_list[c[0]:c[1]]), gpu_stage,
+                                   workers=multigpu._lanes_for(cost)):
         res = format_decoded(args, raw)
         results[c[0]:c[0] + len(res)] = res
     return results

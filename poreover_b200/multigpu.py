@@ -14,15 +14,25 @@ def dist_info():
 
 class WorkQueue:
     """Chunked dynamic queue over range(n_items) shared by all ranks of a torch.distributed job.  The first `ramp`
-    chunks are a quarter of the size: a pipelined consumer starts its first GPU call sooner."""
+    chunks are a quarter of the size: a pipelined consumer starts its first GPU call sooner.  With `weights` (one
+    per item, in queue order) a chunk also ends once it holds `weight_budget`: batches of long reads stay small."""
 
-    def __init__(self, n_items, chunk, store=None, key="poreover_b200_queue", ramp=0):
+    def __init__(self, n_items, chunk, store=None, key="poreover_b200_queue", ramp=0, weights=None, weight_budget=None):
         self.n, self.chunk, self.store, self.key = n_items, max(1, chunk), store, key
         self._local = 0
         self.bounds = [0]  # the same on every rank: chunk k = [bounds[k], bounds[k+1])
         while self.bounds[-1] < n_items:
-            step = max(1, self.chunk // 4) if len(self.bounds) - 1 < ramp else self.chunk
-            self.bounds.append(min(n_items, self.bounds[-1] + step))
+            lo = self.bounds[-1]
+            small = len(self.bounds) - 1 < ramp
+            step = max(1, self.chunk // 4) if small else self.chunk
+            hi = min(n_items, lo + step)
+            if weights is not None and weight_budget:
+                budget, acc, k = (weight_budget / 4 if small else weight_budget), 0, lo
+                while k < hi and (k == lo or acc + weights[k] <= budget):
+                    acc += weights[k]
+                    k += 1
+                hi = k
+            self.bounds.append(hi)
 
     def next(self):
         if self.store is None:
@@ -35,22 +45,26 @@ class WorkQueue:
         return self.bounds[k], self.bounds[k + 1]
 
 
-def run_sharded(items, cost, process_chunk, chunk=256, group=None, store=None, load_chunk=None, finish_chunk=None):
+def run_sharded(items, cost, process_chunk, chunk=256, group=None, store=None, load_chunk=None, finish_chunk=None,
+                cost_budget=None, workers=None):
     """Process `items` across all ranks.  cost[i] orders the queue (descending).  process_chunk(list) ->
     list of results.  With load_chunk, a chunk goes through a pipeline -- payload = load_chunk(list) on a host
     thread, process_chunk(payload) on a second thread (the GPU call), then finish_chunk(its result) -> list of
     results on the calling thread -- so that loading chunk k+2, decoding chunk k+1 and formatting chunk k overlap
-    (the queue itself is only touched from the calling thread).  Returns the full result list in input order on
+    (the queue itself is only touched from the calling thread).  cost_budget caps the summed cost of a chunk;
+    workers = GPU calls in flight (default: ingest.Lookahead's).  Returns the full result list in input order on
     rank 0, None elsewhere."""
     from .ingest import Lookahead
     rank, world, _ = dist_info()
     order = sorted(range(len(items)), key=lambda i: -cost[i])
-    q = WorkQueue(len(order), chunk, store if world > 1 else None, ramp=world if load_chunk else 0)
+    q = WorkQueue(len(order), chunk, store if world > 1 else None, ramp=world if load_chunk else 0,
+                  weights=[cost[i] for i in order] if cost_budget else None, weight_budget=cost_budget)
     mine = {}
     if load_chunk is None:
         stream = ((c, process_chunk([items[i] for i in order[c[0]:c[1]]])) for c in iter(q.next, None))
     else:
-        stream = Lookahead(q.next, lambda c: load_chunk([items[i] for i in order[c[0]:c[1]]]), process_chunk)
+        stream = Lookahead(q.next, lambda c: load_chunk([items[i] for i in order[c[0]:c[1]]]), process_chunk,
+                           workers=workers)
     for c, res in stream:
         if finish_chunk is not None:
             res = finish_chunk(res)
@@ -68,6 +82,18 @@ def run_sharded(items, cost, process_chunk, chunk=256, group=None, store=None, l
         for i, r in part.items():
             out[i] = r
     return out
+
+
+# A chunk holds at most this many bytes of (first-read) input files: 4096 pairs of T~5000 are 0.4 GB, so short reads
+# are limited by the pair count and long reads (2 MB per file at T = 100k) by this.
+CHUNK_BYTES = 1 << 30
+# Reads longer than this (file bytes; ~T = 50k) get wide envelopes and node pools of tens of GB per context: one GPU
+# call in flight instead of two, as before the pipelined command line.
+LONG_READ_BYTES = 1 << 20
+
+
+def _lanes_for(cost):
+    return 1 if cost and max(cost) > LONG_READ_BYTES else None
 
 
 def _host_group():
@@ -111,7 +137,9 @@ def decode_files_all_gpus(args, in_files, chunk=4096):
             return dec.decode_models(payload, args.algorithm, args.beam_width, device=ctx)
 
     chunk = max(8, min(chunk, -(-len(in_files) // (4 * world))))
-    return run_sharded(in_files, [size_of(p) for p in in_files], work, chunk, group, store, load_chunk=load)
+    cost = [size_of(p) for p in in_files]
+    return run_sharded(in_files, cost, work, chunk, group, store, load_chunk=load, cost_budget=CHUNK_BYTES,
+                       workers=_lanes_for(cost))
 
 
 def decode_pairs_all_gpus(args, pair_list, chunk=4096):
@@ -146,4 +174,5 @@ def decode_pairs_all_gpus(args, pair_list, chunk=4096):
             return pd.decode_loaded(args, payload, device=ctx, fmt=False)
 
     return run_sharded(pair_list, cost, gpu_stage, chunk, group, store, load_chunk=lambda sub: pd.load_pairs(args, sub),
-                       finish_chunk=lambda raw: pd.format_decoded(args, raw))
+                       finish_chunk=lambda raw: pd.format_decoded(args, raw), cost_budget=CHUNK_BYTES,
+                       workers=_lanes_for(cost))

@@ -217,6 +217,12 @@ def test_ramped_queue_and_pinned_fallback(monkeypatch):
     assert got == [(0, 64), (64, 128), (128, 384), (384, 640), (640, 896), (896, 1000)]
     assert list(iter(multigpu.WorkQueue(10, 4).next, None)) == [(0, 4), (4, 8), (8, 10)]
     assert list(iter(multigpu.WorkQueue(0, 4, ramp=1).next, None)) == []
+    # chunks are also cut by weight (file bytes): long reads make small batches, a single heavy item still goes through
+    q = multigpu.WorkQueue(10, 4, weights=[5, 5, 5, 1, 1, 1, 1, 1, 1, 1], weight_budget=6)
+    assert list(iter(q.next, None)) == [(0, 1), (1, 2), (2, 4), (4, 8), (8, 10)]
+    q = multigpu.WorkQueue(10, 4, ramp=1, weights=[50, 5, 5, 1, 1, 1, 1, 1, 1, 1], weight_budget=8)
+    assert list(iter(q.next, None)) == [(0, 1), (1, 2), (2, 6), (6, 10)]
+    assert multigpu._lanes_for([100, 3 << 20]) == 1 and multigpu._lanes_for([100, 200000]) is None
     out = multigpu.run_sharded(list(range(40)), [i % 5 for i in range(40)], lambda p: [x * 2 for x in p], chunk=8,
                                load_chunk=lambda sub: [x + 1 for x in sub], finish_chunk=lambda r: [x - 2 for x in r])
     assert out == [2 * i for i in range(40)]
