@@ -267,3 +267,19 @@ def test_load_pairs_host_stage(tmp_path):
     meta, m1, m2, kind = gpd.load_pairs(args, pairs)
     ref = _reference_arrays([os.path.join(str(tmp_path), p[0]) for p in pairs], "bonito")
     assert all(np.array_equal(a, b) for a, b in zip(m1, ref)) and len(m2) == 3
+
+
+def test_real_logits_fixture_through_the_batched_loader(tmp_path):
+    """The reference's own real-data pair (PoreOverNet logits, windows x time x states, 62,000 and 75,600 timesteps):
+    the batched loader must hand the kernels exactly the arrays decode.model_from_trace makes."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "real_pair.npz"))
+    paths = []
+    for name in ("read1", "read2"):
+        f = tmp_path / (name + ".npy")
+        np.save(f, g[name])
+        paths.append(str(f))
+    ref = _reference_arrays(paths, "poreover")
+    b = ingest.load_reads(paths, "poreover", rc=[0, 1])
+    assert b.layout == _lib.BLANK_LAST and b.dtype == _lib.F32 and b.lens.tolist() == [62000, 75600]
+    for i, a in enumerate(ref):
+        assert np.array_equal(_rows(b, i), a)
