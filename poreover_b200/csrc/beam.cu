@@ -728,19 +728,38 @@ struct Engine {
     const int mid = two ? (EMAX >> 1) : EMAX;
     const int j0 = half ? mid : 0, j1 = half ? EMAX : mid;
     const unsigned long long* const k64 = reinterpret_cast<const unsigned long long*>(key);  // [2a] score key, [2a+1] order
+    const unsigned* const k32 = reinterpret_cast<const unsigned*>(key);  // [4a+1] high word of the score key
     unsigned long long ks = 0;
     int eq = 0;
     if (cand) {
-      // fast pass: integer compares of the score keys only; exact ties are counted and resolved below
-      ks = k64[2 * a];
+      // fast pass on the high words only (sign, exponent, 20 mantissa bits: monotone, not strict): a candidate whose
+      // high word is unique has its exact rank; one that is out of the beam by high words is out of the beam
+      const unsigned kh = k32[4 * a + 1];
 #pragma unroll 8
       for (int j = j0; j < j1; ++j) {
-        const unsigned long long kj = k64[2 * j];
-        rank += kj > ks;
-        eq += kj == ks;
+        const unsigned kj = k32[4 * j + 1];
+        rank += kj > kh;
+        eq += kj == kh;
       }
     }
     if (two) { rank += __shfl_xor_sync(0xffffffffu, rank, 1); eq += __shfl_xor_sync(0xffffffffu, eq, 1); }
+    // some candidate of this warp that could be in the beam shares its high word (scores within 2^-20 relative, or
+    // equal): the whole warp repeats the pass on the full 64-bit keys (the shuffles must stay convergent)
+    if (__any_sync(0xffffffffu, cand && rank < W && eq > 1)) {
+      rank = 0; eq = 0;
+      if (cand) {
+        ks = k64[2 * a];
+#pragma unroll 8
+        for (int j = j0; j < j1; ++j) {
+          const unsigned long long kj = k64[2 * j];
+          rank += kj > ks;
+          eq += kj == ks;
+        }
+      }
+      if (two) { rank += __shfl_xor_sync(0xffffffffu, rank, 1); eq += __shfl_xor_sync(0xffffffffu, eq, 1); }
+    } else {
+      eq = 1;  // no exact tie can matter
+    }
     // a candidate that could be in the beam and shares its score with another one: rank the tie by creation order
     // (rare; the whole warp takes the exact pass so that the shuffles stay convergent)
     if (__any_sync(0xffffffffu, cand && rank < W && eq > 1)) {
