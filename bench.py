@@ -324,10 +324,10 @@ def run_ours(args):
         # DRAM traffic of one launch of this kernel on this workload, from the committed ncu --set full capture
         traffic, traffic_src = None, None
         try:
-            ns = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01_e.json")))["viterbi5_f32_kernel"]
+            ns = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01_f.json")))["viterbi5_f32_kernel"]
             if vb.n == 10000 and args.T == 5000:
                 traffic = ns["dram_traffic_bytes_per_launch"]
-                traffic_src = "profiles/ncu_summary_r01_e.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)"
+                traffic_src = "profiles/ncu_summary_r01_f.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)"
         except (OSError, ValueError, KeyError):
             pass
         roof = {"kernel": "viterbi_ctc (%d reads, T=%d, %.2f GB in)" % (vb.n, args.T, float(vb.lens.sum()) * 20 / 1e9),
@@ -349,10 +349,10 @@ def run_ours(args):
         beam["hbm_frame"] = {"algorithmic_bytes_per_launch": alg, "achieved": alg / max(1e-9, beam_ms / 1e3) / 1e9,
                              "peak": peak, "unit": "GB/s", "frac": alg / max(1e-9, beam_ms / 1e3) / 1e9 / peak}
         try:
-            nb = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01_e.json")))["beam_kernel"]
+            nb = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01_f.json")))["beam_kernel"]
             per_pair = (nb["dram_read"] + nb["dram_write"]) * 1e9 / nb["grid"]
             beam["hbm_frame"]["traffic"] = per_pair * P
-            beam["hbm_frame"]["traffic_source"] = ("profiles/ncu_summary_r01_e.json: (dram__bytes_read.sum + "
+            beam["hbm_frame"]["traffic_source"] = ("profiles/ncu_summary_r01_f.json: (dram__bytes_read.sum + "
                                                    "dram__bytes_write.sum) / 444 pairs x pairs per launch")
         except (OSError, ValueError, KeyError):
             beam["hbm_frame"]["traffic"] = None
