@@ -35,7 +35,7 @@ int pob_viterbi(pob_ctx* ctx, int where, const pob_reads_t* reads, int kind, uin
   return POB_OK;
 }
 
-// ---- not yet built in this revision: every symbol of the header exists and fails loudly ----
+// ---- flip-flop Viterbi (transducer.py:35-59): uint8 traces through the host-computed table, or float64 ----
 int pob_viterbi_flipflop(pob_ctx* ctx, int where, const pob_reads_t* reads, const double* lut, uint8_t* out_seq,
                          int32_t* out_s2s, int8_t* out_path, int32_t* out_len) {
   if (!ctx) return POB_EINVAL;
