@@ -90,11 +90,6 @@ nw_fill_kernel(const uint8_t* __restrict__ seq1, const int64_t* __restrict__ off
   }
 }
 
-// One arrival of the calling warp at the CTA's barrier 0.  The row-owner fill executes it from two places (the working
-// path and the sleeping loop of a warp that is outside the band): what matters to bar.sync is that every warp arrives
-// once per anti-diagonal, not where from.  It orders shared-memory accesses among the participants like __syncthreads.
-__device__ __forceinline__ void nw_block_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
-
 // Fill, row-owner variant (the one that runs whenever SZ <= 1024, i.e. band <= 511): thread t owns the rows
 // i = t, t + NT, t + 2 NT, ... (NT == SZ).  The active rows of an anti-diagonal are a contiguous range of fewer than
 // SZ rows (i + start_i and i + end_i both increase strictly with i and a row is active for at most 2 band + 1
@@ -151,25 +146,7 @@ nw_fill_rows_kernel(const uint8_t* __restrict__ seq1, const int64_t* __restrict_
   const int32_t* p1 = sm + 2 * SZ;
   const int32_t* p2 = sm + SZ;
   int32_t* mrow = Mp + t;                   // &M[d][t]
-  // A warp (32 consecutive rows) has nothing to do before the first of its rows comes into sight and between the end
-  // of its rows' bands and the next rows it owns: it sleeps through those diagonals in a loop of bare barriers
-  // (every warp still arrives at one barrier per diagonal) and catches its pointers up when it wakes.
-  int wake = __reduce_min_sync(0xffffffffu, i < l1 ? i + si - 1 : 0x7fffffff);
-  int d = 0;
-  while (d < D) {
-    if (d < wake) {  // warp-uniform
-      const int stop = min(wake, D);
-      const int n = stop - d;
-      for (int k = 0; k < n; ++k) nw_block_barrier();
-      d = stop;
-      mrow += (size_t)n * SZ;
-      const int ph = d % 3;
-      cur = sm + ph * SZ;
-      p1 = sm + ((ph + 2) % 3) * SZ;
-      p2 = sm + ((ph + 1) % 3) * SZ;
-      continue;
-    }
-    bool switched = false;
+  for (int d = 0; d < D; ++d, mrow += SZ) {
     if (i < l1) {
       int j = d - i;
       if (j >= ei) {
@@ -183,7 +160,6 @@ nw_fill_rows_kernel(const uint8_t* __restrict__ seq1, const int64_t* __restrict_
           }
         } while (i < l1 && d - i >= ei);
         fresh = true;
-        switched = true;
         j = d - i;
       }
       if (i < l1 && j >= si - 1) {
@@ -204,13 +180,9 @@ nw_fill_rows_kernel(const uint8_t* __restrict__ seq1, const int64_t* __restrict_
         fresh = false;
       }
     }
-    if (__any_sync(0xffffffffu, switched))
-      wake = __reduce_min_sync(0xffffffffu, i < l1 ? i + si - 1 : 0x7fffffff);
-    nw_block_barrier();
+    __syncthreads();
     int32_t* const nxt = const_cast<int32_t*>(p2);
     p2 = p1; p1 = cur; cur = nxt;
-    ++d;
-    mrow += SZ;
   }
 }
 
