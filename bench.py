@@ -356,6 +356,19 @@ def run_ours(args):
                                                    "dram__bytes_write.sum) / 444 pairs x pairs per launch")
         except (OSError, ValueError, KeyError):
             beam["hbm_frame"]["traffic"] = None
+        # ... and in the instruction-issue frame, the resource the kernel does use: warp instructions per pair from the
+        # same capture x pairs per launch / the live kernel time, against 4 issue slots per SM and clock (148 SMs)
+        try:
+            nb = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01_f.json")))["beam_kernel"]
+            sm_mhz = float((clocks or {}).get("sm_mhz") or 0.0) or 1965.0
+            issued = float(nb["warp_instructions"]) / float(nb["grid"]) * P / max(1e-9, beam_ms / 1e3)
+            peak_issue = 148 * 4 * sm_mhz * 1e6
+            beam["issue_frame"] = {"achieved": issued / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-instructions/s",
+                                   "frac": issued / peak_issue,
+                                   "source": "profiles/ncu_summary_r01_f.json smsp__inst_executed.sum / 444 pairs x pairs "
+                                             "per launch / live kernel time; peak = 148 SMs x 4 schedulers x SM clock"}
+        except Exception:  # the frame is an annotation: never let it take the bench line down
+            pass
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
