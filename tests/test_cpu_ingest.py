@@ -283,3 +283,40 @@ def test_real_logits_fixture_through_the_batched_loader(tmp_path):
     assert b.layout == _lib.BLANK_LAST and b.dtype == _lib.F32 and b.lens.tolist() == [62000, 75600]
     for i, a in enumerate(ref):
         assert np.array_equal(_rows(b, i), a)
+
+
+def test_work_queue_bounds_partition_the_items():
+    """Whatever the chunk size, ramp and byte budget: the chunks are non-empty, contiguous and cover every item once."""
+    from poreover_b200 import multigpu
+    rng = np.random.default_rng(12)
+    for _ in range(200):
+        n = int(rng.integers(0, 300))
+        chunk = int(rng.integers(1, 64))
+        ramp = int(rng.integers(0, 4))
+        weights = sorted((int(x) for x in rng.integers(0, 50, size=n)), reverse=True) if rng.random() < 0.7 else None
+        budget = int(rng.integers(1, 200)) if weights is not None else None
+        q = multigpu.WorkQueue(n, chunk, ramp=ramp, weights=weights, weight_budget=budget)
+        got = list(iter(q.next, None))
+        assert all(lo < hi for lo, hi in got)
+        assert [lo for lo, _ in got] == [0] * bool(got) + [hi for _, hi in got[:-1]]
+        assert (got[-1][1] if got else 0) == n
+        assert all(hi - lo <= chunk for lo, hi in got)
+        if weights is not None:
+            for lo, hi in got:  # within the budget, except for a single item that alone exceeds it
+                assert hi - lo == 1 or sum(weights[lo:hi]) <= budget
+
+
+def test_fasta_format_is_the_reference_loop():
+    """decode.py:20-27 literally, against the join-based version, for every length around the line width."""
+    def ref(name, seq, width=60):
+        fasta = '>' + name + '\n'
+        window = 0
+        while window + width < len(seq):
+            fasta += (seq[window:window + width] + '\n')
+            window += width
+        fasta += (seq[window:] + '\n')
+        return fasta
+    for n in list(range(0, 200)) + [599, 600, 601, 6000]:
+        s = ''.join("ACGT"[(7 * i) % 4] for i in range(n))
+        for w in (60, 1, 7):
+            assert gdecode.fasta_format("read", s, w) == ref("read", s, w), (n, w)
