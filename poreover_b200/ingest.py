@@ -33,7 +33,12 @@ def n_threads():
     env = os.environ.get("POREOVER_B200_LOADER_THREADS")
     if env:
         return max(1, int(env))
-    return max(1, min(32, os.cpu_count() or 4))
+    cores = os.cpu_count() or 4
+    try:  # under torchrun the ranks of a box share its cores
+        cores //= max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    except ValueError:
+        pass
+    return max(2, min(32, cores))
 
 
 def pool():
