@@ -124,6 +124,11 @@ __device__ __forceinline__ double lae(double a, double b) {
   return (m == ninf()) ? m : r;
 }
 
+__device__ __forceinline__ unsigned sign_acc(unsigned d, unsigned acc) {
+  unsigned r;
+  asm("mad.hi.u32 %0, %1, 2, %2;" : "=r"(r) : "r"(d), "r"(acc));
+  return r;
+}
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
@@ -162,7 +167,9 @@ __device__ __forceinline__ ReadView make_view(const pob_reads& r, int item) {
 }
 
 enum { SH_NB = 0, SH_NUSED, SH_FQH, SH_FQT, SH_AFREE, SH_ORDER, SH_TID, SH_STAMP, SH_RQH, SH_RQT, SH_STATUS, SH_FIRSTALIVE,
-       SH_TOTALLOC, SH_TOTFIRST, SH_DMIN, SH_TB0, SH_TB1, SH_XSTEP, SH_COUNT };
+       SH_TOTALLOC, SH_TOTFIRST, SH_DMIN, SH_TB0, SH_TB1, SH_XSTEP, SH_NL0, SH_NL1, SH_SREF /* double: 2 slots */,
+       SH_SREF_HI, SH_PCNT, SH_PM0, SH_PM1, SH_PM2, SH_PM3,
+       SH_ENV = 32 /* [2][2] band of row u */, SH_ENVT = 36 /* [2][2] band of column v */, SH_COUNT = 48 };
 
 // Per-CTA engine state.  Scalars and global-memory views live in a static __shared__ struct; the per-active-slot
 // arrays live in dynamic shared memory at offsets that depend only on EMAX / W / NP, so every access compiles
@@ -199,6 +206,7 @@ __shared__ long long g_pclk_last;
 #else
 #define PCLK(i) do { } while (0)
 #endif
+__device__ unsigned long long g_exact_prunes;  // how often the ranking needed its exact pass (diagnostic)
 extern __shared__ __align__(16) char pob_smem[];
 
 // Shared-memory arrays of the active slots (index a in [0, EMAX)); a_slot[a] < 0 = unused.
@@ -241,13 +249,17 @@ extern __shared__ __align__(16) char pob_smem[];
   int32_t* const a_che = (int32_t*)(sm_ + 216 * EMAX);                                              \
   int32_t* const beam = (int32_t*)(sm_ + 224 * EMAX);                                               \
   int32_t* const sh = beam + ((W + 3) & ~3);                                                        \
-  int16_t* const slot2e = (int16_t*)(sh + 32);                                                      \
+  int16_t* const slot2e = (int16_t*)(sh + SH_COUNT);                                                \
   uint8_t* const a_last = (uint8_t*)(slot2e + NP);                                                  \
   const int eb_ = (EMAX + 15) & ~15;                                                                \
   uint8_t* const a_pstat = a_last + eb_;                                                            \
   uint8_t* const a_same = a_pstat + eb_;                                                            \
   uint8_t* const a_inbeam = a_same + eb_;                                                           \
   uint8_t* const a_needed = a_inbeam + eb_;                                                         \
+  const int E4 = (EMAX + 3) & ~3;                                                                   \
+  uint32_t* const k32 = (uint32_t*)(a_needed + eb_);                                                \
+  double* const resmax = (double*)(k32 + E4);                                                       \
+  int16_t* const lst = (int16_t*)(resmax + 2 * EMAX);                                               \
   NodeHdr* const hdr = g_es.hdr;                                                                    \
   int32_t* const freelist = g_es.freelist;                                                          \
   int2* const retq = g_es.retq;                                                                     \
@@ -386,6 +398,135 @@ struct Engine {
     else return q->prob;
   }
 
+  // Everything a thread needs to recompute cells of one (active slot, read): views of the node's window, of its
+  // parent's window and of the read's probability rows.  Filled from the shared-memory arrays, so that any thread can
+  // take over any item (see long_chains).
+  struct SwItem {
+    Ent* wb;
+    const Ent* pwb;
+    const char* ybase;
+    long yrowb, ycol_last, ycol_blank;
+    int lo, hi, plo, phi, pstat, pa, wmask, yT;
+    bool same, f64, yrc;
+  };
+
+  __device__ __forceinline__ void load_item(int a, int r, SwItem& I) const {
+    POB_VIEWS
+    I.lo = a_lo[2 * a + r]; I.hi = a_hi[2 * a + r];
+    I.wmask = g_es.mask[r];
+    I.wb = wbase(a_slot[a], r);
+    const ReadView& v = g_es.rv[r];
+    I.f64 = v.f64; I.yrc = v.rc; I.yT = v.T;
+    const long es = I.f64 ? 8 : 4;
+    I.yrowb = (long)v.S * es;
+    I.ybase = (const char*)v.base;
+    I.ycol_last = (long)v.pcol(a_last[a]) * es;
+    I.ycol_blank = (long)v.cblank * es;
+    I.pstat = a_pstat[a];
+    I.same = a_same[a] != 0;
+    I.pa = 0; I.plo = 0; I.phi = 0; I.pwb = nullptr;
+    if (I.pstat == PS_INE) {
+      I.pa = a_par[a];
+      I.plo = a_lo[2 * I.pa + r]; I.phi = a_hi[2 * I.pa + r]; I.pwb = wbase(a_pslot[a], r);
+    } else if (I.pstat == PS_FROZEN) {
+      I.plo = a_plo[2 * a + r]; I.phi = a_phi[2 * a + r]; I.pwb = wbase(a_pslot[a], r);
+    }
+  }
+
+  __device__ __forceinline__ void load_y(const SwItem& I, const char* row, double& yl, double& yb) const {
+    if (I.f64) { yl = __ldg((const double*)(row + I.ycol_last)); yb = __ldg((const double*)(row + I.ycol_blank)); }
+    else { yl = (double)__ldg((const float*)(row + I.ycol_last)); yb = (double)__ldg((const float*)(row + I.ycol_blank)); }
+  }
+
+  __device__ __forceinline__ double parent_at(const SwItem& I, int r, int t) const {
+    if (I.pstat == PS_INE || I.pstat == PS_FROZEN) return frozen_at(I.pwb, t, I.wmask, I.plo, I.phi, I.same);
+    if (I.pstat == PS_ROOT) return root_prob(r, t - 1);
+    return ninf();
+  }
+
+  // Private recomputation of the cells [cs, lim) of one (node, read), cs < lim: every parent entry read here is
+  // final.  Leaves the node's values at lim - 1 in p_prev / ng_prev / g_prev and folds the new values into maxv.
+  __device__ __forceinline__ void chain(const SwItem& I, int a, int r, int cs, int lim, bool mirror, double& p_prev,
+                                        double& ng_prev, double& g_prev, double& maxv) const {
+    p_prev = ninf(); ng_prev = ninf();
+    if (cs - 1 >= I.lo && cs - 1 < I.hi) {
+      const Ent* se = I.wb + (cs & I.wmask);
+      p_prev = se->prob;
+      if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { ng_prev = se->nogap; }
+    }
+    const long ystep = I.yrc ? -I.yrowb : I.yrowb;
+    const char* row = I.ybase + (long)(I.yrc ? (I.yT - 1 - cs) : cs) * I.yrowb;
+    double yl, yb;
+    load_y(I, row, yl, yb);
+    double pv = parent_at(I, r, cs);
+    // merge-repeats: the no-gap chain ng(t) = lae(pv(t) + y, ng(t-1) + y) does not depend on prob(t-1), so ng(t+1)
+    // is evaluated next to prob(t) = lae(prob(t-1) + yblank, ng(t)) -- two independent log-add-exps per
+    // iteration instead of two dependent ones (same operations on the same operands, hence the same values)
+    double ng_cur = ninf();
+    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_cur = lae(pv + yl, ng_prev + yl);
+    // inputs are requested two timesteps ahead: those of t+1 were loaded during iteration t-1 (or just below),
+    // so the no-gap chain of t+1 never waits for a load issued in the same iteration
+    double yl_n = 0, yb_n = 0, pv_n = ninf();
+    row += ystep;
+    if (cs + 1 < lim) {
+      load_y(I, row, yl_n, yb_n);
+      pv_n = parent_at(I, r, cs + 1);
+    }
+    for (int t = cs; t < lim; ++t) {
+      double yl_n2 = 0, yb_n2 = 0, pv_n2 = ninf();
+      row += ystep;
+      if (t + 2 < lim) {
+        load_y(I, row, yl_n2, yb_n2);
+        pv_n2 = parent_at(I, r, t + 2);
+      }
+      double prob;
+      Ent* o = I.wb + ((t + 1) & I.wmask);
+      if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
+        const double ng_nxt = lae(pv_n + yl_n, ng_cur + yl_n);  // for t+1; unused after the last iteration
+        const double gp = p_prev + yb;
+        const double ng = ng_cur;
+        prob = lae(gp, ng);
+        double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
+        *reinterpret_cast<double4*>(o) = v4;
+        ng_prev = ng; g_prev = gp;
+        ng_cur = ng_nxt;
+      } else {
+        prob = lae(pv + yl, p_prev + yb);
+        o->prob = prob;
+      }
+      if (mirror) mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
+      p_prev = prob;
+      if (prob > maxv) maxv = prob;
+      yl = yl_n; yb = yb_n; pv = pv_n;
+      yl_n = yl_n2; yb_n = yb_n2; pv_n = pv_n2;
+    }
+  }
+
+  // Whole-band recomputations (nodes that entered the expanded beam in this step) are long dependent chains, and the
+  // threads that own them are scattered over all warps: left in place, every warp of the block would run a dozen
+  // iterations with one or two active lanes.  Their owners queue them instead (one list per read, so that chains of
+  // equal length share a warp), and the LAST warps of the block (which own few items of their own) run one chain per
+  // lane.  Only the band maximum travels back through shared memory; the values at the end of the chain are in the
+  // node's window.
+  __device__ __noinline__ void long_chains(int nl0, int nl1, int s0, int e0, int s1, int e1, bool mirror) {
+    POB_VIEWS
+    const int k0 = (nl0 + 31) >> 5, k1 = (nl1 + 31) >> 5;
+    // worker index, counted from the end of the block; a block with fewer warps than lists' warps takes several rounds
+    for (int w = (int)blockDim.x - 1 - (int)threadIdx.x; w < 32 * (k0 + k1); w += (int)blockDim.x) {
+      int r = 0, idx = w;
+      if (w >= 32 * k0) { r = 1; idx = w - 32 * k0; }
+      if (idx >= (r ? nl1 : nl0)) continue;
+      const int a = lst[r * EMAX + idx];
+      const int ts = r ? s1 : s0, te = r ? e1 : e0;
+      const int lim = min(te, sh[SH_TB0 + r]);
+      SwItem I;
+      load_item(a, r, I);
+      double p_prev, ng_prev, g_prev = ninf(), maxv = ninf();
+      if (ts < lim) chain(I, a, r, ts, lim, mirror, p_prev, ng_prev, g_prev, maxv);
+      resmax[2 * a + r] = maxv;
+    }
+  }
+
   // ---- band sweep over the expanded beam (BeamSearch.h:361-375, :146-156), incremental ----------------
   // reads_mask bit r: read r swept over [s_r, e_r).  Thread (2a + r) owns (active slot a, read r).
   //
@@ -395,7 +536,8 @@ struct Engine {
   //     sweep / single updates from inputs that are still current; cs = clamp(che, s, e) is where new work
   //     starts (new and revived nodes: cs = s);
   //   * phase A (no barrier): each item computes [cs, min(e, Tb)) on its own; all parent entries it reads
-  //     there are final because Tb = 1 + min over live-parent items of the parent's cs;
+  //     there are final because Tb = 1 + min over live-parent items of the parent's cs.  New and revived nodes
+  //     (whole band) are handed to long_chains();
   //   * phase B (one barrier per timestep): the time-major loop over [Tb, e) with parent values exchanged
   //     through shared memory.  A node whose live parent produced a new value at t-1 recomputes from t on
   //     even inside its own clean range (dirtiness propagates down the tree);
@@ -408,58 +550,34 @@ struct Engine {
     const int a = tid >> 1, r = tid & 1;
     const bool used = a < EMAX && a_slot[a] >= 0;
     const bool on = used && ((reads_mask >> r) & 1);
-    int lo = 0, hi = 0, plo = 0, phi = 0, pstat = PS_DEAD, pa = 0, cs = 0;
-    bool same = false, was_fresh = true;
+    int cs = 0;
+    bool was_fresh = true, longi = false;
     double p_prev = ninf(), ng_prev = ninf(), g_prev = ninf(), maxv = ninf();
     const int ts = r ? s1 : s0, te = r ? e1 : e0;
-    Ent* wb = nullptr;
-    const Ent* pwb = nullptr;
-    int wmask = 0;
-    const char* ylast_p = nullptr;
-    const char* yblank_p = nullptr;
-    long ystep = 0, ycol_last = 0, ycol_blank = 0;
-    const char* ybase = nullptr;
-    bool f64 = false, yrc = false;
-    int yT = 0;
-    long yrowb = 0;
+    SwItem I;
+    I.lo = I.hi = I.plo = I.phi = I.pa = I.wmask = I.yT = 0; I.pstat = PS_DEAD; I.same = I.f64 = I.yrc = false;
+    I.wb = nullptr; I.pwb = nullptr; I.ybase = nullptr; I.yrowb = I.ycol_last = I.ycol_blank = 0;
     PCLK(12);
     deferred_finalize();
     const bool mirror = g_es.mir_off >= 0;
     PCLK(13);
     if (on && te > ts) {
-      const int slot = a_slot[a];
-      const int last = a_last[a];
-      lo = a_lo[2 * a + r]; hi = a_hi[2 * a + r];
-      wmask = g_es.mask[r];
-      wb = wbase(slot, r);
-      {
-        const ReadView v = g_es.rv[r];
-        f64 = v.f64; yrc = v.rc; yT = v.T;
-        const long es = f64 ? 8 : 4;
-        yrowb = (long)v.S * es;
-        ybase = (const char*)v.base;
-        ystep = v.rc ? -yrowb : yrowb;
-        ycol_last = (long)v.pcol(last) * es;
-        ycol_blank = (long)v.cblank * es;
-      }
+      load_item(a, r, I);
       const int che = a_che[2 * a + r];
       was_fresh = che < 0;
       cs = full ? ts : min(max(che, ts), te);
-      pstat = a_pstat[a];
-      same = a_same[a] != 0;
-      if (pstat == PS_INE) {
-        pa = a_par[a];
-        const int pche = a_che[2 * pa + r];
+      if (I.pstat == PS_INE) {
+        const int pche = a_che[2 * I.pa + r];
         const int pcs = full ? ts : min(max(pche, ts), te);
         atomicMin(&sh[SH_TB0 + r], pcs + 1);
-        plo = a_lo[2 * pa + r]; phi = a_hi[2 * pa + r]; pwb = wbase(a_pslot[a], r);
-      } else if (pstat == PS_FROZEN) {
-        plo = a_plo[2 * a + r]; phi = a_phi[2 * a + r]; pwb = wbase(a_pslot[a], r);
       }
+      // a node that entered the expanded beam in this step recomputes its whole band: queue it for long_chains()
+      longi = !full && was_fresh && te - ts >= 2;
+      if (longi) lst[r * EMAX + atomicAdd(&sh[SH_NL0 + r], 1)] = (int16_t)a;
       PCLK(14);
       // clean part of the band: only the maximum is needed (independent loads, four in flight)
       {
-        const int c0 = max(ts, lo), c1 = min(cs, hi);
+        const int c0 = max(ts, I.lo), c1 = min(cs, I.hi);
         // [c0, g1) from the window, [g1, m1) from the shared-memory mirror, [m1, c1) from the window again (rare)
         int g1 = c0, m1 = c0;
         if (mirror && che >= 0) {
@@ -478,10 +596,10 @@ struct Engine {
           const int b0 = part ? m1 : c0, b1 = part ? c1 : g1;
           for (int t = b0; t < b1; t += 4) {
             double v0 = ninf(), v1 = ninf(), v2 = ninf(), v3 = ninf();
-            v0 = (wb + ((t + 1) & wmask))->prob;
-            if (t + 1 < b1) v1 = (wb + ((t + 2) & wmask))->prob;
-            if (t + 2 < b1) v2 = (wb + ((t + 3) & wmask))->prob;
-            if (t + 3 < b1) v3 = (wb + ((t + 4) & wmask))->prob;
+            v0 = (I.wb + ((t + 1) & I.wmask))->prob;
+            if (t + 1 < b1) v1 = (I.wb + ((t + 2) & I.wmask))->prob;
+            if (t + 2 < b1) v2 = (I.wb + ((t + 3) & I.wmask))->prob;
+            if (t + 3 < b1) v3 = (I.wb + ((t + 4) & I.wmask))->prob;
             maxv = fmax(fmax(maxv, v0), fmax(fmax(v1, v2), v3));
           }
         }
@@ -491,72 +609,19 @@ struct Engine {
     __syncthreads();
     PCLK(1);
     const int Tb0 = sh[SH_TB0], Tb1 = sh[SH_TB1];
+    const int nl0 = sh[SH_NL0], nl1 = sh[SH_NL1];
     const int Tb = r ? Tb1 : Tb0;  // first timestep of this read that needs the synchronised loop
     bool computing = false;        // p_prev / ng_prev hold the node's values at the previous timestep
+    const int limA = min(te, Tb);
     // ---- phase A: private work [cs, min(te, Tb))
-    if (on && te > ts) {
-      const int limA = min(te, Tb);
-      if (cs < limA) {
-        if (cs - 1 >= lo && cs - 1 < hi) {
-          const Ent* se = wb + (cs & wmask);
-          p_prev = se->prob;
-          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { ng_prev = se->nogap; }
-        }
-        computing = true;
-        const char* row = ybase + (long)(yrc ? (yT - 1 - cs) : cs) * yrowb;
-        ylast_p = row + ycol_last; yblank_p = row + ycol_blank;
-        double yl, yb;
-        if (f64) { yl = __ldg((const double*)ylast_p); yb = __ldg((const double*)yblank_p); }
-        else { yl = (double)__ldg((const float*)ylast_p); yb = (double)__ldg((const float*)yblank_p); }
-        double pv = ninf();
-        if (pstat == PS_INE || pstat == PS_FROZEN) pv = frozen_at(pwb, cs, wmask, plo, phi, same);
-        else if (pstat == PS_ROOT) pv = root_prob(r, cs - 1);
-        // merge-repeats: the no-gap chain ng(t) = lae(pv(t) + y, ng(t-1) + y) does not depend on prob(t-1), so ng(t+1)
-        // is evaluated next to prob(t) = lae(prob(t-1) + yblank, ng(t)) -- two independent log-add-exps per
-        // iteration instead of two dependent ones (same operations on the same operands, hence the same values)
-        double ng_cur = ninf();
-        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_cur = lae(pv + yl, ng_prev + yl);
-        // inputs are requested two timesteps ahead: those of t+1 were loaded during iteration t-1 (or just below),
-        // so the no-gap chain of t+1 never waits for a load issued in the same iteration
-        double yl_n = 0, yb_n = 0, pv_n = ninf();
-        ylast_p += ystep; yblank_p += ystep;
-        if (cs + 1 < limA) {
-          if (f64) { yl_n = __ldg((const double*)ylast_p); yb_n = __ldg((const double*)yblank_p); }
-          else { yl_n = (double)__ldg((const float*)ylast_p); yb_n = (double)__ldg((const float*)yblank_p); }
-          if (pstat == PS_INE || pstat == PS_FROZEN) pv_n = frozen_at(pwb, cs + 1, wmask, plo, phi, same);
-          else if (pstat == PS_ROOT) pv_n = root_prob(r, cs);
-        }
-        for (int t = cs; t < limA; ++t) {
-          double yl_n2 = 0, yb_n2 = 0, pv_n2 = ninf();
-          ylast_p += ystep; yblank_p += ystep;
-          if (t + 2 < limA) {
-            if (f64) { yl_n2 = __ldg((const double*)ylast_p); yb_n2 = __ldg((const double*)yblank_p); }
-            else { yl_n2 = (double)__ldg((const float*)ylast_p); yb_n2 = (double)__ldg((const float*)yblank_p); }
-            if (pstat == PS_INE || pstat == PS_FROZEN) pv_n2 = frozen_at(pwb, t + 2, wmask, plo, phi, same);
-            else if (pstat == PS_ROOT) pv_n2 = root_prob(r, t + 1);
-          }
-          double prob;
-          Ent* o = wb + ((t + 1) & wmask);
-          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
-            const double ng_nxt = lae(pv_n + yl_n, ng_cur + yl_n);  // for t+1; unused after the last iteration
-            const double gp = p_prev + yb;
-            const double ng = ng_cur;
-            prob = lae(gp, ng);
-            double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
-            *reinterpret_cast<double4*>(o) = v4;
-            ng_prev = ng; g_prev = gp;
-            ng_cur = ng_nxt;
-          } else {
-            prob = lae(pv + yl, p_prev + yb);
-            o->prob = prob;
-          }
-          if (mirror) mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
-          p_prev = prob;
-          if (prob > maxv) maxv = prob;
-          yl = yl_n; yb = yb_n; pv = pv_n;
-          yl_n = yl_n2; yb_n = yb_n2; pv_n = pv_n2;
-        }
-      }
+    if (on && te > ts && cs < limA) {
+      computing = true;
+      if (!longi) chain(I, a, r, cs, limA, mirror, p_prev, ng_prev, g_prev, maxv);
+    }
+    if (nl0 + nl1 > 0) {
+      if ((int)blockDim.x - 1 - tid < 32 * (((nl0 + 31) >> 5) + ((nl1 + 31) >> 5))) long_chains(nl0, nl1, s0, e0, s1, e1, mirror);
+      __syncthreads();
+      if (longi) maxv = resmax[2 * a + r];
     }
     PCLK(2);
     // ---- phase B: synchronised time-major loop over [Tb, te)
@@ -565,51 +630,54 @@ struct Engine {
       uint8_t* const pchg = reinterpret_cast<uint8_t*>(tmpa);  // [2][EMAX*2] "parent value changed" flags
       const bool inB = on && te > ts && Tb < te;
       double ylast = 0, yblank = 0;
+      const long ystep = I.yrc ? -I.yrowb : I.yrowb;
+      const char* row = nullptr;
       if (inB) {
+        if (longi && computing) {
+          // the chain ran on another thread: its last values are in the window
+          const Ent* se = I.wb + (Tb & I.wmask);
+          p_prev = se->prob;
+          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { g_prev = se->gap; ng_prev = se->nogap; }
+        }
         // publish the node's value at Tb-1: computed in phase A, or a stored clean entry
         double2 pb; pb.x = ninf(); pb.y = ninf();
         const int tp = Tb - 1;
         if (computing) { pb.x = p_prev; pb.y = g_prev; }
-        else if (tp >= lo && tp < hi) {
-          const Ent* se = wb + ((tp + 1) & wmask);
+        else if (tp >= I.lo && tp < I.hi) {
+          const Ent* se = I.wb + ((tp + 1) & I.wmask);
           pb.x = se->prob;
           if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pb.y = se->gap;
         }
         pub[a * 2 + r] = pb;
         pchg[a * 2 + r] = computing;
-        const char* row = ybase + (long)(yrc ? (yT - 1 - Tb) : Tb) * yrowb;
-        ylast_p = row + ycol_last; yblank_p = row + ycol_blank;
-        if (f64) { ylast = __ldg((const double*)ylast_p); yblank = __ldg((const double*)yblank_p); }
-        else { ylast = (double)__ldg((const float*)ylast_p); yblank = (double)__ldg((const float*)yblank_p); }
+        row = I.ybase + (long)(I.yrc ? (I.yT - 1 - Tb) : Tb) * I.yrowb;
+        load_y(I, row, ylast, yblank);
       }
       __syncthreads();
       PCLK(3);
-      const double2* pub_rd = pub + (size_t)pa * 2 + r;
+      const double2* pub_rd = pub + (size_t)I.pa * 2 + r;
       double2* pub_wr = pub + (size_t)(a < EMAX ? a : 0) * 2 + r;
       const int pstride = EMAX * 2;
       double fz_next = ninf();
-      if (inB && pstat == PS_FROZEN) fz_next = frozen_at(pwb, Tb, wmask, plo, phi, same);
+      if (inB && I.pstat == PS_FROZEN) fz_next = frozen_at(I.pwb, Tb, I.wmask, I.plo, I.phi, I.same);
       for (int it = 0; it < iters; ++it) {
         const int t = Tb + it;
         const bool go = inB && t < te;
         if (go) {
           double pv;
           bool pchanged = false;
-          if (pstat == PS_INE) {
+          if (I.pstat == PS_INE) {
             const double2 pb = pub_rd[(it & 1) * pstride];
-            pv = (MODEL == POB_MODEL_CTC_MERGE_REPEATS && same) ? pb.y : pb.x;
-            pchanged = pchg[(it & 1) * pstride + pa * 2 + r] != 0;
-          } else if (pstat == PS_FROZEN) {
+            pv = (MODEL == POB_MODEL_CTC_MERGE_REPEATS && I.same) ? pb.y : pb.x;
+            pchanged = pchg[(it & 1) * pstride + I.pa * 2 + r] != 0;
+          } else if (I.pstat == PS_FROZEN) {
             pv = fz_next;
-            if (t + 1 < te) fz_next = frozen_at(pwb, t + 1, wmask, plo, phi, same);
-          } else if (pstat == PS_ROOT) pv = root_prob(r, t - 1);
+            if (t + 1 < te) fz_next = frozen_at(I.pwb, t + 1, I.wmask, I.plo, I.phi, I.same);
+          } else if (I.pstat == PS_ROOT) pv = root_prob(r, t - 1);
           else pv = ninf();
           const double yl = ylast, yb = yblank;
-          ylast_p += ystep; yblank_p += ystep;
-          if (t + 1 < te) {
-            if (f64) { ylast = __ldg((const double*)ylast_p); yblank = __ldg((const double*)yblank_p); }
-            else { ylast = (double)__ldg((const float*)ylast_p); yblank = (double)__ldg((const float*)yblank_p); }
-          }
+          row += ystep;
+          if (t + 1 < te) load_y(I, row, ylast, yblank);
           const bool must = computing || t >= cs || pchanged;
           double2 pb;
           if (must) {
@@ -617,8 +685,8 @@ struct Engine {
               // first recomputed timestep of a node that was clean so far: fetch its own values at t-1
               computing = true;
               p_prev = ninf(); ng_prev = ninf();
-              if (t - 1 >= lo && t - 1 < hi) {
-                const Ent* se = wb + (t & wmask);
+              if (t - 1 >= I.lo && t - 1 < I.hi) {
+                const Ent* se = I.wb + (t & I.wmask);
                 p_prev = se->prob;
                 if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_prev = se->nogap;
               }
@@ -627,15 +695,15 @@ struct Engine {
                 cs = t;
                 maxv = ninf();
                 for (int q = ts; q < t; ++q) {
-                  if (q >= lo && q < hi) {
-                    const double v = (wb + ((q + 1) & wmask))->prob;
+                  if (q >= I.lo && q < I.hi) {
+                    const double v = (I.wb + ((q + 1) & I.wmask))->prob;
                     if (v > maxv) maxv = v;
                   }
                 }
               }
             }
             double prob;
-            Ent* o = wb + ((t + 1) & wmask);
+            Ent* o = I.wb + ((t + 1) & I.wmask);
             if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
               const double gp = p_prev + yb;
               const double ng = lae(pv + yl, ng_prev + yl);
@@ -655,8 +723,8 @@ struct Engine {
           } else {
             // still clean at t: hand the stored value to the children
             pb.x = ninf(); pb.y = ninf();
-            if (t >= lo && t < hi) {
-              const Ent* se = wb + ((t + 1) & wmask);
+            if (t >= I.lo && t < I.hi) {
+              const Ent* se = I.wb + ((t + 1) & I.wmask);
               pb.x = se->prob;
               if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pb.y = se->gap;
             }
@@ -671,6 +739,7 @@ struct Engine {
     if (on) {
       if (te > ts) {
         // window bookkeeping: after this sweep every entry of [ts, te) is current
+        int lo = I.lo, hi = I.hi;
         if (ts > hi || ts < lo) { lo = ts; hi = te; }
         else hi = max(hi, te);
         if (hi - lo > g_es.cap[r]) lo = hi - g_es.cap[r];
@@ -693,9 +762,9 @@ struct Engine {
     const double other = __shfl_xor_sync(0xffffffffu, maxv, 1);
     if (used) {
       if (mode == MODE_ROWCOL) {
-        if (r == 0) key[a] = make_key(no_nan(maxv + other), (double)a_order[a]);
+        if (r == 0) set_key(a, no_nan(maxv + other));
       } else if (r == 1) {
-        key[a] = make_key(no_nan(a_last0[a] + maxv), (double)a_order[a]);
+        set_key(a, no_nan(a_last0[a] + maxv));
       }
     }
     pre_prune();
@@ -703,16 +772,77 @@ struct Engine {
     PCLK(5);
   }
 
+
   // scalars of the coming prune / sweep, reset by thread 0 BEFORE the barrier that precedes prune()
   __device__ __forceinline__ void pre_prune() {
     POB_VIEWS
     if (threadIdx.x == 0) {
       sh[SH_NB] = min(sh[SH_NUSED], W); sh[SH_DMIN] = 0x7fffffff;
+      sh[SH_NL0] = 0; sh[SH_NL1] = 0;
+      sh[SH_PCNT] = 0; sh[SH_PM0] = 0; sh[SH_PM1] = 0; sh[SH_PM2] = 0; sh[SH_PM3] = 0;
     }
   }
 
+  // Ranking key of an active slot: the exact pair (order-preserving integer image of the FP64 score, creation order)
+  // and a 31-bit fixed-point image of the score relative to the top score of the previous prune (2^-23 nats per unit,
+  // +-127 nats, saturating).  The map score -> k32 is monotone (not strict), so ranks computed on k32 are exact
+  // whenever they come out distinct; prune() checks that and falls back to the exact keys otherwise.
+  __device__ __forceinline__ void set_key(int a, double score) {
+    POB_VIEWS
+    key[a] = make_key(score, (double)a_order[a]);
+    const double sref = *reinterpret_cast<const double*>(sh + SH_SREF);
+    double d = score - sref;
+    d = fmin(fmax(d, -127.0), 127.0);
+    k32[a] = (unsigned)__double2int_rn((d + 128.0) * 8388608.0);
+  }
+  __device__ __forceinline__ void clear_key(int a) {
+    POB_VIEWS
+    key[a] = make_key(ninf(), 4.5e9);
+    k32[a] = 0;
+  }
+
+  // exact ranking on the 64-bit keys, ties by creation order: only when the fast pass saw equal 31-bit keys inside
+  // the beam (two scores within 2^-23, more than 127 nats from the reference, or fewer finite candidates than W)
+  __device__ __noinline__ void prune_exact() {
+    POB_VIEWS
+    const int tid = threadIdx.x;
+    const bool two = (int)blockDim.x >= 2 * EMAX;
+    const int a = two ? (tid >> 1) : tid;
+    const int half = two ? (tid & 1) : 0;
+    const bool cand = a < EMAX && a_slot[a] >= 0;
+    const int mid = two ? (EMAX >> 1) : EMAX;
+    const int j0 = half ? mid : 0, j1 = half ? EMAX : mid;
+    int rank = 0;
+    if (tid == 0) sh[SH_DMIN] = 0x7fffffff;
+    if (cand) {
+      const unsigned long long ks = (unsigned long long)__double_as_longlong(key[a].x);
+      const double ko = key[a].y;
+      for (int j = j0; j < j1; ++j) {
+        const double2 kj = key[j];
+        const unsigned long long s = (unsigned long long)__double_as_longlong(kj.x);
+        rank += (s > ks) || (s == ks && kj.y < ko);
+      }
+    }
+    if (two) rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+    __syncthreads();
+    if (a < EMAX && half == 0) {
+      const bool inb = cand && rank < W;
+      a_inbeam[a] = inb;
+      if (inb) {
+        beam[rank] = a;
+        atomicMin(&sh[SH_DMIN], a_depth[a]);
+        if (rank == 0) {
+          const double sc = skey_inv((unsigned long long)__double_as_longlong(key[a].x));
+          if (sc > -1e300) *reinterpret_cast<double*>(sh + SH_SREF) = sc;
+        }
+      }
+    }
+    if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&g_exact_prunes), 1ULL);
+    __syncthreads();
+  }
+
   // ---- Beam::prune (Beam.h:93-108): rank by score desc, exact ties by creation order ----------
-  // one barrier at the end; also clears the per-step flags
+  // one barrier at the end (three more when the exact pass is needed); also clears the per-step flags
   __device__ __noinline__ void prune() {
     POB_VIEWS
     const int tid = threadIdx.x;
@@ -725,73 +855,64 @@ struct Engine {
     // this call (they must not be reset earlier: a sweep without a synchronised phase has no barrier between its
     // readers and its end), and the next sweep's atomicMin comes after the barriers of the expansion
     if (tid == 0) { sh[SH_TB0] = 0x7fffffff; sh[SH_TB1] = 0x7fffffff; }
-    const int mid = two ? (EMAX >> 1) : EMAX;
-    const int j0 = half ? mid : 0, j1 = half ? EMAX : mid;
-    const unsigned long long* const k64 = reinterpret_cast<const unsigned long long*>(key);  // [2a] score key, [2a+1] order
-    const unsigned* const k32 = reinterpret_cast<const unsigned*>(key);  // [4a+1] high word of the score key
-    unsigned long long ks = 0;
-    int eq = 0;
+    // all-pairs rank on the 31-bit keys, four per shared-memory load; two threads share a candidate's key range
+    const int nq = E4 >> 2;
+    const int qmid = two ? ((nq + 1) >> 1) : nq;
+    const int q0 = half ? qmid : 0, q1 = half ? nq : qmid;
     if (cand) {
-      // fast pass on the high words only (sign, exponent, 20 mantissa bits: monotone, not strict): a candidate whose
-      // high word is unique has its exact rank; one that is out of the beam by high words is out of the beam
-      const unsigned kh = k32[4 * a + 1];
-#pragma unroll 8
-      for (int j = j0; j < j1; ++j) {
-        const unsigned kj = k32[4 * j + 1];
-        rank += kj > kh;
-        eq += kj == kh;
+      const unsigned kh = k32[a];
+      const uint4* const kv = reinterpret_cast<const uint4*>(k32);
+      unsigned r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+#pragma unroll 4
+      for (int q = q0; q < q1; ++q) {
+        const uint4 v = kv[q];
+        // keys are < 2^31: kh - kj has its top bit set exactly when kj > kh; mad.hi(d, 2, r) = r + (d >> 31) is one
+        // instruction on the FMA pipe next to the subtraction on the ALU pipe
+        r0 = sign_acc(kh - v.x, r0); r1 = sign_acc(kh - v.y, r1);
+        r2 = sign_acc(kh - v.z, r2); r3 = sign_acc(kh - v.w, r3);
       }
+      rank = (int)(r0 + r1 + r2 + r3);
     }
-    if (two) { rank += __shfl_xor_sync(0xffffffffu, rank, 1); eq += __shfl_xor_sync(0xffffffffu, eq, 1); }
-    // some candidate of this warp that could be in the beam shares its high word (scores within 2^-20 relative, or
-    // equal): the whole warp repeats the pass on the full 64-bit keys (the shuffles must stay convergent)
-    if (__any_sync(0xffffffffu, cand && rank < W && eq > 1)) {
-      rank = 0; eq = 0;
-      if (cand) {
-        ks = k64[2 * a];
-#pragma unroll 8
-        for (int j = j0; j < j1; ++j) {
-          const unsigned long long kj = k64[2 * j];
-          rank += kj > ks;
-          eq += kj == ks;
-        }
-      }
-      if (two) { rank += __shfl_xor_sync(0xffffffffu, rank, 1); eq += __shfl_xor_sync(0xffffffffu, eq, 1); }
-    } else {
-      eq = 1;  // no exact tie can matter
-    }
-    // a candidate that could be in the beam and shares its score with another one: rank the tie by creation order
-    // (rare; the whole warp takes the exact pass so that the shuffles stay convergent)
-    if (__any_sync(0xffffffffu, cand && rank < W && eq > 1)) {
-      int tie = 0;
-      if (cand) {
-        const double ko = key[a].y;
-        for (int j = j0; j < j1; ++j) {
-          const double2 kj = key[j];
-          tie += ((unsigned long long)__double_as_longlong(kj.x) == ks) && kj.y < ko;
-        }
-      }
-      if (two) tie += __shfl_xor_sync(0xffffffffu, tie, 1);
-      rank += tie;
-    }
-    // no barrier here: the ranking loop only reads key[], the block below only writes other arrays, and the scalars
+    if (two) rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+    // no barrier here: the ranking loop only reads k32[], the block below only writes other arrays, and the scalars
     // it updates were reset by pre_prune() before the barrier that precedes this call
     int dmin_mine = 0x7fffffff;
+    bool inb = false;
     if (a < EMAX && half == 0) {
       a_needed[a] = 0;
-      const bool inb = cand && rank < W;
+      inb = cand && rank < W;
       a_inbeam[a] = inb;
       if (inb) {
         beam[rank] = a;
         dmin_mine = a_depth[a];
+        if (rank == 0) {
+          const double sc = skey_inv((unsigned long long)__double_as_longlong(key[a].x));
+          if (sc > -1e300) *reinterpret_cast<double*>(sh + SH_SREF) = sc;
+        }
       }
+    }
+    // the ranks inside the beam must be distinct: collect them as bit masks (and their count) per warp
+    {
+      const unsigned nin = __popc(__ballot_sync(0xffffffffu, inb));
+      const int nw = (W + 31) >> 5;
+      for (int w = 0; w < nw; ++w) {
+        const unsigned m = __reduce_or_sync(0xffffffffu, (inb && (rank >> 5) == w) ? (1u << (rank & 31)) : 0u);
+        if ((tid & 31) == 0 && m) atomicOr(reinterpret_cast<unsigned*>(&sh[SH_PM0 + w]), m);
+      }
+      if ((tid & 31) == 0 && nin) atomicAdd(&sh[SH_PCNT], (int)nin);
     }
     // minimum depth of the new beam: one shared-memory atomic per warp instead of one per beam node
     dmin_mine = __reduce_min_sync(0xffffffffu, dmin_mine);
     if ((tid & 31) == 0 && dmin_mine != 0x7fffffff) atomicMin(&sh[SH_DMIN], dmin_mine);
     __syncthreads();
+    {
+      const int cnt = sh[SH_PCNT];
+      const int bits = __popc(sh[SH_PM0]) + __popc(sh[SH_PM1]) + __popc(sh[SH_PM2]) + __popc(sh[SH_PM3]);
+      if (cnt != sh[SH_NB] || bits != cnt) prune_exact();
+    }
     PCLK(6);
   }
+
 
   // ---- retire an active slot: write the header home, queue the node for reclamation ----
   __device__ void retire(int a) {
@@ -808,7 +929,7 @@ struct Engine {
     retq[pos % RQ] = make_int2(slot, stamp);
     slot2e[slot] = -1;
     a_slot[a] = -1;
-    key[a] = make_key(ninf(), 4.5e9);
+    clear_key(a);
     a_free[atomicAdd(&sh[SH_AFREE], 1)] = a;
     atomicSub(&sh[SH_NUSED], 1);
   }
@@ -830,7 +951,7 @@ struct Engine {
     a_che[2 * a] = a_che[2 * a + 1] = -1;
     a_last[a] = (uint8_t)last; a_pstat[a] = PS_INE; a_same[a] = (a_last[pa] == last);
     a_inbeam[a] = 0; a_needed[a] = 1;
-    key[a] = make_key(ninf(), 4.5e9);
+    clear_key(a);
     slot2e[slot] = (int16_t)a;
   }
 
@@ -854,7 +975,7 @@ struct Engine {
     a_che[2 * a] = a_che[2 * a + 1] = -1;  // retained entries are stale with respect to the live parent
     a_last[a] = (uint8_t)h.last; a_pstat[a] = PS_INE; a_same[a] = (a_last[pa] == h.last);
     a_inbeam[a] = 0; a_needed[a] = 1;
-    key[a] = make_key(ninf(), 4.5e9);
+    clear_key(a);
     slot2e[slot] = (int16_t)a;
   }
 
@@ -1085,11 +1206,12 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     slot2e[s] = -1;
   }
   for (int a = tid; a < EMAX; a += NT) {
-    a_slot[a] = -1; a_free[a] = EMAX - 1 - a; key[a] = make_key(ninf(), 4.5e9);
+    a_slot[a] = -1; a_free[a] = EMAX - 1 - a; clear_key(a);
     a_inbeam[a] = 0; a_needed[a] = 0;
   }
+  for (int i = EMAX + tid; i < E4; i += NT) k32[i] = 0;  // padding of the last key quad
   if (tid == 0) {
-    for (int k = 0; k < 32; ++k) sh[k] = 0;
+    for (int k = 0; k < SH_COUNT; ++k) sh[k] = 0;
     sh[SH_FQH] = 0; sh[SH_FQT] = NP; sh[SH_AFREE] = EMAX; sh[SH_ORDER] = 1; sh[SH_TID] = 1;
     sh[SH_DMIN] = 0x7fffffff; sh[SH_FIRSTALIVE] = 0x7fffffff;
     sh[SH_TB0] = 0x7fffffff; sh[SH_TB1] = 0x7fffffff;
@@ -1134,7 +1256,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
   __syncthreads();
   {
     const double p = update_all(tid < nbase, tid, 0, 0);
-    if (mode == MODE_1D && tid < nbase) key[tid] = make_key(no_nan(p), (double)a_order[tid]);
+    if (mode == MODE_1D && tid < nbase) set_key(tid, no_nan(p));
     if (mode != MODE_1D) update_all(tid < nbase, tid, 1, 0);
   }
 
@@ -1167,7 +1289,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
       const double p = update_all(mine, tid, 0, t);
       if (mine) {
         n_updates++;
-        key[tid] = make_key(no_nan(p), (double)a_order[tid]);  // last_probability(): value at the last t
+        set_key(tid, no_nan(p));  // last_probability(): value at the last t
       }
       pre_prune();
       __syncthreads();
@@ -1202,8 +1324,8 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     // The band of row u / column v is read by every thread at the top of every step.  Thread 0 copies the entries
     // of the next row and the next column into shared memory with cp.async while the current step runs (two slots
     // each, indexed by parity), so that the next step starts from shared memory instead of a global load.
-    int* const senv = sh + 24;   // [2][2] band of row u  (slot u & 1)
-    int* const senvt = sh + 28;  // [2][2] band of column v (slot v & 1)
+    int* const senv = sh + SH_ENV;    // [2][2] band of row u  (slot u & 1)
+    int* const senvt = sh + SH_ENVT;  // [2][2] band of column v (slot v & 1)
     if (tid == 0) { senv[0] = env[0]; senv[1] = env[1]; senvt[0] = envt[0]; senvt[1] = envt[1]; }
     __syncthreads();
     // the staging and prefetching below is done by the last threads of the block: they own no (node, read) item, so
@@ -1336,6 +1458,14 @@ __global__ void backtrace_kernel(const uint32_t* __restrict__ trace, const int64
 
 }  // namespace
 // debug export (not part of the ABI): cycles per engine phase, only in builds with -DPOB_PHASE_CLOCKS
+extern "C" int pob_debug_exact_prunes(unsigned long long* out, int reset) {
+  POB_CUDA(cudaMemcpyFromSymbol(out, g_exact_prunes, sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z = 0;
+    POB_CUDA(cudaMemcpyToSymbol(g_exact_prunes, &z, sizeof(z)));
+  }
+  return POB_OK;
+}
 extern "C" int pob_debug_phase_clocks(unsigned long long* out32, int reset) {
 #ifdef POB_PHASE_CLOCKS
   POB_CUDA(cudaMemcpyFromSymbol(out32, g_phase_clk, 32 * sizeof(unsigned long long)));
@@ -1366,7 +1496,8 @@ size_t ws_bytes(int model, int NP, int CAP0, int CAP1, int RQ, int Umax, int Vma
 
 size_t smem_bytes(int W, int NP, int EMAX) {
   // must match POB_VIEWS
-  size_t b = 224 * (size_t)EMAX + 4 * ((W + 3) & ~3) + 4 * 32 + 2 * (size_t)NP + 5 * ((EMAX + 15) & ~15);
+  size_t b = 224 * (size_t)EMAX + 4 * ((W + 3) & ~3) + 4 * SH_COUNT + 2 * (size_t)NP + 5 * ((EMAX + 15) & ~15);
+  b += 4 * (size_t)((EMAX + 3) & ~3) + 16 * (size_t)EMAX + 4 * (size_t)EMAX;  // k32, resmax, lst
   return pob_align_up(b, 16);
 }
 
@@ -1500,6 +1631,10 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   P.work_counter = counter;
   P.counters = ctx->d_counters;
   P.trace = trace; P.trace_off = trace_off; P.out_top = top; P.out_score = out_score;
+  if (getenv("POB_DEBUG_VERBOSE"))
+    fprintf(stderr, "[pob] beam launch: items %d W %d mode %d NP %d CAP %d/%d span %d/%d threads %d grid %d (%d/SM) smem %zu mirror %d ws/CTA %.1f MB\n",
+            n_items, W, mode, P.NP, P.CAP0, P.CAP1, max_span0, max_span1, threads, grid, per_sm, smem, P.mir_off >= 0,
+            stride / 1048576.0);
   if (n_items > 0) {
     pob_prof_scope ps(ctx, mode == MODE_1D ? POB_K_BEAM_1D : POB_K_BEAM_2D);
     kern<<<grid, threads, smem, ctx->stream>>>(P);

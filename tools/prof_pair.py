@@ -30,5 +30,11 @@ for c in range(calls):
     ctx.sync()
     p = ctx.profile_get()
     print("call", c, {k: round(v["ms"], 3) for k, v in p.items()}, ctx.counters())
+try:
+    ex = C.c_ulonglong(0)
+    L.pob_debug_exact_prunes(C.byref(ex), 0)
+    print("exact prune passes:", ex.value, "of", ctx.counters())
+except AttributeError:
+    pass
 st = ctx.from_device(o[8], (n,), np.int32)
 print("status bits:", np.bitwise_or.reduce(st), "pairs/s (beam only):", n / (p["beam_pair"]["ms"] / 1e3))
