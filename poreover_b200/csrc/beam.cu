@@ -258,8 +258,9 @@ extern __shared__ __align__(16) char pob_smem[];
   uint8_t* const a_needed = a_inbeam + eb_;                                                         \
   const int E4 = (EMAX + 3) & ~3;                                                                   \
   uint32_t* const k32 = (uint32_t*)(a_needed + eb_);                                                \
-  double* const resmax = (double*)(k32 + E4);                                                       \
-  int16_t* const lst = (int16_t*)(resmax + 2 * EMAX);                                               \
+  double* const resmax = (double*)key;   /* [2a + r] band maximum handed back by long_chains(): a slot's key is dead  \
+                                            from the expansion until set_key() at the end of the sweep */              \
+  int16_t* const lst = (int16_t*)tmpb;   /* [2][EMAX] work lists of long_chains() */                                  \
   NodeHdr* const hdr = g_es.hdr;                                                                    \
   int32_t* const freelist = g_es.freelist;                                                          \
   int2* const retq = g_es.retq;                                                                     \
@@ -1497,7 +1498,7 @@ size_t ws_bytes(int model, int NP, int CAP0, int CAP1, int RQ, int Umax, int Vma
 size_t smem_bytes(int W, int NP, int EMAX) {
   // must match POB_VIEWS
   size_t b = 224 * (size_t)EMAX + 4 * ((W + 3) & ~3) + 4 * SH_COUNT + 2 * (size_t)NP + 5 * ((EMAX + 15) & ~15);
-  b += 4 * (size_t)((EMAX + 3) & ~3) + 16 * (size_t)EMAX + 4 * (size_t)EMAX;  // k32, resmax, lst
+  b += 4 * (size_t)((EMAX + 3) & ~3);  // k32
   return pob_align_up(b, 16);
 }
 
@@ -1598,7 +1599,13 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
     int want_blocks = 2048 / threads;
     if (want_blocks > 12) want_blocks = 12;
     if (max_cta_sm > 0 && want_blocks > max_cta_sm) want_blocks = max_cta_sm;
-    int pct = (int)((want_blocks * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+    // the carve-out comes in steps (0, 8, 16, 32, 64, 100, 132, 164, 196, 228 KB): ask for the smallest one that
+    // holds the wanted blocks (1 KB per block is reserved by the system), as a percentage that maps back onto it
+    static const int steps_kb[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
+    const size_t need = (size_t)want_blocks * (smem + 1024);
+    int kb = 228;
+    for (int s : steps_kb) if ((size_t)s * 1024 >= need) { kb = s; break; }
+    int pct = kb * 100 / 228;
     if (pct > 100) pct = 100;
     POB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
   }
