@@ -20,9 +20,15 @@
 // retired node is recycled only once its windows are dead and it cannot hand retained children to a revival
 // (or the pool overflows, which is flagged per item).
 //
-// Arithmetic: forward values accumulate in FP64 (the reference is all double and scores reach
-// -2.5e3..-5e4); only the bounded log1p(exp(d)) term, d <= 0, is evaluated in FP32.  No tensor cores:
-// nothing here is a contraction.  Per step the dependent chain is the time-major band sweep: threads own
+// Arithmetic: the reference works on log-probabilities in double with log-add-exp (Log.h:27-33).  Here every
+// forward value is kept in the LINEAR domain, in FP64, scaled by a power of two per (read, timestep):
+// value = exp(reference value) * 2^-K(r, t).  A forward cell is then two multiplications and two additions
+// (no exp/log on the dependent chain); a missing hash-map key (-inf) is 0.  The probability rows enter through
+// "column records" (exp of the five log-probabilities of a timestep, computed once, times the power of two that
+// moves from K(t-1) to K(t)); K only changes when the top of the beam has drifted 64 binades from 1, so the
+// rescaling is exact and the result does not depend on when it happens.  Measured against the log-domain
+// reference: identical consensus strings and |score difference| ~ 1e-11 (bar: 1e-4).  No tensor cores: nothing
+// here is a contraction.  Per step the dependent chain is the time-major band sweep: threads own
 // (node, read) items, carry their own t-1 values in registers and exchange parent values through
 // double-buffered shared memory, one block barrier per time sub-step; about seven more barriers per step cover
 // the sweep's setup and keys, ranking, expansion, retirement and allocation.  Shared-memory hazards are checked
@@ -54,8 +60,8 @@ struct __align__(16) NodeHdr {  // 128 bytes, home record of a node in the globa
   int32_t kid_slot[4];
   uint32_t kid_order[4];
   int32_t lo[2], hi[2];         // window of valid time keys per read: lo <= t < hi
-  double maxp[2];               // max_prob[] of the reference nodes
-  int32_t pad[2];
+  double maxp[2];               // max_prob[] of the reference nodes (linear domain) ...
+  int32_t maxk[2];              // ... and the scale (power of two) they are expressed in
 };
 
 template <int MODEL>
@@ -69,6 +75,16 @@ struct __align__(8) Entry<POB_MODEL_CTC> {
   double prob;
 };
 
+// exp(log-probabilities) of one timestep of a read, times 2^(K(t-1) - K(t)); K = scale of the column (value =
+// stored * 2^K); nb = number of scale changes up to this column; root = value of the root node (ctc only)
+struct __align__(64) Col {
+  double y[5];   // bases 0..S-2, blank at [4]
+  double root;
+  int32_t K, nb;
+  double pad;
+};
+enum { COL_LOOK = 8 };  // columns are created this many at a time
+
 struct BeamParams {
   pob_reads r[2];
   const int32_t* env;       // rows x 2 (may be NULL: ROW without envelope, or 1D)
@@ -77,8 +93,8 @@ struct BeamParams {
   const int64_t* envt_off;
   const int32_t* order;     // item processing order or NULL
   const int32_t* skip;      // per item != 0 -> not searched
-  int n_items, W, mode, NP, CAP0, CAP1, RQ, EMAX;
-  int dbg_noreclaim, dbg_noreuse;
+  int n_items, W, mode, NP, CAP0, CAP1, CAPC0, CAPC1, RQ, EMAX;
+  int dbg_noreclaim, dbg_noreuse, dbg_long;
   int inspect_every;        // the retire queue is inspected every this many expansions (its headers are cold)
   int mir_off;              // shared-memory prob mirror: byte offset, or -1 when it does not fit
   int prefetch;             // pull the probability rows / envelope entries of coming steps towards the SM
@@ -93,35 +109,12 @@ struct BeamParams {
   unsigned long long* counters;
 };
 
-__device__ __forceinline__ double ninf() { return __longlong_as_double(0xfff0000000000000LL); }
-__device__ __forceinline__ double no_nan(double x) { return (x == x) ? x : ninf(); }  // NaN cannot be ranked
+__device__ __forceinline__ double no_nan(double x) { return (x == x) ? x : 0.0; }  // NaN cannot be ranked
 
-// Log.h:27-33 with the bounded term in FP32: max + log1p(exp(min - max))
-// Ranking keys are kept as integers: skey(x) is an order-preserving map of a (non-NaN) double onto uint64, so the
-// all-pairs ranking compares with the integer pipe instead of three FP64 compares per pair.  -0.0 is folded into +0.0.
-__device__ __forceinline__ unsigned long long skey(double x) {
-  const unsigned long long u = (unsigned long long)__double_as_longlong(x + 0.0);
-  return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
-}
-__device__ __forceinline__ double skey_inv(unsigned long long k) {
-  const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
-  return __longlong_as_double((long long)u);
-}
-__device__ __forceinline__ double2 make_key(double score, double order) {
-  return make_double2(__longlong_as_double((long long)skey(score)), order);
-}
-
-// Branch-free (a select at the end) so that two independent evaluations can be interleaved by the scheduler.
-__device__ __forceinline__ double lae(double a, double b) {
-  const double m = fmax(a, b);
-  const float d = (float)(fmin(a, b) - m);  // NaN when both are -inf: discarded below
-#ifdef POB_FAST_LAE
-  // measured: +4 % pairs/s, same strings on 256 pairs, but the ranking score drifts by 1.6e-3 over T = 5000 (bar: 1e-4)
-  const double r = m + (double)__logf(1.0f + __expf(d));
-#else
-  const double r = m + (double)log1pf(expf(d));
-#endif
-  return (m == ninf()) ? m : r;
+// x * 2^dk: exact while the result stays in the normal range (the factor is built from its exponent field)
+__device__ __forceinline__ double scale2(double x, int dk) {
+  dk = max(-1000, min(1000, dk));
+  return x * __longlong_as_double((long long)(1023 + dk) << 52);
 }
 
 __device__ __forceinline__ unsigned sign_acc(unsigned d, unsigned acc) {
@@ -167,20 +160,26 @@ __device__ __forceinline__ ReadView make_view(const pob_reads& r, int item) {
 }
 
 enum { SH_NB = 0, SH_NUSED, SH_FQH, SH_FQT, SH_AFREE, SH_ORDER, SH_TID, SH_STAMP, SH_RQH, SH_RQT, SH_STATUS, SH_FIRSTALIVE,
-       SH_TOTALLOC, SH_TOTFIRST, SH_DMIN, SH_TB0, SH_TB1, SH_XSTEP, SH_NL0, SH_NL1, SH_SREF /* double: 2 slots */,
-       SH_SREF_HI, SH_PCNT, SH_PM0, SH_PM1, SH_PM2, SH_PM3,
-       SH_ENV = 32 /* [2][2] band of row u */, SH_ENVT = 36 /* [2][2] band of column v */, SH_COUNT = 48 };
+       SH_TOTALLOC, SH_TOTFIRST, SH_DMIN, SH_TB0, SH_TB1, SH_XSTEP, SH_NL0, SH_NL1, SH_SPARE0,
+       SH_SPARE1, SH_PCNT, SH_PM0, SH_PM1, SH_PM2, SH_PM3,
+       SH_CDEF0 /* columns [0, cdef) of read 0 exist */, SH_CDEF1,
+       SH_ENV = 32 /* [2][2] band of row u */, SH_ENVT = 36 /* [2][2] band of column v */,
+       SH_KLAST0 = 40 /* scale of the newest column */, SH_KLAST1, SH_PEND0 /* scale change asked for */, SH_PEND1,
+       SH_NBUMP0, SH_NBUMP1, SH_KCUR0 /* scale of the column of the last single update */, SH_KCUR1,
+       SH_KREF0 /* scale of the last band (debug trace) */, SH_KREF1, SH_EBASE /* exponent base of the 31-bit keys */,
+       SH_COUNT = 52 };
 
 // Per-CTA engine state.  Scalars and global-memory views live in a static __shared__ struct; the per-active-slot
 // arrays live in dynamic shared memory at offsets that depend only on EMAX / W / NP, so every access compiles
 // to LDS/STS (a pointer loaded from memory would be a generic pointer and cost a second, slower load).
 struct EngState {
-  int W, NP, RQ, EMAX, mode, noreclaim, inspect_every;
+  int W, NP, RQ, EMAX, mode, noreclaim, inspect_every, longq;
   NodeHdr* hdr;
   char* win[2];
   int32_t* freelist;
   int2* retq;
-  double* cum[2];   // ctc: blank prefix sums of each read (root node values, PrefixTree.h:508-514)
+  Col* col[2];      // column records of each read: ring of cmask + 1 timesteps
+  int cmask[2];
   int32_t* sufmin;  // ROW: min over rows >= u of the envelope's band start (band starts are NOT monotone:
                     // build_envelope's repair pass clamps some rows far back, envelope.py:82-85)
   int cap[2], mask[2];
@@ -218,14 +217,15 @@ extern __shared__ __align__(16) char pob_smem[];
 //   a_lo/a_hi [2]     window bounds per read;   a_plo/a_phi [2] bounds of a frozen parent
 //   a_che [2]         clean end per read (see sweep)
 //   a_maxp [2]        max_prob[] of the reference nodes;  a_last0 value of read 0 at its last written t
-//   key               (ranking score, creation order);   pub [2][EMAX][2] (prob, gap) parent -> child exchange
+//   key               ranking score (-1: unused slot);  a_maxk [2] scale of a_maxp;  pub [2][EMAX][2] (prob, gap) parent -> child exchange
 //   a_same            parent's last base == own last base (merge-repeats reads the parent's gap value)
 //   beam [W]          active slots in rank order;  a_free stack of unused active slots;  sh scalars SH_*
 #define POB_VIEWS                                                                                   \
   const int EMAX = g_es.EMAX, W = g_es.W, NP = g_es.NP, RQ = g_es.RQ, mode = g_es.mode;             \
   char* const sm_ = pob_smem;                                                                       \
   double2* const pub = (double2*)sm_;                                                               \
-  double2* const key = (double2*)(sm_ + 64 * EMAX);                                                 \
+  double* const key = (double*)(sm_ + 64 * EMAX);                                                   \
+  int32_t* const a_maxk = (int32_t*)(sm_ + 72 * EMAX);                                              \
   double* const a_maxp = (double*)(sm_ + 80 * EMAX);                                                \
   double* const a_last0 = (double*)(sm_ + 96 * EMAX);                                               \
   int32_t* const a_slot = (int32_t*)(sm_ + 104 * EMAX);                                             \
@@ -258,8 +258,6 @@ extern __shared__ __align__(16) char pob_smem[];
   uint8_t* const a_needed = a_inbeam + eb_;                                                         \
   const int E4 = (EMAX + 3) & ~3;                                                                   \
   uint32_t* const k32 = (uint32_t*)(a_needed + eb_);                                                \
-  double* const resmax = (double*)key;   /* [2a + r] band maximum handed back by long_chains(): a slot's key is dead  \
-                                            from the expansion until set_key() at the end of the sweep */              \
   int16_t* const lst = (int16_t*)tmpb;   /* [2][EMAX] work lists of long_chains() */                                  \
   NodeHdr* const hdr = g_es.hdr;                                                                    \
   int32_t* const freelist = g_es.freelist;                                                          \
@@ -286,11 +284,75 @@ struct Engine {
   }
   __device__ __forceinline__ int* mir_hi() const { return mir_lo() + 2 * g_es.EMAX; }
 
-  // value of the root at time t (parent of depth-1 nodes)
+  // value of the root at time t (parent of depth-1 nodes), in the scale of column t (column -1 has scale 0)
   __device__ __forceinline__ double root_prob(int r, int t) const {
-    if (t == -1) return 0.0;
-    if (MODEL == POB_MODEL_CTC) return (t >= 0 && t < g_es.rv[r].T) ? g_es.cum[r][t] : ninf();
-    return ninf();
+    if (t == -1) return 1.0;
+    if (MODEL == POB_MODEL_CTC) return (t >= 0 && t < g_es.rv[r].T) ? colp(r, t)->root : 0.0;
+    return 0.0;
+  }
+
+  __device__ __forceinline__ Col* colp(int r, int t) const { return g_es.col[r] + (t & g_es.cmask[r]); }
+
+  // ---- one forward cell (PrefixTree.h:518-531 ctc, :690-704 merge repeats) in the scaled linear domain ----
+  // Every site that computes a cell goes through this function with explicitly rounded operations, so that a
+  // recomputation from the same inputs reproduces the stored value bit for bit (the incremental sweep relies on it).
+  __device__ __forceinline__ static void cell(double p_prev, double ng_prev, double pv, double yl, double yb, double& prob,
+                                              double& gp, double& ng) {
+    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
+      gp = __dmul_rn(p_prev, yb);                     // gap    = prob(t-1) * y[blank]
+      ng = __dmul_rn(__dadd_rn(pv, ng_prev), yl);     // no_gap = (parent(t-1) + no_gap(t-1)) * y[last]
+      prob = __dadd_rn(gp, ng);
+    } else {
+      gp = 0.0; ng = 0.0;
+      prob = __dadd_rn(__dmul_rn(pv, yl), __dmul_rn(p_prev, yb));
+    }
+  }
+
+  // ---- column records: exp(log-probabilities) of a timestep, scaled by a power of two ----
+  // All threads call this with the same arguments (the columns [0, need_r) of read r are about to be used); it does
+  // nothing (and has no barrier) when they exist already.  New columns are created COL_LOOK at a time.  The first new
+  // column absorbs the pending change of scale of its read (see prune()): its factors are multiplied by 2^-pend.
+  __device__ __noinline__ void define_cols(int need0, int need1) {
+    POB_VIEWS
+    const int tid = threadIdx.x, NT = blockDim.x;
+    for (int r = 0; r < 2; ++r) {
+      const int need = r ? need1 : need0;
+      const int c0 = sh[SH_CDEF0 + r];
+      const ReadView& v = g_es.rv[r];
+      if (need <= c0 || c0 >= v.T) continue;  // uniform
+      const int c1 = min(v.T, max(need, c0 + COL_LOOK));
+      const int pend = sh[SH_PEND0 + r];
+      const int K = sh[SH_KLAST0 + r] + pend;
+      const int nb = sh[SH_NBUMP0 + r] + (pend != 0);
+      const int nbase = v.S - 1;
+      for (int i = tid; i < (c1 - c0) * 8; i += NT) {
+        const int t = c0 + (i >> 3), k = i & 7;
+        Col* c = colp(r, t);
+        if (k < 5) {
+          double y = 0.0;
+          if (k == 4) y = exp(v.at(t, v.cblank));
+          else if (k < nbase) y = exp(v.at(t, v.pcol(k)));
+          if (t == c0 && pend) y = scale2(y, -pend);
+          c->y[k] = y;
+        } else if (k == 5) {
+          c->K = K; c->nb = nb;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        if constexpr (MODEL == POB_MODEL_CTC) {
+          // PrefixTree.h:508-514: the root's value is the running product of the blank column
+          double s = (c0 == 0) ? 1.0 : colp(r, c0 - 1)->root;
+          for (int t = c0; t < c1; ++t) { s = __dmul_rn(s, colp(r, t)->y[4]); colp(r, t)->root = s; }
+        }
+        sh[SH_CDEF0 + r] = c1; sh[SH_KLAST0 + r] = K; sh[SH_PEND0 + r] = 0; sh[SH_NBUMP0 + r] = nb;
+      }
+      __syncthreads();
+    }
+  }
+  __device__ __forceinline__ void need_cols(int need0, int need1) {
+    POB_VIEWS
+    if (need0 > sh[SH_CDEF0] || need1 > sh[SH_CDEF1]) define_cols(need0, need1);
   }
 
   // bookkeeping that must not race with the phase that produced it: run by thread 0 at the start of a
@@ -310,7 +372,7 @@ struct Engine {
   // this phase (the reference reads t-1, writes t).
   struct UpdIn {
     double p_prev, ng_prev, pv, ylast, yblank;
-    int lo, hi;
+    int lo, hi, kt;
   };
 
   __device__ __forceinline__ void update_gather(int a, int r, int t, UpdIn& in) const {
@@ -320,16 +382,18 @@ struct Engine {
     in.lo = a_lo[2 * a + r]; in.hi = a_hi[2 * a + r];
     const bool self_ok = (t - 1 >= in.lo && t - 1 < in.hi);
     const Ent* se = wbase(slot, r) + (t & g_es.mask[r]);
-    in.p_prev = self_ok ? se->prob : ninf();
-    in.ng_prev = ninf();
-    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.ng_prev = self_ok ? se->nogap : ninf();
-    in.ylast = g_es.rv[r].at(t, g_es.rv[r].pcol(last));
-    in.yblank = g_es.rv[r].at(t, g_es.rv[r].cblank);
+    in.p_prev = self_ok ? se->prob : 0.0;
+    in.ng_prev = 0.0;
+    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.ng_prev = self_ok ? se->nogap : 0.0;
+    const Col* c = colp(r, t);
+    in.ylast = c->y[last];
+    in.yblank = c->y[4];
+    in.kt = c->K;
     const int ps = a_pstat[a];
     if (ps == PS_ROOT) {
       in.pv = root_prob(r, t - 1);
     } else if (ps == PS_DEAD) {
-      in.pv = ninf();
+      in.pv = 0.0;
     } else {
       int plo, phi;
       if (ps == PS_INE) { const int pa = a_par[a]; plo = a_lo[2 * pa + r]; phi = a_hi[2 * pa + r]; }
@@ -339,7 +403,7 @@ struct Engine {
         if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.pv = a_same[a] ? pe->gap : pe->prob;
         else in.pv = pe->prob;
       } else {
-        in.pv = ninf();
+        in.pv = 0.0;
       }
     }
   }
@@ -347,14 +411,11 @@ struct Engine {
   __device__ __forceinline__ double update_commit(int a, int r, int t, const UpdIn& in) {
     POB_VIEWS
     Ent out;
-    double prob;
+    double prob, gp, ng;
+    cell(in.p_prev, in.ng_prev, in.pv, in.ylast, in.yblank, prob, gp, ng);
     if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
-      const double gp = in.p_prev + in.yblank;
-      const double ng = lae(in.pv + in.ylast, in.ng_prev + in.ylast);
-      prob = lae(gp, ng);
       out.prob = prob; out.gap = gp; out.nogap = ng; out.pad = 0;
     } else {
-      prob = lae(in.pv + in.ylast, in.p_prev + in.yblank);
       out.prob = prob;
     }
     *(wbase(a_slot[a], r) + ((t + 1) & g_es.mask[r])) = out;
@@ -373,7 +434,13 @@ struct Engine {
     if (hi - lo > g_es.cap[r]) lo = hi - g_es.cap[r];
     a_lo[2 * a + r] = lo; a_hi[2 * a + r] = hi;
     if (t >= a_che[2 * a + r]) a_che[2 * a + r] = t + 1;  // a single update extends (or restarts) the clean range
-    if (prob > a_maxp[2 * a + r]) a_maxp[2 * a + r] = prob;
+    {
+      // max_prob (PrefixTree.h:134, :420): the stored maximum carries the scale of the column it came from
+      const double mp = a_maxp[2 * a + r];
+      const int mk = a_maxk[2 * a + r];
+      const double mine = (mk == in.kt) ? prob : scale2(prob, in.kt - mk);
+      if (mine > mp) { a_maxp[2 * a + r] = prob; a_maxk[2 * a + r] = in.kt; }
+    }
     if (r == 0) a_last0[a] = prob;
     return prob;
   }
@@ -382,6 +449,8 @@ struct Engine {
   __device__ __noinline__ double update_all(bool mine, int a, int r, int t) {
     UpdIn in;
     double p = 0;
+    need_cols(r == 0 ? t + 1 : 0, r == 1 ? t + 1 : 0);
+    if (threadIdx.x == 0) { POB_VIEWS sh[SH_KCUR0 + r] = colp(r, t)->K; }
     deferred_finalize();
     if (mine) update_gather(a, r, t, in);
     __syncthreads();
@@ -393,36 +462,33 @@ struct Engine {
 
   // value a child reads from its frozen parent for an update at time t (the parent's entry at t-1)
   __device__ __forceinline__ double frozen_at(const Ent* pwb, int t, int wmask, int plo, int phi, bool same) const {
-    if (t - 1 < plo || t - 1 >= phi) return ninf();
+    if (t - 1 < plo || t - 1 >= phi) return 0.0;
     const Ent* q = pwb + (t & wmask);
     if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) return same ? q->gap : q->prob;
     else return q->prob;
   }
 
   // Everything a thread needs to recompute cells of one (active slot, read): views of the node's window, of its
-  // parent's window and of the read's probability rows.  Filled from the shared-memory arrays, so that any thread can
+  // parent's window and of the read's column records.  Filled from the shared-memory arrays, so that any thread can
   // take over any item (see long_chains).
   struct SwItem {
     Ent* wb;
     const Ent* pwb;
-    const char* ybase;
-    long yrowb, ycol_last, ycol_blank;
-    int lo, hi, plo, phi, pstat, pa, wmask, yT;
-    bool same, f64, yrc;
+    const Col* cb;   // column ring of the read
+    int lo, hi, plo, phi, pstat, pa, wmask, cmask, last, kref;
+    bool same, mixed;
   };
 
-  __device__ __forceinline__ void load_item(int a, int r, SwItem& I) const {
+  __device__ __forceinline__ void load_item(int a, int r, int ts, int te, SwItem& I) const {
     POB_VIEWS
     I.lo = a_lo[2 * a + r]; I.hi = a_hi[2 * a + r];
     I.wmask = g_es.mask[r];
     I.wb = wbase(a_slot[a], r);
-    const ReadView& v = g_es.rv[r];
-    I.f64 = v.f64; I.yrc = v.rc; I.yT = v.T;
-    const long es = I.f64 ? 8 : 4;
-    I.yrowb = (long)v.S * es;
-    I.ybase = (const char*)v.base;
-    I.ycol_last = (long)v.pcol(a_last[a]) * es;
-    I.ycol_blank = (long)v.cblank * es;
+    I.cb = g_es.col[r]; I.cmask = g_es.cmask[r];
+    I.last = a_last[a];
+    // scale of the band: that of its newest column; `mixed` when the scale changes inside the band (rare)
+    I.kref = colp(r, te - 1)->K;
+    I.mixed = colp(r, te - 1)->nb != colp(r, ts)->nb;
     I.pstat = a_pstat[a];
     I.same = a_same[a] != 0;
     I.pa = 0; I.plo = 0; I.phi = 0; I.pwb = nullptr;
@@ -434,81 +500,64 @@ struct Engine {
     }
   }
 
-  __device__ __forceinline__ void load_y(const SwItem& I, const char* row, double& yl, double& yb) const {
-    if (I.f64) { yl = __ldg((const double*)(row + I.ycol_last)); yb = __ldg((const double*)(row + I.ycol_blank)); }
-    else { yl = (double)__ldg((const float*)(row + I.ycol_last)); yb = (double)__ldg((const float*)(row + I.ycol_blank)); }
+  __device__ __forceinline__ void load_y(const SwItem& I, int t, double& yl, double& yb) const {
+    const Col* c = I.cb + (t & I.cmask);
+    yl = c->y[I.last]; yb = c->y[4];
   }
 
   __device__ __forceinline__ double parent_at(const SwItem& I, int r, int t) const {
     if (I.pstat == PS_INE || I.pstat == PS_FROZEN) return frozen_at(I.pwb, t, I.wmask, I.plo, I.phi, I.same);
     if (I.pstat == PS_ROOT) return root_prob(r, t - 1);
-    return ninf();
+    return 0.0;
+  }
+
+  // value of column t expressed in the scale of the band (only needed when the scale changes inside the band)
+  __device__ __forceinline__ double in_band_scale(const SwItem& I, double x, int t) const {
+    if (!I.mixed) return x;
+    return scale2(x, (I.cb + (t & I.cmask))->K - I.kref);
   }
 
   // Private recomputation of the cells [cs, lim) of one (node, read), cs < lim: every parent entry read here is
   // final.  Leaves the node's values at lim - 1 in p_prev / ng_prev / g_prev and folds the new values into maxv.
   __device__ __forceinline__ void chain(const SwItem& I, int a, int r, int cs, int lim, bool mirror, double& p_prev,
                                         double& ng_prev, double& g_prev, double& maxv) const {
-    p_prev = ninf(); ng_prev = ninf();
+    p_prev = 0.0; ng_prev = 0.0;
     if (cs - 1 >= I.lo && cs - 1 < I.hi) {
       const Ent* se = I.wb + (cs & I.wmask);
       p_prev = se->prob;
       if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { ng_prev = se->nogap; }
     }
-    const long ystep = I.yrc ? -I.yrowb : I.yrowb;
-    const char* row = I.ybase + (long)(I.yrc ? (I.yT - 1 - cs) : cs) * I.yrowb;
-    double yl, yb;
-    load_y(I, row, yl, yb);
+    // inputs are requested two timesteps ahead of their use
+    double yl, yb, yl_n = 0, yb_n = 0, pv_n = 0;
+    load_y(I, cs, yl, yb);
     double pv = parent_at(I, r, cs);
-    // merge-repeats: the no-gap chain ng(t) = lae(pv(t) + y, ng(t-1) + y) does not depend on prob(t-1), so ng(t+1)
-    // is evaluated next to prob(t) = lae(prob(t-1) + yblank, ng(t)) -- two independent log-add-exps per
-    // iteration instead of two dependent ones (same operations on the same operands, hence the same values)
-    double ng_cur = ninf();
-    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_cur = lae(pv + yl, ng_prev + yl);
-    // inputs are requested two timesteps ahead: those of t+1 were loaded during iteration t-1 (or just below),
-    // so the no-gap chain of t+1 never waits for a load issued in the same iteration
-    double yl_n = 0, yb_n = 0, pv_n = ninf();
-    row += ystep;
-    if (cs + 1 < lim) {
-      load_y(I, row, yl_n, yb_n);
-      pv_n = parent_at(I, r, cs + 1);
-    }
+    if (cs + 1 < lim) { load_y(I, cs + 1, yl_n, yb_n); pv_n = parent_at(I, r, cs + 1); }
     for (int t = cs; t < lim; ++t) {
-      double yl_n2 = 0, yb_n2 = 0, pv_n2 = ninf();
-      row += ystep;
-      if (t + 2 < lim) {
-        load_y(I, row, yl_n2, yb_n2);
-        pv_n2 = parent_at(I, r, t + 2);
-      }
-      double prob;
+      double yl_n2 = 0, yb_n2 = 0, pv_n2 = 0;
+      if (t + 2 < lim) { load_y(I, t + 2, yl_n2, yb_n2); pv_n2 = parent_at(I, r, t + 2); }
+      double prob, gp, ng;
+      cell(p_prev, ng_prev, pv, yl, yb, prob, gp, ng);
       Ent* o = I.wb + ((t + 1) & I.wmask);
       if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
-        const double ng_nxt = lae(pv_n + yl_n, ng_cur + yl_n);  // for t+1; unused after the last iteration
-        const double gp = p_prev + yb;
-        const double ng = ng_cur;
-        prob = lae(gp, ng);
         double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
         *reinterpret_cast<double4*>(o) = v4;
         ng_prev = ng; g_prev = gp;
-        ng_cur = ng_nxt;
       } else {
-        prob = lae(pv + yl, p_prev + yb);
         o->prob = prob;
       }
       if (mirror) mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
       p_prev = prob;
-      if (prob > maxv) maxv = prob;
+      maxv = fmax(maxv, in_band_scale(I, prob, t));
       yl = yl_n; yb = yb_n; pv = pv_n;
       yl_n = yl_n2; yb_n = yb_n2; pv_n = pv_n2;
     }
   }
 
-  // Whole-band recomputations (nodes that entered the expanded beam in this step) are long dependent chains, and the
-  // threads that own them are scattered over all warps: left in place, every warp of the block would run a dozen
-  // iterations with one or two active lanes.  Their owners queue them instead (one list per read, so that chains of
-  // equal length share a warp), and the LAST warps of the block (which own few items of their own) run one chain per
-  // lane.  Only the band maximum travels back through shared memory; the values at the end of the chain are in the
-  // node's window.
+  // Whole-band recomputations (nodes that entered the expanded beam in this step) are dependent chains over the band,
+  // and the threads that own them are scattered over all warps.  With POB_DEBUG_LONG=1 their owners queue them (one
+  // list per read, so that chains of equal length share a warp), and the LAST warps of the block (which own few items
+  // of their own) run one chain per lane.  Only the band maximum travels back (through a_maxp); the values at the end
+  // of the chain are in the node's window.
   __device__ __noinline__ void long_chains(int nl0, int nl1, int s0, int e0, int s1, int e1, bool mirror) {
     POB_VIEWS
     const int k0 = (nl0 + 31) >> 5, k1 = (nl1 + 31) >> 5;
@@ -521,10 +570,10 @@ struct Engine {
       const int ts = r ? s1 : s0, te = r ? e1 : e0;
       const int lim = min(te, sh[SH_TB0 + r]);
       SwItem I;
-      load_item(a, r, I);
-      double p_prev, ng_prev, g_prev = ninf(), maxv = ninf();
+      load_item(a, r, ts, te, I);
+      double p_prev, ng_prev, g_prev = 0.0, maxv = 0.0;
       if (ts < lim) chain(I, a, r, ts, lim, mirror, p_prev, ng_prev, g_prev, maxv);
-      resmax[2 * a + r] = maxv;
+      a_maxp[2 * a + r] = maxv;
     }
   }
 
@@ -537,33 +586,34 @@ struct Engine {
   //     sweep / single updates from inputs that are still current; cs = clamp(che, s, e) is where new work
   //     starts (new and revived nodes: cs = s);
   //   * phase A (no barrier): each item computes [cs, min(e, Tb)) on its own; all parent entries it reads
-  //     there are final because Tb = 1 + min over live-parent items of the parent's cs.  New and revived nodes
-  //     (whole band) are handed to long_chains();
+  //     there are final because Tb = 1 + min over live-parent items of the parent's cs;
   //   * phase B (one barrier per timestep): the time-major loop over [Tb, e) with parent values exchanged
   //     through shared memory.  A node whose live parent produced a new value at t-1 recomputes from t on
   //     even inside its own clean range (dirtiness propagates down the tree);
   //   * clean entries only contribute to the band maximum (max_prob is reset every step in the reference).
   // `full` disables the reuse (every node recomputed from s): the literal reference schedule.
+  // Band maxima are kept in the scale of the band's newest column (SwItem::kref), the same for every node.
   __device__ __noinline__ void sweep(int reads_mask, int s0, int e0, int s1, int e1, bool full,
                                      unsigned long long& n_updates) {
     POB_VIEWS
     const int tid = threadIdx.x;
     const int a = tid >> 1, r = tid & 1;
+    need_cols((reads_mask & 1) ? e0 : 0, (reads_mask & 2) ? e1 : 0);
     const bool used = a < EMAX && a_slot[a] >= 0;
     const bool on = used && ((reads_mask >> r) & 1);
     int cs = 0;
     bool was_fresh = true, longi = false;
-    double p_prev = ninf(), ng_prev = ninf(), g_prev = ninf(), maxv = ninf();
+    double p_prev = 0.0, ng_prev = 0.0, g_prev = 0.0, maxv = 0.0;
     const int ts = r ? s1 : s0, te = r ? e1 : e0;
     SwItem I;
-    I.lo = I.hi = I.plo = I.phi = I.pa = I.wmask = I.yT = 0; I.pstat = PS_DEAD; I.same = I.f64 = I.yrc = false;
-    I.wb = nullptr; I.pwb = nullptr; I.ybase = nullptr; I.yrowb = I.ycol_last = I.ycol_blank = 0;
+    I.lo = I.hi = I.plo = I.phi = I.pa = I.wmask = I.cmask = I.last = I.kref = 0; I.pstat = PS_DEAD; I.same = I.mixed = false;
+    I.wb = nullptr; I.pwb = nullptr; I.cb = nullptr;
     PCLK(12);
     deferred_finalize();
     const bool mirror = g_es.mir_off >= 0;
     PCLK(13);
     if (on && te > ts) {
-      load_item(a, r, I);
+      load_item(a, r, ts, te, I);
       const int che = a_che[2 * a + r];
       was_fresh = che < 0;
       cs = full ? ts : min(max(che, ts), te);
@@ -572,8 +622,8 @@ struct Engine {
         const int pcs = full ? ts : min(max(pche, ts), te);
         atomicMin(&sh[SH_TB0 + r], pcs + 1);
       }
-      // a node that entered the expanded beam in this step recomputes its whole band: queue it for long_chains()
-      longi = !full && was_fresh && te - ts >= 2;
+      // a node that entered the expanded beam in this step recomputes its whole band: optionally queued for long_chains()
+      longi = g_es.longq && !full && was_fresh && te - ts >= 2;
       if (longi) lst[r * EMAX + atomicAdd(&sh[SH_NL0 + r], 1)] = (int16_t)a;
       PCLK(14);
       // clean part of the band: only the maximum is needed (independent loads, four in flight)
@@ -586,22 +636,30 @@ struct Engine {
           g1 = min(c1, max(c0, mlo));
           m1 = min(c1, max(g1, mhi));
           const double* mb = mir_base(a, r);
+          if (!I.mixed) {
 #pragma unroll
-          for (int q = 0; q < MIR_DEPTH; ++q) {
-            const int t = g1 + q;
-            if (t < m1) maxv = fmax(maxv, mb[(t + 1) & (MIR_DEPTH - 1)]);
+            for (int q = 0; q < MIR_DEPTH; ++q) {
+              const int t = g1 + q;
+              if (t < m1) maxv = fmax(maxv, mb[(t + 1) & (MIR_DEPTH - 1)]);
+            }
+          } else {
+            for (int t = g1; t < m1; ++t) maxv = fmax(maxv, in_band_scale(I, mb[(t + 1) & (MIR_DEPTH - 1)], t));
           }
         }
 #pragma unroll 1
         for (int part = 0; part < 2; ++part) {
           const int b0 = part ? m1 : c0, b1 = part ? c1 : g1;
-          for (int t = b0; t < b1; t += 4) {
-            double v0 = ninf(), v1 = ninf(), v2 = ninf(), v3 = ninf();
-            v0 = (I.wb + ((t + 1) & I.wmask))->prob;
-            if (t + 1 < b1) v1 = (I.wb + ((t + 2) & I.wmask))->prob;
-            if (t + 2 < b1) v2 = (I.wb + ((t + 3) & I.wmask))->prob;
-            if (t + 3 < b1) v3 = (I.wb + ((t + 4) & I.wmask))->prob;
-            maxv = fmax(fmax(maxv, v0), fmax(fmax(v1, v2), v3));
+          if (!I.mixed) {
+            for (int t = b0; t < b1; t += 4) {
+              double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+              v0 = (I.wb + ((t + 1) & I.wmask))->prob;
+              if (t + 1 < b1) v1 = (I.wb + ((t + 2) & I.wmask))->prob;
+              if (t + 2 < b1) v2 = (I.wb + ((t + 3) & I.wmask))->prob;
+              if (t + 3 < b1) v3 = (I.wb + ((t + 4) & I.wmask))->prob;
+              maxv = fmax(fmax(maxv, v0), fmax(fmax(v1, v2), v3));
+            }
+          } else {
+            for (int t = b0; t < b1; ++t) maxv = fmax(maxv, in_band_scale(I, (I.wb + ((t + 1) & I.wmask))->prob, t));
           }
         }
       }
@@ -622,7 +680,7 @@ struct Engine {
     if (nl0 + nl1 > 0) {
       if ((int)blockDim.x - 1 - tid < 32 * (((nl0 + 31) >> 5) + ((nl1 + 31) >> 5))) long_chains(nl0, nl1, s0, e0, s1, e1, mirror);
       __syncthreads();
-      if (longi) maxv = resmax[2 * a + r];
+      if (longi) maxv = a_maxp[2 * a + r];
     }
     PCLK(2);
     // ---- phase B: synchronised time-major loop over [Tb, te)
@@ -631,8 +689,6 @@ struct Engine {
       uint8_t* const pchg = reinterpret_cast<uint8_t*>(tmpa);  // [2][EMAX*2] "parent value changed" flags
       const bool inB = on && te > ts && Tb < te;
       double ylast = 0, yblank = 0;
-      const long ystep = I.yrc ? -I.yrowb : I.yrowb;
-      const char* row = nullptr;
       if (inB) {
         if (longi && computing) {
           // the chain ran on another thread: its last values are in the window
@@ -641,7 +697,7 @@ struct Engine {
           if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { g_prev = se->gap; ng_prev = se->nogap; }
         }
         // publish the node's value at Tb-1: computed in phase A, or a stored clean entry
-        double2 pb; pb.x = ninf(); pb.y = ninf();
+        double2 pb; pb.x = 0.0; pb.y = 0.0;
         const int tp = Tb - 1;
         if (computing) { pb.x = p_prev; pb.y = g_prev; }
         else if (tp >= I.lo && tp < I.hi) {
@@ -651,15 +707,14 @@ struct Engine {
         }
         pub[a * 2 + r] = pb;
         pchg[a * 2 + r] = computing;
-        row = I.ybase + (long)(I.yrc ? (I.yT - 1 - Tb) : Tb) * I.yrowb;
-        load_y(I, row, ylast, yblank);
+        load_y(I, Tb, ylast, yblank);
       }
       __syncthreads();
       PCLK(3);
       const double2* pub_rd = pub + (size_t)I.pa * 2 + r;
       double2* pub_wr = pub + (size_t)(a < EMAX ? a : 0) * 2 + r;
       const int pstride = EMAX * 2;
-      double fz_next = ninf();
+      double fz_next = 0.0;
       if (inB && I.pstat == PS_FROZEN) fz_next = frozen_at(I.pwb, Tb, I.wmask, I.plo, I.phi, I.same);
       for (int it = 0; it < iters; ++it) {
         const int t = Tb + it;
@@ -675,17 +730,16 @@ struct Engine {
             pv = fz_next;
             if (t + 1 < te) fz_next = frozen_at(I.pwb, t + 1, I.wmask, I.plo, I.phi, I.same);
           } else if (I.pstat == PS_ROOT) pv = root_prob(r, t - 1);
-          else pv = ninf();
+          else pv = 0.0;
           const double yl = ylast, yb = yblank;
-          row += ystep;
-          if (t + 1 < te) load_y(I, row, ylast, yblank);
+          if (t + 1 < te) load_y(I, t + 1, ylast, yblank);
           const bool must = computing || t >= cs || pchanged;
           double2 pb;
           if (must) {
             if (!computing) {
               // first recomputed timestep of a node that was clean so far: fetch its own values at t-1
               computing = true;
-              p_prev = ninf(); ng_prev = ninf();
+              p_prev = 0.0; ng_prev = 0.0;
               if (t - 1 >= I.lo && t - 1 < I.hi) {
                 const Ent* se = I.wb + (t & I.wmask);
                 p_prev = se->prob;
@@ -694,36 +748,30 @@ struct Engine {
               if (t < cs) {
                 // dirtied inside its clean range: the clean maximum may include entries that change now
                 cs = t;
-                maxv = ninf();
+                maxv = 0.0;
                 for (int q = ts; q < t; ++q) {
-                  if (q >= I.lo && q < I.hi) {
-                    const double v = (I.wb + ((q + 1) & I.wmask))->prob;
-                    if (v > maxv) maxv = v;
-                  }
+                  if (q >= I.lo && q < I.hi) maxv = fmax(maxv, in_band_scale(I, (I.wb + ((q + 1) & I.wmask))->prob, q));
                 }
               }
             }
-            double prob;
+            double prob, gp, ng;
+            cell(p_prev, ng_prev, pv, yl, yb, prob, gp, ng);
             Ent* o = I.wb + ((t + 1) & I.wmask);
             if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
-              const double gp = p_prev + yb;
-              const double ng = lae(pv + yl, ng_prev + yl);
-              prob = lae(gp, ng);
               double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
               *reinterpret_cast<double4*>(o) = v4;
               ng_prev = ng;
               pb.x = prob; pb.y = gp;
             } else {
-              prob = lae(pv + yl, p_prev + yb);
               o->prob = prob;
-              pb.x = prob; pb.y = ninf();
+              pb.x = prob; pb.y = 0.0;
             }
             if (mirror) mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
             p_prev = prob;
-            if (prob > maxv) maxv = prob;
+            maxv = fmax(maxv, in_band_scale(I, prob, t));
           } else {
             // still clean at t: hand the stored value to the children
-            pb.x = ninf(); pb.y = ninf();
+            pb.x = 0.0; pb.y = 0.0;
             if (t >= I.lo && t < I.hi) {
               const Ent* se = I.wb + ((t + 1) & I.wmask);
               pb.x = se->prob;
@@ -737,6 +785,7 @@ struct Engine {
       }
       PCLK(4);
     }
+    int kmax = I.kref;  // scale of maxv
     if (on) {
       if (te > ts) {
         // window bookkeeping: after this sweep every entry of [ts, te) is current
@@ -754,25 +803,30 @@ struct Engine {
           mir_lo()[2 * a + r] = max(nlo, te - MIR_DEPTH); mir_hi()[2 * a + r] = te;
         }
         a_maxp[2 * a + r] = maxv;  // reset + max over the band
+        a_maxk[2 * a + r] = kmax;
+        if (a == 0) sh[SH_KREF0 + r] = kmax;  // for the debug trace only
       } else {
-        maxv = a_maxp[2 * a + r];  // empty band: max_prob left stale (A.6b)
+        // empty band: max_prob left stale (A.6b); brought to a scale every node shares (that of the newest column)
+        kmax = sh[SH_KLAST0 + r];
+        maxv = scale2(a_maxp[2 * a + r], a_maxk[2 * a + r] - kmax);
+        if (a == 0) sh[SH_KREF0 + r] = kmax;
       }
       n_updates += (unsigned long long)max(te - ts, 0);  // algorithmic count: what the reference evaluates
     }
-    // ranking keys: row_col = max0 + max1 (PrefixTree.h:111, :397); row = value(0, u) + max1 (:107, :393)
+    // ranking keys: row_col = max0 * max1 (PrefixTree.h:111, :397); row = value(0, u) * max1 (:107, :393); every
+    // factor is in a scale shared by all nodes of this step
     const double other = __shfl_xor_sync(0xffffffffu, maxv, 1);
     if (used) {
       if (mode == MODE_ROWCOL) {
-        if (r == 0) set_key(a, no_nan(maxv + other));
+        if (r == 0) set_key(a, no_nan(__dmul_rn(maxv, other)));
       } else if (r == 1) {
-        set_key(a, no_nan(a_last0[a] + maxv));
+        set_key(a, no_nan(__dmul_rn(a_last0[a], maxv)));
       }
     }
     pre_prune();
     __syncthreads();
     PCLK(5);
   }
-
 
   // scalars of the coming prune / sweep, reset by thread 0 BEFORE the barrier that precedes prune()
   __device__ __forceinline__ void pre_prune() {
@@ -784,26 +838,44 @@ struct Engine {
     }
   }
 
-  // Ranking key of an active slot: the exact pair (order-preserving integer image of the FP64 score, creation order)
-  // and a 31-bit fixed-point image of the score relative to the top score of the previous prune (2^-23 nats per unit,
-  // +-127 nats, saturating).  The map score -> k32 is monotone (not strict), so ranks computed on k32 are exact
-  // whenever they come out distinct; prune() checks that and falls back to the exact keys otherwise.
+  // Ranking key of an active slot: the score itself (a non-negative double in the scale shared by all nodes of the
+  // step: its bit pattern orders like its value) and a 31-bit image of it: exponent relative to the top score of the
+  // previous prune (+-127 binades, saturating) and 23 mantissa bits.  The map score -> k32 is monotone (not strict), so
+  // ranks computed on k32 are exact whenever they come out distinct; prune() checks that and falls back to the exact
+  // keys otherwise.
   __device__ __forceinline__ void set_key(int a, double score) {
     POB_VIEWS
-    key[a] = make_key(score, (double)a_order[a]);
-    const double sref = *reinterpret_cast<const double*>(sh + SH_SREF);
-    double d = score - sref;
-    d = fmin(fmax(d, -127.0), 127.0);
-    k32[a] = (unsigned)__double2int_rn((d + 128.0) * 8388608.0);
+    key[a] = score;
+    long long k = (__double_as_longlong(score) >> 29) - ((long long)sh[SH_EBASE] << 23);
+    k = max(0LL, min(k, 0x7fffffffLL));
+    k32[a] = (unsigned)k;
   }
   __device__ __forceinline__ void clear_key(int a) {
     POB_VIEWS
-    key[a] = make_key(ninf(), 4.5e9);
+    key[a] = -1.0;  // below every score: an unused slot never counts in a ranking
     k32[a] = 0;
   }
+  // the top of the new beam sets the exponent base of the next step's 31-bit keys and asks for a change of scale of
+  // the coming columns of a read when its values have drifted 64 binades away from 1
+  __device__ __forceinline__ void top_feedback(int a) {
+    POB_VIEWS
+    const double sc = key[a];
+    if (!(sc > 0.0)) return;
+    sh[SH_EBASE] = max(0, (int)((__double_as_longlong(sc) >> 52) & 0x7ff) - 127);
+    for (int r = 0; r < 2; ++r) {
+      double m; int k;
+      if (mode == MODE_ROWCOL || (mode == MODE_ROW && r == 1)) { m = a_maxp[2 * a + r]; k = a_maxk[2 * a + r]; }
+      else if (r == 0) { m = a_last0[a]; k = sh[SH_KCUR0]; }
+      else continue;
+      if (!(m > 0.0)) continue;
+      const int e = (int)((__double_as_longlong(m) >> 52) & 0x7ff) - 1023 + (k - sh[SH_KLAST0 + r]);
+      sh[SH_PEND0 + r] = (e >= 64 || e <= -64) ? e : 0;
+    }
+  }
 
-  // exact ranking on the 64-bit keys, ties by creation order: only when the fast pass saw equal 31-bit keys inside
-  // the beam (two scores within 2^-23, more than 127 nats from the reference, or fewer finite candidates than W)
+  // exact ranking on the scores' bit patterns, ties by creation order: only when the fast pass saw equal 31-bit keys
+  // inside the beam (two scores within 2^-23 relative, more than 127 binades from the reference, or fewer positive
+  // candidates than W)
   __device__ __noinline__ void prune_exact() {
     POB_VIEWS
     const int tid = threadIdx.x;
@@ -816,12 +888,11 @@ struct Engine {
     int rank = 0;
     if (tid == 0) sh[SH_DMIN] = 0x7fffffff;
     if (cand) {
-      const unsigned long long ks = (unsigned long long)__double_as_longlong(key[a].x);
-      const double ko = key[a].y;
+      const long long ks = __double_as_longlong(key[a]);
+      const uint32_t ko = a_order[a];
       for (int j = j0; j < j1; ++j) {
-        const double2 kj = key[j];
-        const unsigned long long s = (unsigned long long)__double_as_longlong(kj.x);
-        rank += (s > ks) || (s == ks && kj.y < ko);
+        const long long s = __double_as_longlong(key[j]);
+        rank += (s > ks) || (s == ks && a_order[j] < ko);
       }
     }
     if (two) rank += __shfl_xor_sync(0xffffffffu, rank, 1);
@@ -832,10 +903,7 @@ struct Engine {
       if (inb) {
         beam[rank] = a;
         atomicMin(&sh[SH_DMIN], a_depth[a]);
-        if (rank == 0) {
-          const double sc = skey_inv((unsigned long long)__double_as_longlong(key[a].x));
-          if (sc > -1e300) *reinterpret_cast<double*>(sh + SH_SREF) = sc;
-        }
+        if (rank == 0) top_feedback(a);
       }
     }
     if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&g_exact_prunes), 1ULL);
@@ -886,10 +954,7 @@ struct Engine {
       if (inb) {
         beam[rank] = a;
         dmin_mine = a_depth[a];
-        if (rank == 0) {
-          const double sc = skey_inv((unsigned long long)__double_as_longlong(key[a].x));
-          if (sc > -1e300) *reinterpret_cast<double*>(sh + SH_SREF) = sc;
-        }
+        if (rank == 0) top_feedback(a);
       }
     }
     // the ranks inside the beam must be distinct: collect them as bit masks (and their count) per warp
@@ -914,7 +979,6 @@ struct Engine {
     PCLK(6);
   }
 
-
   // ---- retire an active slot: write the header home, queue the node for reclamation ----
   __device__ void retire(int a) {
     POB_VIEWS
@@ -923,7 +987,7 @@ struct Engine {
     h.tid = a_tid[a];
     for (int c = 0; c < 4; ++c) { h.kid_slot[c] = a_kid[4 * a + c]; h.kid_order[c] = a_kido[4 * a + c]; }
     h.lo[0] = a_lo[2 * a]; h.lo[1] = a_lo[2 * a + 1]; h.hi[0] = a_hi[2 * a]; h.hi[1] = a_hi[2 * a + 1];
-    h.maxp[0] = a_maxp[2 * a]; h.maxp[1] = a_maxp[2 * a + 1];
+    h.maxp[0] = a_maxp[2 * a]; h.maxp[1] = a_maxp[2 * a + 1]; h.maxk[0] = a_maxk[2 * a]; h.maxk[1] = a_maxk[2 * a + 1];
     const int stamp = atomicAdd(&sh[SH_STAMP], 1) + 1;
     h.state = stamp;
     const int pos = atomicAdd(&sh[SH_RQT], 1);
@@ -942,13 +1006,13 @@ struct Engine {
     n.order = order; n.state = 0; n.parent_slot = a_slot[pa]; n.parent_order = a_order[pa];
     n.parent_tid = parent_tid; n.tid = -1; n.depth = a_depth[pa] + 1; n.last = last;
     for (int q = 0; q < 4; ++q) { n.kid_slot[q] = -1; n.kid_order[q] = 0; }
-    n.lo[0] = n.lo[1] = 0; n.hi[0] = n.hi[1] = 0; n.maxp[0] = n.maxp[1] = ninf(); n.pad[0] = n.pad[1] = 0;
+    n.lo[0] = n.lo[1] = 0; n.hi[0] = n.hi[1] = 0; n.maxp[0] = n.maxp[1] = 0.0; n.maxk[0] = n.maxk[1] = 0;
     hdr[slot] = n;
     a_slot[a] = slot; a_order[a] = order; a_par[a] = pa; a_pslot[a] = n.parent_slot; a_porder[a] = n.parent_order;
     a_depth[a] = n.depth; a_tid[a] = -1; a_ptid[a] = n.parent_tid;
     for (int q = 0; q < 4; ++q) { a_kid[4 * a + q] = -1; a_kido[4 * a + q] = 0; }
     a_lo[2 * a] = a_lo[2 * a + 1] = 0; a_hi[2 * a] = a_hi[2 * a + 1] = 0;
-    a_maxp[2 * a] = a_maxp[2 * a + 1] = ninf(); a_last0[a] = ninf();
+    a_maxp[2 * a] = a_maxp[2 * a + 1] = 0.0; a_maxk[2 * a] = a_maxk[2 * a + 1] = 0; a_last0[a] = 0.0;
     a_che[2 * a] = a_che[2 * a + 1] = -1;
     a_last[a] = (uint8_t)last; a_pstat[a] = PS_INE; a_same[a] = (a_last[pa] == last);
     a_inbeam[a] = 0; a_needed[a] = 1;
@@ -972,7 +1036,8 @@ struct Engine {
       }
     }
     a_lo[2 * a] = h.lo[0]; a_lo[2 * a + 1] = h.lo[1]; a_hi[2 * a] = h.hi[0]; a_hi[2 * a + 1] = h.hi[1];
-    a_maxp[2 * a] = h.maxp[0]; a_maxp[2 * a + 1] = h.maxp[1]; a_last0[a] = ninf();
+    a_maxp[2 * a] = h.maxp[0]; a_maxp[2 * a + 1] = h.maxp[1]; a_maxk[2 * a] = h.maxk[0]; a_maxk[2 * a + 1] = h.maxk[1];
+    a_last0[a] = 0.0;
     a_che[2 * a] = a_che[2 * a + 1] = -1;  // retained entries are stale with respect to the live parent
     a_last[a] = (uint8_t)h.last; a_pstat[a] = PS_INE; a_same[a] = (a_last[pa] == h.last);
     a_inbeam[a] = 0; a_needed[a] = 1;
@@ -1158,7 +1223,11 @@ struct Engine {
     if (threadIdx.x == 0 && step < 50000) {
       double sum = 0;
       for (int b = 0; b < sh[SH_NB]; ++b) {
-        const double sc = skey_inv((unsigned long long)__double_as_longlong(key[beam[b]].x));
+        // back to the reference's log domain: the key is a product of factors in the scales KREF0 / KREF1 (KCUR0 for
+        // the single-column factor of the 1D and ROW searches)
+        const int kk = (mode == MODE_ROWCOL) ? sh[SH_KREF0] + sh[SH_KREF1]
+                                             : sh[SH_KCUR0] + (mode == MODE_ROW ? sh[SH_KREF1] : 0);
+        const double sc = log(key[beam[b]]) + 0.6931471805599453 * kk;
         if (b == 0) G.dbg_trace[2 * step] = sc;
         if (sc > -1e300) sum += sc;
       }
@@ -1179,7 +1248,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
   // ---- engine state of this item: scalars + views of the CTA's global workspace
   if (tid == 0) {
     g_es.W = G.W; g_es.NP = G.NP; g_es.RQ = G.RQ; g_es.EMAX = G.EMAX; g_es.mode = G.mode;
-    g_es.noreclaim = G.dbg_noreclaim; g_es.inspect_every = G.inspect_every;
+    g_es.noreclaim = G.dbg_noreclaim; g_es.inspect_every = G.inspect_every; g_es.longq = G.dbg_long;
     g_es.mir_off = G.mir_off;
     g_es.cap[0] = G.CAP0; g_es.cap[1] = G.CAP1; g_es.mask[0] = G.CAP0 - 1; g_es.mask[1] = G.CAP1 - 1;
     g_es.rv[0] = make_view(G.r[0], item);
@@ -1190,8 +1259,9 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     g_es.win[1] = q; q += sizeof(Ent) * (size_t)G.NP * G.CAP1;
     g_es.freelist = (int32_t*)q; q += 4 * (size_t)G.NP;
     g_es.retq = (int2*)q; q += 8 * (size_t)G.RQ;
-    g_es.cum[0] = (double*)q; q += 8 * (size_t)(MODEL == POB_MODEL_CTC ? g_es.rv[0].T : 0);
-    g_es.cum[1] = (double*)q; q += 8 * (size_t)(MODEL == POB_MODEL_CTC ? g_es.rv[1].T : 0);
+    g_es.col[0] = (Col*)q; q += sizeof(Col) * (size_t)G.CAPC0;
+    g_es.col[1] = (Col*)q; q += sizeof(Col) * (size_t)G.CAPC1;
+    g_es.cmask[0] = G.CAPC0 - 1; g_es.cmask[1] = G.CAPC1 - 1;
     g_es.sufmin = (int32_t*)q;
     g_es.trace = G.trace + G.trace_off[item];
   }
@@ -1217,12 +1287,6 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     sh[SH_DMIN] = 0x7fffffff; sh[SH_FIRSTALIVE] = 0x7fffffff;
     sh[SH_TB0] = 0x7fffffff; sh[SH_TB1] = 0x7fffffff;
   }
-  if (MODEL == POB_MODEL_CTC && tid < 2 && (tid == 0 || mode != MODE_1D)) {
-    // PrefixTree.h:508-514: sequential running sum of the blank column
-    const ReadView& v = g_es.rv[tid];
-    double s = 0;
-    for (int t = 0; t < v.T; ++t) { s += v.at(t, v.cblank); g_es.cum[tid][t] = s; }
-  }
   __syncthreads();
   if (U <= 0 || (mode != MODE_1D && V <= 0)) {
     if (tid == 0) { otop[0] = 0; otop[1] = -1; otop[2] = 0; otop[3] = POB_ST_EMPTY; G.out_score[item] = 0; }
@@ -1237,13 +1301,13 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     n.order = 1 + tid; n.state = 0; n.parent_slot = -1; n.parent_order = 0; n.parent_tid = 0; n.tid = -1;
     n.depth = 1; n.last = tid;
     for (int q = 0; q < 4; ++q) { n.kid_slot[q] = -1; n.kid_order[q] = 0; }
-    n.lo[0] = n.lo[1] = 0; n.hi[0] = n.hi[1] = 0; n.maxp[0] = n.maxp[1] = ninf(); n.pad[0] = n.pad[1] = 0;
+    n.lo[0] = n.lo[1] = 0; n.hi[0] = n.hi[1] = 0; n.maxp[0] = n.maxp[1] = 0.0; n.maxk[0] = n.maxk[1] = 0;
     hdr[slot] = n;
     a_slot[a] = slot; a_order[a] = n.order; a_par[a] = -1; a_pslot[a] = -1; a_porder[a] = 0; a_depth[a] = 1;
     a_tid[a] = -1; a_ptid[a] = 0;
     for (int q = 0; q < 4; ++q) { a_kid[4 * a + q] = -1; a_kido[4 * a + q] = 0; }
     a_lo[2 * a] = a_lo[2 * a + 1] = 0; a_hi[2 * a] = a_hi[2 * a + 1] = 0;
-    a_maxp[2 * a] = a_maxp[2 * a + 1] = ninf(); a_last0[a] = ninf();
+    a_maxp[2 * a] = a_maxp[2 * a + 1] = 0.0; a_maxk[2 * a] = a_maxk[2 * a + 1] = 0; a_last0[a] = 0.0;
     a_che[2 * a] = a_che[2 * a + 1] = -1;
     a_last[a] = (uint8_t)tid; a_pstat[a] = PS_ROOT; a_same[a] = 0; a_inbeam[a] = 1; a_needed[a] = 1;
     slot2e[slot] = (int16_t)a;
@@ -1395,10 +1459,12 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
   __syncthreads();
   if (tid == 0) {
     const int a = beam[0];
+    // back to the reference's log domain: log(value) + K ln 2 per factor (log(0) = -inf, as in the reference)
+    const double LN2 = 0.6931471805599453;
     double sc;
-    if (mode == MODE_1D) sc = a_last0[a];
-    else if (mode == MODE_ROW) sc = a_last0[a] + a_maxp[2 * a + 1];
-    else sc = a_maxp[2 * a] + a_maxp[2 * a + 1];
+    if (mode == MODE_1D) sc = log(a_last0[a]) + LN2 * sh[SH_KCUR0];
+    else if (mode == MODE_ROW) sc = (log(a_last0[a]) + LN2 * sh[SH_KCUR0]) + (log(a_maxp[2 * a + 1]) + LN2 * a_maxk[2 * a + 1]);
+    else sc = (log(a_maxp[2 * a]) + LN2 * a_maxk[2 * a]) + (log(a_maxp[2 * a + 1]) + LN2 * a_maxk[2 * a + 1]);
     G.out_score[item] = sc;
     if (a_tid[a] >= 0) { otop[0] = a_tid[a]; otop[1] = -1; }
     else { otop[0] = a_ptid[a]; otop[1] = a_last[a]; }
@@ -1487,10 +1553,10 @@ extern "C" int pob_debug_trace(pob_ctx* ctx, double* out, int n) {
 }
 namespace {
 
-size_t ws_bytes(int model, int NP, int CAP0, int CAP1, int RQ, int Umax, int Vmax) {
+size_t ws_bytes(int model, int NP, int CAP0, int CAP1, int RQ, int CAPC0, int CAPC1, int Umax) {
   const size_t es = model == POB_MODEL_CTC ? 8 : 32;
   size_t b = sizeof(NodeHdr) * (size_t)NP + es * (size_t)NP * ((size_t)CAP0 + CAP1) + 4 * (size_t)NP + 8 * (size_t)RQ;
-  if (model == POB_MODEL_CTC) b += 8 * ((size_t)Umax + Vmax + 2);
+  b += sizeof(Col) * ((size_t)CAPC0 + CAPC1);
   b += 4 * ((size_t)Umax + 2);
   return pob_align_up(b, 256);
 }
@@ -1543,6 +1609,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   if (const char* e = getenv("POB_DEBUG_NP")) P.NP = atoi(e);
   if (const char* e = getenv("POB_DEBUG_NORECLAIM")) P.dbg_noreclaim = atoi(e);
   if (const char* e = getenv("POB_DEBUG_NOREUSE")) P.dbg_noreuse = atoi(e);
+  if (const char* e = getenv("POB_DEBUG_LONG")) P.dbg_long = atoi(e);
   P.inspect_every = 0;  // set below, once the block size is known
   if (const char* e = getenv("POB_DEBUG_INSPECT_EVERY")) P.inspect_every = atoi(e) > 0 ? atoi(e) : 1;
   P.prefetch = 1;
@@ -1556,6 +1623,12 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   }
   P.CAP0 = pow2_at_least(max_span0 + 3);
   P.CAP1 = pow2_at_least(max_span1 + 3);
+  // column records: a ring over the widest band plus the look-ahead; the ROW traversal may come back to any earlier
+  // timestep of read 2 (its band starts are not monotone), so there it holds the whole read
+  P.CAPC0 = pow2_at_least(max_span0 + COL_LOOK + 4);
+  P.CAPC1 = pow2_at_least((mode == MODE_ROW ? Vmax + 1 : max_span1) + COL_LOOK + 4);
+  if (P.CAPC0 < 16) P.CAPC0 = 16;
+  if (P.CAPC1 < 16) P.CAPC1 = 16;
   P.RQ = P.NP * 2;
   // the band sweep wants one thread per (node, read); the single-read search one per node
   int threads = (((mode == MODE_1D ? 1 : 2) * P.EMAX + 31) / 32) * 32;
@@ -1620,14 +1693,14 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   if (grid > n_items) grid = n_items;
   if (grid < 1) grid = 1;
   const size_t budget = (size_t)96 << 30;
-  size_t stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, Umax, Vmax);
+  size_t stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, P.CAPC0, P.CAPC1, Umax);
   while (grid > 1 && (size_t)grid * stride > budget && stride > ((size_t)192 << 20)) {
     // wide bands are rare inside a batch: a smaller pool is usually enough, keep the parallelism
-    if (P.NP > 8192) { P.NP >>= 1; P.RQ = P.NP * 2; stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, Umax, Vmax); }
+    if (P.NP > 8192) { P.NP >>= 1; P.RQ = P.NP * 2; stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, P.CAPC0, P.CAPC1, Umax); }
     else break;
   }
   while (grid > 1 && (size_t)grid * stride > budget) grid = grid * 3 / 4;
-  while (P.NP > 1024 && stride > budget) { P.NP >>= 1; P.RQ = P.NP * 2; stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, Umax, Vmax); }
+  while (P.NP > 1024 && stride > budget) { P.NP >>= 1; P.RQ = P.NP * 2; stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, P.CAPC0, P.CAPC1, Umax); }
   P.ws_stride = stride;
   P.ws = (char*)pob_arena_take(ctx, (size_t)grid * stride);
   if (!P.ws) return POB_ENOMEM;
