@@ -44,7 +44,10 @@
 namespace {
 
 enum { MODE_1D = 0, MODE_ROW = 1, MODE_ROWCOL = 2 };
-enum { MIR_DEPTH = 8 };  // newest `prob` values of every (active slot, read) mirrored in shared memory
+#ifndef POB_MIR_DEPTH
+#define POB_MIR_DEPTH 8
+#endif
+enum { MIR_DEPTH = POB_MIR_DEPTH };  // newest `prob` values of every (active slot, read) mirrored in shared memory
 enum { PS_ROOT = 0, PS_INE = 1, PS_FROZEN = 2, PS_DEAD = 3 };  // where a node's parent values come from
 enum { KID_ACTIVE = 0, KID_REVIVE = 1, KID_FRESH = 2 };
 
@@ -97,6 +100,8 @@ struct BeamParams {
   int dbg_noreclaim, dbg_noreuse, dbg_long;
   int inspect_every;        // the retire queue is inspected every this many expansions (its headers are cold)
   int mir_off;              // shared-memory prob mirror: byte offset, or -1 when it does not fit
+  int mir_depth;            // its depth: the newest mir_depth (power of two) values of every (active slot, read)
+  int col_off;              // column records in shared memory: byte offset, or -1 (global workspace)
   int prefetch;             // pull the probability rows / envelope entries of coming steps towards the SM
   double* dbg_trace;        // optional: [step][2] = (top score, sum of beam scores) after each prune
   char* ws;                 // workspace, one stride per resident CTA
@@ -184,7 +189,8 @@ struct EngState {
                     // build_envelope's repair pass clamps some rows far back, envelope.py:82-85)
   int cap[2], mask[2];
   ReadView rv[2];
-  int mir_off;  // byte offset in pob_smem of the prob mirror (MIR_DEPTH newest values per active slot and read), -1 = off
+  int mir_off;  // byte offset in pob_smem of the prob mirror (mdepth newest values per active slot and read), -1 = off
+  int mdepth, mdmask;
   uint32_t* trace;
 };
 __shared__ EngState g_es;
@@ -206,7 +212,7 @@ __shared__ long long g_pclk_last;
 #define PCLK(i) do { } while (0)
 #endif
 __device__ unsigned long long g_exact_prunes;  // how often the ranking needed its exact pass (diagnostic)
-extern __shared__ __align__(16) char pob_smem[];
+extern __shared__ __align__(128) char pob_smem[];
 
 // Shared-memory arrays of the active slots (index a in [0, EMAX)); a_slot[a] < 0 = unused.
 //   slot2e  [NP]      pool slot -> active slot or -1
@@ -277,10 +283,11 @@ struct Engine {
   // time keys [mlo, mhi); every write of a window entry of an active node also writes the mirror.  A node that has
   // just taken its active slot (a_che < 0: nothing written yet) has an empty mirror whatever the bounds say.
   __device__ __forceinline__ double* mir_base(int a, int r) const {
-    return reinterpret_cast<double*>(pob_smem + g_es.mir_off) + (size_t)(2 * a + r) * MIR_DEPTH;
+    // rows are mdepth + 1 apart: an odd stride in 8-byte units keeps lanes that read the same timestep on distinct banks
+    return reinterpret_cast<double*>(pob_smem + g_es.mir_off) + (size_t)(2 * a + r) * (MIR_DEPTH + 1);
   }
   __device__ __forceinline__ int* mir_lo() const {
-    return reinterpret_cast<int*>(pob_smem + g_es.mir_off + (size_t)g_es.EMAX * 2 * MIR_DEPTH * 8);
+    return reinterpret_cast<int*>(pob_smem + g_es.mir_off + (size_t)g_es.EMAX * 2 * (MIR_DEPTH + 1) * 8);
   }
   __device__ __forceinline__ int* mir_hi() const { return mir_lo() + 2 * g_es.EMAX; }
 
@@ -517,21 +524,33 @@ struct Engine {
     return scale2(x, (I.cb + (t & I.cmask))->K - I.kref);
   }
 
-  // Private recomputation of the cells [cs, lim) of one (node, read), cs < lim: every parent entry read here is
-  // final.  Leaves the node's values at lim - 1 in p_prev / ng_prev / g_prev and folds the new values into maxv.
-  __device__ __forceinline__ void chain(const SwItem& I, int a, int r, int cs, int lim, bool mirror, double& p_prev,
-                                        double& ng_prev, double& g_prev, double& maxv) const {
-    p_prev = 0.0; ng_prev = 0.0;
+  // Inputs of the first two cells of a private recomputation starting at cs: the node's own values at cs - 1, the
+  // column factors and the parent's values.  None of them is written during the private phase of a sweep, so the
+  // loads can be issued long before their use (before the scan and the barrier that precede that phase).
+  // (Four cells ahead was measured slower: 4432 against 4833 pairs/s.)
+  struct ChainIn {
+    double p_prev, ng_prev, yl, yb, pv, yl_n, yb_n, pv_n;
+  };
+  __device__ __forceinline__ void chain_preload(const SwItem& I, int r, int cs, int te, ChainIn& C) const {
+    C.p_prev = 0.0; C.ng_prev = 0.0;
     if (cs - 1 >= I.lo && cs - 1 < I.hi) {
       const Ent* se = I.wb + (cs & I.wmask);
-      p_prev = se->prob;
-      if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { ng_prev = se->nogap; }
+      C.p_prev = se->prob;
+      if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { C.ng_prev = se->nogap; }
     }
+    load_y(I, cs, C.yl, C.yb);
+    C.pv = parent_at(I, r, cs);
+    C.yl_n = 0; C.yb_n = 0; C.pv_n = 0;
+    if (cs + 1 < te) { load_y(I, cs + 1, C.yl_n, C.yb_n); C.pv_n = parent_at(I, r, cs + 1); }
+  }
+
+  // Private recomputation of the cells [cs, lim) of one (node, read), cs < lim: every parent entry read here is
+  // final.  Leaves the node's values at lim - 1 in p_prev / ng_prev / g_prev and folds the new values into maxv.
+  __device__ __forceinline__ void chain(const SwItem& I, int a, int r, int cs, int lim, bool mirror, const ChainIn& C,
+                                        double& p_prev, double& ng_prev, double& g_prev, double& maxv) const {
+    p_prev = C.p_prev; ng_prev = C.ng_prev;
     // inputs are requested two timesteps ahead of their use
-    double yl, yb, yl_n = 0, yb_n = 0, pv_n = 0;
-    load_y(I, cs, yl, yb);
-    double pv = parent_at(I, r, cs);
-    if (cs + 1 < lim) { load_y(I, cs + 1, yl_n, yb_n); pv_n = parent_at(I, r, cs + 1); }
+    double yl = C.yl, yb = C.yb, pv = C.pv, yl_n = C.yl_n, yb_n = C.yb_n, pv_n = C.pv_n;
     for (int t = cs; t < lim; ++t) {
       double yl_n2 = 0, yb_n2 = 0, pv_n2 = 0;
       if (t + 2 < lim) { load_y(I, t + 2, yl_n2, yb_n2); pv_n2 = parent_at(I, r, t + 2); }
@@ -572,7 +591,11 @@ struct Engine {
       SwItem I;
       load_item(a, r, ts, te, I);
       double p_prev, ng_prev, g_prev = 0.0, maxv = 0.0;
-      if (ts < lim) chain(I, a, r, ts, lim, mirror, p_prev, ng_prev, g_prev, maxv);
+      if (ts < lim) {
+        ChainIn C;
+        chain_preload(I, r, ts, te, C);
+        chain(I, a, r, ts, lim, mirror, C, p_prev, ng_prev, g_prev, maxv);
+      }
       a_maxp[2 * a + r] = maxv;
     }
   }
@@ -606,6 +629,8 @@ struct Engine {
     double p_prev = 0.0, ng_prev = 0.0, g_prev = 0.0, maxv = 0.0;
     const int ts = r ? s1 : s0, te = r ? e1 : e0;
     SwItem I;
+    ChainIn C;
+    C.p_prev = C.ng_prev = C.yl = C.yb = C.pv = C.yl_n = C.yb_n = C.pv_n = 0.0;
     I.lo = I.hi = I.plo = I.phi = I.pa = I.wmask = I.cmask = I.last = I.kref = 0; I.pstat = PS_DEAD; I.same = I.mixed = false;
     I.wb = nullptr; I.pwb = nullptr; I.cb = nullptr;
     PCLK(12);
@@ -625,6 +650,12 @@ struct Engine {
       // a node that entered the expanded beam in this step recomputes its whole band: optionally queued for long_chains()
       longi = g_es.longq && !full && was_fresh && te - ts >= 2;
       if (longi) lst[r * EMAX + atomicAdd(&sh[SH_NL0 + r], 1)] = (int16_t)a;
+      if (cs < te && !longi) {
+        chain_preload(I, r, cs, te, C);
+        // a long private chain (new node: whole band): pull the rest of the parent's entries into L1 (four to a line)
+        if (te - cs > 2 && I.pwb != nullptr)
+          for (int q = cs + 2; q < te; q += 4) prefetch_l1(I.pwb + (q & I.wmask));
+      }
       PCLK(14);
       // clean part of the band: only the maximum is needed (independent loads, four in flight)
       {
@@ -637,6 +668,7 @@ struct Engine {
           m1 = min(c1, max(g1, mhi));
           const double* mb = mir_base(a, r);
           if (!I.mixed) {
+            // predicated and unrolled: all loads of a round are in flight together
 #pragma unroll
             for (int q = 0; q < MIR_DEPTH; ++q) {
               const int t = g1 + q;
@@ -675,7 +707,7 @@ struct Engine {
     // ---- phase A: private work [cs, min(te, Tb))
     if (on && te > ts && cs < limA) {
       computing = true;
-      if (!longi) chain(I, a, r, cs, limA, mirror, p_prev, ng_prev, g_prev, maxv);
+      if (!longi) chain(I, a, r, cs, limA, mirror, C, p_prev, ng_prev, g_prev, maxv);
     }
     if (nl0 + nl1 > 0) {
       if ((int)blockDim.x - 1 - tid < 32 * (((nl0 + 31) >> 5) + ((nl1 + 31) >> 5))) long_chains(nl0, nl1, s0, e0, s1, e1, mirror);
@@ -1249,7 +1281,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
   if (tid == 0) {
     g_es.W = G.W; g_es.NP = G.NP; g_es.RQ = G.RQ; g_es.EMAX = G.EMAX; g_es.mode = G.mode;
     g_es.noreclaim = G.dbg_noreclaim; g_es.inspect_every = G.inspect_every; g_es.longq = G.dbg_long;
-    g_es.mir_off = G.mir_off;
+    g_es.mir_off = G.mir_off; g_es.mdepth = G.mir_depth; g_es.mdmask = G.mir_depth - 1;
     g_es.cap[0] = G.CAP0; g_es.cap[1] = G.CAP1; g_es.mask[0] = G.CAP0 - 1; g_es.mask[1] = G.CAP1 - 1;
     g_es.rv[0] = make_view(G.r[0], item);
     if (G.mode != MODE_1D) g_es.rv[1] = make_view(G.r[1], item); else { g_es.rv[1] = g_es.rv[0]; g_es.rv[1].T = 0; }
@@ -1259,8 +1291,13 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     g_es.win[1] = q; q += sizeof(Ent) * (size_t)G.NP * G.CAP1;
     g_es.freelist = (int32_t*)q; q += 4 * (size_t)G.NP;
     g_es.retq = (int2*)q; q += 8 * (size_t)G.RQ;
-    g_es.col[0] = (Col*)q; q += sizeof(Col) * (size_t)G.CAPC0;
-    g_es.col[1] = (Col*)q; q += sizeof(Col) * (size_t)G.CAPC1;
+    if (G.col_off >= 0) {
+      g_es.col[0] = (Col*)(pob_smem + G.col_off);
+      g_es.col[1] = g_es.col[0] + G.CAPC0;
+    } else {
+      g_es.col[0] = (Col*)q; q += sizeof(Col) * (size_t)G.CAPC0;
+      g_es.col[1] = (Col*)q; q += sizeof(Col) * (size_t)G.CAPC1;
+    }
     g_es.cmask[0] = G.CAPC0 - 1; g_es.cmask[1] = G.CAPC1 - 1;
     g_es.sufmin = (int32_t*)q;
     g_es.trace = G.trace + G.trace_off[item];
@@ -1642,19 +1679,33 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
     if (P.inspect_every < 1) P.inspect_every = 1;
   }
   size_t smem = smem_bytes(W, P.NP, P.EMAX);
-  // prob mirror: 2 * EMAX * MIR_DEPTH doubles + two int bounds per (slot, read); only where it costs no CTA per SM
-  P.mir_off = -1;
-  {
-    const size_t mir = (size_t)P.EMAX * 2 * MIR_DEPTH * 8 + (size_t)P.EMAX * 2 * 2 * 4;
-    bool on = mode != MODE_1D && smem + mir <= 74 * 1024;  // three CTAs per SM share 227 KB
+  // The pair searches run two CTAs of 288 threads per SM (113 registers per thread: no spills; three CTAs at 72 registers
+  // were measured slower) and share 227 KB of shared memory.
+  int max_cta_sm = 0;  // 0 = as many as fit
+  if (threads > 128 && threads <= 288) max_cta_sm = 2;
+  if (const char* e = getenv("POB_DEBUG_CTA_PER_SM")) max_cta_sm = atoi(e);
+  // prob mirror: 2 * EMAX rows of (depth + 1) doubles + two int bounds per (slot, read); the deepest that fits
+  P.mir_off = -1; P.mir_depth = 8;
+  if (mode != MODE_1D) {
+    const size_t budget_cta = (max_cta_sm == 2 ? 227 * 1024 / 2 : max_cta_sm == 1 ? 200 * 1024 : 227 * 1024 / 3) - 1024;
+    const size_t mir = (size_t)P.EMAX * 2 * (MIR_DEPTH + 1) * 8 + (size_t)P.EMAX * 2 * 2 * 4;
+    bool on = smem + mir <= budget_cta;
     if (const char* e = getenv("POB_DEBUG_MIRROR")) on = on && atoi(e) != 0;
-    if (on) { P.mir_off = (int)smem; smem = pob_align_up(smem + mir, 16); }
+    if (on) { P.mir_off = (int)smem; P.mir_depth = MIR_DEPTH; smem = pob_align_up(smem + mir, 16); }
+  }
+  // column records (64 B per timestep of the band ring) in shared memory when they fit next to the rest
+  P.col_off = -1;
+  {
+    const size_t budget_cta = (max_cta_sm == 2 ? 227 * 1024 / 2 : max_cta_sm == 1 ? 200 * 1024 : 227 * 1024 / 3) - 1024;
+    const size_t cb = sizeof(Col) * ((size_t)P.CAPC0 + P.CAPC1);
+    bool on = pob_align_up(smem, 64) + cb <= budget_cta;
+    on = false;  // measured slower (the larger carve-out leaves no L1 for the windows)
+    if (const char* e = getenv("POB_DEBUG_COLSMEM")) on = atoi(e) != 0 && pob_align_up(smem, 64) + cb <= budget_cta;
+    if (on) { smem = pob_align_up(smem, 64); P.col_off = (int)smem; smem += cb; }
   }
   if (smem > 200 * 1024) return POB_EUNSUPPORTED;
   void (*kern)(BeamParams);
   const bool ctc = model == POB_MODEL_CTC;
-  int max_cta_sm = 0;  // 0 = as many as fit
-  if (const char* e = getenv("POB_DEBUG_CTA_PER_SM")) max_cta_sm = atoi(e);
   constexpr int M0 = POB_MODEL_CTC, M1 = POB_MODEL_CTC_MERGE_REPEATS;
   if (threads <= 64) { threads = 64; kern = ctc ? beam_kernel<M0, 64, 12> : beam_kernel<M1, 64, 12>; }
   else if (threads <= 128) { kern = ctc ? beam_kernel<M0, 128, 6> : beam_kernel<M1, 128, 6>; }
@@ -1713,7 +1764,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   P.trace = trace; P.trace_off = trace_off; P.out_top = top; P.out_score = out_score;
   if (getenv("POB_DEBUG_VERBOSE"))
     fprintf(stderr, "[pob] beam launch: items %d W %d mode %d NP %d CAP %d/%d span %d/%d threads %d grid %d (%d/SM) smem %zu mirror %d ws/CTA %.1f MB\n",
-            n_items, W, mode, P.NP, P.CAP0, P.CAP1, max_span0, max_span1, threads, grid, per_sm, smem, P.mir_off >= 0,
+            n_items, W, mode, P.NP, P.CAP0, P.CAP1, max_span0, max_span1, threads, grid, per_sm, smem, P.mir_off >= 0 ? P.mir_depth : 0,
             stride / 1048576.0);
   if (n_items > 0) {
     pob_prof_scope ps(ctx, mode == MODE_1D ? POB_K_BEAM_1D : POB_K_BEAM_2D);

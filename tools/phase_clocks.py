@@ -12,7 +12,7 @@ if sys.argv[1] == "build":
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(ROOT, "poreover_b200", "csrc", "*.cu")))
     subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
-                           "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-DPOB_PHASE_CLOCKS", "-o", OUT] + srcs)
+                           "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-DPOB_PHASE_CLOCKS"] + os.environ.get("POB_CLK_FLAGS", "").split() + ["-o", OUT] + srcs)
     sys.exit(0)
 os.environ["POB_DEBUG_LIB"] = OUT
 sys.path.insert(0, ROOT)
