@@ -648,14 +648,18 @@ struct Engine {
         atomicMin(&sh[SH_TB0 + r], pcs + 1);
       }
       // a node that entered the expanded beam in this step recomputes its whole band: optionally queued for long_chains()
+#ifdef POB_LONGQ
       longi = g_es.longq && !full && was_fresh && te - ts >= 2;
       if (longi) lst[r * EMAX + atomicAdd(&sh[SH_NL0 + r], 1)] = (int16_t)a;
+#endif
+#ifdef POB_HOIST
       if (cs < te && !longi) {
         chain_preload(I, r, cs, te, C);
         // a long private chain (new node: whole band): pull the rest of the parent's entries into L1 (four to a line)
         if (te - cs > 2 && I.pwb != nullptr)
           for (int q = cs + 2; q < te; q += 4) prefetch_l1(I.pwb + (q & I.wmask));
       }
+#endif
       PCLK(14);
       // clean part of the band: only the maximum is needed (independent loads, four in flight)
       {
@@ -700,20 +704,27 @@ struct Engine {
     __syncthreads();
     PCLK(1);
     const int Tb0 = sh[SH_TB0], Tb1 = sh[SH_TB1];
+#ifdef POB_LONGQ
     const int nl0 = sh[SH_NL0], nl1 = sh[SH_NL1];
+#endif
     const int Tb = r ? Tb1 : Tb0;  // first timestep of this read that needs the synchronised loop
     bool computing = false;        // p_prev / ng_prev hold the node's values at the previous timestep
     const int limA = min(te, Tb);
     // ---- phase A: private work [cs, min(te, Tb))
     if (on && te > ts && cs < limA) {
       computing = true;
+#ifndef POB_HOIST
+      chain_preload(I, r, cs, te, C);
+#endif
       if (!longi) chain(I, a, r, cs, limA, mirror, C, p_prev, ng_prev, g_prev, maxv);
     }
+#ifdef POB_LONGQ
     if (nl0 + nl1 > 0) {
       if ((int)blockDim.x - 1 - tid < 32 * (((nl0 + 31) >> 5) + ((nl1 + 31) >> 5))) long_chains(nl0, nl1, s0, e0, s1, e1, mirror);
       __syncthreads();
       if (longi) maxv = a_maxp[2 * a + r];
     }
+#endif
     PCLK(2);
     // ---- phase B: synchronised time-major loop over [Tb, te)
     const int iters = max(max((reads_mask & 1) ? e0 - Tb0 : 0, (reads_mask & 2) ? e1 - Tb1 : 0), 0);
@@ -1630,7 +1641,9 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   if (r2) P.r[1] = *r2;
   P.env = env; P.env_off = env_off; P.envt = envt; P.envt_off = envt_off; P.order = order; P.skip = skip;
   P.n_items = n_items; P.W = W; P.mode = mode;
-  P.EMAX = 5 * W + 4;
+  // active slots: the expanded beam (W nodes and their 4 W children), rounded so that the (node, read) threads fill
+  // whole warps (W = 25: 128 slots, 256 threads, 85 registers per thread at three CTAs per SM)
+  P.EMAX = ((5 * W > 8 ? 5 * W : 8) + 15) / 16 * 16;
   // Node pool: the expanded beam (5W) plus retired nodes whose windows can still be read.  About W nodes
   // retire per step and stay readable for one band width, so the pool scales with W x widest band; an
   // overflow is flagged per item (POB_ST_POOL_OVERFLOW), never silent.
@@ -1679,10 +1692,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
     if (P.inspect_every < 1) P.inspect_every = 1;
   }
   size_t smem = smem_bytes(W, P.NP, P.EMAX);
-  // The pair searches run two CTAs of 288 threads per SM (113 registers per thread: no spills; three CTAs at 72 registers
-  // were measured slower) and share 227 KB of shared memory.
-  int max_cta_sm = 0;  // 0 = as many as fit
-  if (threads > 128 && threads <= 288) max_cta_sm = 2;
+  int max_cta_sm = 0;  // 0 = as many as fit (three CTAs of 256 / 288 threads per SM)
   if (const char* e = getenv("POB_DEBUG_CTA_PER_SM")) max_cta_sm = atoi(e);
   // prob mirror: 2 * EMAX rows of (depth + 1) doubles + two int bounds per (slot, read); the deepest that fits
   P.mir_off = -1; P.mir_depth = 8;
@@ -1709,6 +1719,11 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   constexpr int M0 = POB_MODEL_CTC, M1 = POB_MODEL_CTC_MERGE_REPEATS;
   if (threads <= 64) { threads = 64; kern = ctc ? beam_kernel<M0, 64, 12> : beam_kernel<M1, 64, 12>; }
   else if (threads <= 128) { kern = ctc ? beam_kernel<M0, 128, 6> : beam_kernel<M1, 128, 6>; }
+  else if (threads <= 256) {
+    kern = ctc ? beam_kernel<M0, 256, 3> : beam_kernel<M1, 256, 3>;
+    if (max_cta_sm == 2) kern = ctc ? beam_kernel<M0, 256, 2> : beam_kernel<M1, 256, 2>;
+    if (max_cta_sm == 4) kern = ctc ? beam_kernel<M0, 256, 4> : beam_kernel<M1, 256, 4>;
+  }
   else if (threads <= 288) {
     kern = ctc ? beam_kernel<M0, 288, 3> : beam_kernel<M1, 288, 3>;
     if (max_cta_sm == 2) kern = ctc ? beam_kernel<M0, 288, 2> : beam_kernel<M1, 288, 2>;
