@@ -216,7 +216,10 @@ int pob_pair_decode(pob_ctx* ctx, int where, const pob_reads_t* reads1, const po
   Geometry g1, g2;
   POB_TRY(fetch_geometry(ctx, where, reads1, g1));
   POB_TRY(fetch_geometry(ctx, where, reads2, g2));
-  const size_t rows1 = (size_t)g1.off[n], rows2 = (size_t)g2.off[n];
+  // the batch may be a slice of a larger packed batch: its rows are [off[0], off[n]) and every packed output /
+  // scratch array below is rebased by off[0], so that the absolute row offsets address it
+  const size_t base1 = (size_t)g1.off[0], base2 = (size_t)g2.off[0];
+  const size_t rows1 = (size_t)g1.off[n] - base1, rows2 = (size_t)g2.off[n] - base2;
   pob_reads_t d1 = *reads1, d2 = *reads2;
   uint8_t *d_seq1 = out_seq1, *d_seq2 = out_seq2, *d_cons = out_cons;
   int32_t *d_len1 = out_len1, *d_len2 = out_len2, *d_clen = out_cons_len, *d_stats = out_stats, *d_status = out_status;
@@ -227,6 +230,7 @@ int pob_pair_decode(pob_ctx* ctx, int where, const pob_reads_t* reads1, const po
     POB_TRY(stage_out(ctx, out_seq1, rows1 + 4, &d_seq1));
     POB_TRY(stage_out(ctx, out_seq2, rows2 + 4, &d_seq2));
     POB_TRY(stage_out(ctx, out_cons, rows1 + rows2 + 4, &d_cons));
+    d_seq1 -= base1; d_seq2 -= base2; d_cons -= base1 + base2;
     POB_TRY(stage_out(ctx, out_len1, (size_t)n, &d_len1));
     POB_TRY(stage_out(ctx, out_len2, (size_t)n, &d_len2));
     POB_TRY(stage_out(ctx, out_cons_len, (size_t)n, &d_clen));
@@ -238,6 +242,7 @@ int pob_pair_decode(pob_ctx* ctx, int where, const pob_reads_t* reads1, const po
   int32_t *d_s2s1, *d_s2s2, *d_st1, *d_st2;
   POB_TRY(pob_take(ctx, rows1 + 4, &d_s2s1));
   POB_TRY(pob_take(ctx, rows2 + 4, &d_s2s2));
+  d_s2s1 -= base1; d_s2s2 -= base2;
   POB_TRY(pob_take(ctx, (size_t)n, &d_st1));
   POB_TRY(pob_take(ctx, (size_t)n, &d_st2));
   POB_TRY(pob_viterbi_launch(ctx, d1, kind, d_seq1, d_s2s1, nullptr, d_len1, d_st1));
@@ -324,9 +329,9 @@ int pob_pair_decode(pob_ctx* ctx, int where, const pob_reads_t* reads1, const po
   }
   if (where == POB_HOST) {
     if (out_stats) memcpy(out_stats, stats.data(), stats.size() * 4);
-    POB_TRY(copy_back(ctx, out_seq1, d_seq1, rows1));
-    POB_TRY(copy_back(ctx, out_seq2, d_seq2, rows2));
-    POB_TRY(copy_back(ctx, out_cons, d_cons, rows1 + rows2));
+    POB_TRY(copy_back(ctx, out_seq1 + base1, d_seq1 + base1, rows1));
+    POB_TRY(copy_back(ctx, out_seq2 + base2, d_seq2 + base2, rows2));
+    POB_TRY(copy_back(ctx, out_cons + base1 + base2, d_cons + base1 + base2, rows1 + rows2));
     POB_TRY(copy_back(ctx, out_len1, d_len1, (size_t)n));
     POB_TRY(copy_back(ctx, out_len2, d_len2, (size_t)n));
     POB_TRY(copy_back(ctx, out_cons_len, d_clen, (size_t)n));

@@ -51,13 +51,21 @@ int check_reads(const pob_reads_t* r, int min_states, int max_states) {
 // total packed rows of a HOST descriptor
 size_t total_rows(const pob_reads_t* r) { return r->n > 0 ? (size_t)r->row_off[r->n] : 0; }
 
-// copy a host descriptor's arrays into the arena, produce the device descriptor
+// first packed row of a HOST descriptor: a batch may be a slice [lo, hi) of a larger packed batch (row_off + lo, n =
+// hi - lo, same data pointer), so its rows start at row_off[0], not at 0
+size_t first_row(const pob_reads_t* r) { return r->n > 0 ? (size_t)r->row_off[0] : 0; }
+
+// copy a host descriptor's arrays into the arena, produce the device descriptor.  Only the rows [row_off[0],
+// row_off[n]) travel; the device data pointer is rebased so that the (absolute) row offsets keep addressing them.
 int stage_reads(pob_ctx* ctx, const pob_reads_t* h, pob_reads_t* d) {
   *d = *h;
-  size_t rows = total_rows(h);
+  const size_t r0 = first_row(h), rows = total_rows(h) - r0;
+  const size_t rowb = (size_t)h->n_states * elt_size(h->dtype);
   const char* data;
-  POB_TRY(stage_in(ctx, (const char*)h->data, rows * h->n_states * elt_size(h->dtype), &data, 64));
-  d->data = data;
+  // 256-byte aligned staging keeps the 16-byte alignment of the reads whatever r0 is (r0 * rowb is a multiple of 16
+  // for every read the packer aligned)
+  POB_TRY(stage_in(ctx, (const char*)h->data + r0 * rowb, rows * rowb, &data, 64));
+  d->data = data - r0 * rowb;
   POB_TRY(stage_in(ctx, h->row_off, (size_t)h->n + 1, &d->row_off));
   POB_TRY(stage_in(ctx, h->row_len, (size_t)h->n, &d->row_len));
   POB_TRY(stage_in(ctx, h->rc, (size_t)h->n, &d->rc));

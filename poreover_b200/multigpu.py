@@ -45,6 +45,50 @@ class WorkQueue:
         return self.bounds[k], self.bounds[k + 1]
 
 
+def drain_queue(queue, work, lanes=2):
+    """Empty this rank's share of `queue` with `lanes` host threads (GPU calls in flight): each thread pulls the next
+    chunk (lo, hi) and runs work(lo, hi, lane).  Returns [(lo, hi, result)] in the order this rank pulled them.  The
+    queue is shared by all ranks of the job (fetch-and-add on the store), so a rank that finishes early simply pulls
+    more; an exception in any lane stops the others after their current chunk and is re-raised here."""
+    import threading
+    lock, out, errs = threading.Lock(), [], []
+
+    def lane_loop(lane):
+        try:
+            while not errs:
+                with lock:  # one store round trip at a time per process
+                    c = queue.next()
+                if c is None:
+                    return
+                r = work(c[0], c[1], lane)
+                with lock:
+                    out.append((c[0], c[1], r))
+        except BaseException as e:  # noqa: BLE001 -- handed to the caller
+            errs.append(e)
+
+    if lanes <= 1:
+        lane_loop(0)
+    else:
+        ths = [threading.Thread(target=lane_loop, args=(k,), daemon=True) for k in range(lanes)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+    if errs:
+        raise errs[0]
+    return out
+
+
+_queue_serial = [0]
+
+
+def _next_queue_key():
+    """A store key no earlier queue of this process group has used (every rank calls run_sharded the same number of
+    times, so the serial agrees across ranks)."""
+    _queue_serial[0] += 1
+    return "poreover_b200_queue_%d" % _queue_serial[0]
+
+
 def run_sharded(items, cost, process_chunk, chunk=256, group=None, store=None, load_chunk=None, finish_chunk=None,
                 cost_budget=None, workers=None):
     """Process `items` across all ranks.  cost[i] orders the queue (descending).  process_chunk(list) ->
@@ -57,7 +101,7 @@ def run_sharded(items, cost, process_chunk, chunk=256, group=None, store=None, l
     from .ingest import Lookahead
     rank, world, _ = dist_info()
     order = sorted(range(len(items)), key=lambda i: -cost[i])
-    q = WorkQueue(len(order), chunk, store if world > 1 else None, ramp=world if load_chunk else 0,
+    q = WorkQueue(len(order), chunk, store if world > 1 else None, key=_next_queue_key(), ramp=world if load_chunk else 0,
                   weights=[cost[i] for i in order] if cost_budget else None, weight_budget=cost_budget)
     mine = {}
     if load_chunk is None:
