@@ -460,15 +460,28 @@ def run_pairs(args):
         C.memmove(p.value, a.ctypes.data, a.nbytes)
         return p.value
 
+    def pinned_zeros(shape, dtype):
+        """numpy view of freshly pinned host memory (cudaMallocHost): copies to and from it are asynchronous"""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = _lib.vp()
+        check(L.pob_malloc_host(max(nbytes, 1) + 64, C.byref(p)), "pob_malloc_host")
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        a = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        a[...] = 0
+        return a
+
     def host_reads(b):
-        return ReadsT(pinned_like(b.data), b.row_off.ctypes.data, b.lens.ctypes.data,
-                      b.rc.ctypes.data if b.rc is not None else None, b.n, b.n_states, b.dtype, b.layout)
+        # the whole descriptor in pinned memory: probabilities and the (small) index arrays
+        return ReadsT(pinned_like(b.data), pinned_like(b.row_off), pinned_like(b.lens),
+                      pinned_like(b.rc) if b.rc is not None else None, b.n, b.n_states, b.dtype, b.layout)
 
     h1, h2 = host_reads(b1), host_reads(b2)
-    hs1, hs2 = np.zeros(rows1 + 64, np.uint8), np.zeros(rows2 + 64, np.uint8)
-    hc = np.zeros(rows1 + rows2 + 64, np.uint8)
-    hl1, hl2, hlc, hst = (np.zeros(G, np.int32) for _ in range(4))
-    hsc, hstats = np.zeros(G, np.float64), np.zeros((G, 4), np.int32)
+    pin_out = not args.pageable_outputs
+    zeros = pinned_zeros if pin_out else np.zeros
+    hs1, hs2 = zeros(rows1 + 64, np.uint8), zeros(rows2 + 64, np.uint8)
+    hc = zeros(rows1 + rows2 + 64, np.uint8)
+    hl1, hl2, hlc, hst = (zeros(G, np.int32) for _ in range(4))
+    hsc, hstats = zeros(G, np.float64), zeros((G, 4), np.int32)
     A = lambda a: a.ctypes.data  # noqa: E731
     coff = b1.row_off + b2.row_off
     bytes_io = [0, 0]
@@ -522,6 +535,7 @@ def run_pairs(args):
     d2h = int(rows1 + rows2 + (rows1 + rows2) + G * (4 * 4 + 8))
     e2e = {"value": G * args.steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": 1e3 * e2e_s / args.steps, "records_gathered_on_rank0_inside": bool(use_dist),
+           "host_buffers": "inputs pinned (cudaMallocHost); outputs " + ("pinned" if pin_out else "pageable"),
            "rank0_ms_per_step": {"decode_own_chunks": 1e3 * e2e_parts["drain_s"] / args.steps,
                                  "gather_records": 1e3 * e2e_parts["gather_s"] / args.steps},
            "consensus_lengths_equal_single_gpu_pass": e2e_ok}
@@ -783,6 +797,7 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=0, help="items per step of the reference arm (default: by config and cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-weak", action="store_true")
+    ap.add_argument("--pageable-outputs", action="store_true", help="e2e leg: results into pageable instead of pinned host arrays")
     args = ap.parse_args()
     if args.pairs_per_gpu and not args.pairs:
         args.pairs = args.pairs_per_gpu

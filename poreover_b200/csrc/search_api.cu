@@ -1,6 +1,9 @@
 // extern "C" entry points of the beam searches and the fused pair-decode pipeline.
 #include "staging.cuh"
 
+#include <chrono>
+#include <stdlib.h>
+
 namespace {
 
 // host-side copy of the row geometry of a reads descriptor
@@ -211,8 +214,19 @@ int pob_pair_decode(pob_ctx* ctx, int where, const pob_reads_t* reads1, const po
   if (!out_seq1 || !out_len1 || !out_seq2 || !out_len2 || !out_cons || !out_cons_len || !out_status)
     return POB_EINVAL;
   const int model = kind == POB_KIND_BONITO ? POB_MODEL_CTC_MERGE_REPEATS : POB_MODEL_CTC;
+  // POB_DEBUG_TIMING=1: wall-clock milliseconds of the call's host-visible stages on stderr
+  static const bool timing = getenv("POB_DEBUG_TIMING") != nullptr;
+  auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tmark = timing ? tnow() : 0.0;
+  auto stage_done = [&](const char* what) {
+    if (!timing) return;
+    const double t = tnow();
+    fprintf(stderr, "[pob timing] %-22s %8.3f ms\n", what, t - tmark);
+    tmark = t;
+  };
   POB_CUDA(cudaSetDevice(ctx->device));
   POB_TRY(pob_arena_reset(ctx));
+  stage_done("arena reset");
   Geometry g1, g2;
   POB_TRY(fetch_geometry(ctx, where, reads1, g1));
   POB_TRY(fetch_geometry(ctx, where, reads2, g2));
@@ -236,6 +250,7 @@ int pob_pair_decode(pob_ctx* ctx, int where, const pob_reads_t* reads1, const po
     POB_TRY(stage_out(ctx, out_cons_len, (size_t)n, &d_clen));
     POB_TRY(stage_out(ctx, out_status, (size_t)n, &d_status));
   }
+  stage_done("geometry + staging");
   if (where == POB_HOST || !d_score) POB_TRY(pob_take(ctx, (size_t)n, &d_score));
   if (where == POB_HOST || !d_stats) POB_TRY(pob_take(ctx, (size_t)n * 4, &d_stats));
   // ---- stage 1: best-path decode + base->timestep mapping of both reads (transducer.py, pair_decode.py:361-382)
@@ -253,6 +268,7 @@ int pob_pair_decode(pob_ctx* ctx, int where, const pob_reads_t* reads1, const po
   POB_CUDA(cudaMemcpyAsync(st1.data(), d_st1, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   POB_CUDA(cudaMemcpyAsync(st2.data(), d_st2, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   POB_CUDA(cudaStreamSynchronize(ctx->stream));
+  stage_done("viterbi + read-back");
   // ---- host: who is skipped before alignment, scratch geometry of the rest
   std::vector<int32_t> skip(n, 0), status(n, 0);
   const int SZ = pob_nw_slots(band_width);
@@ -313,12 +329,14 @@ int pob_pair_decode(pob_ctx* ctx, int where, const pob_reads_t* reads1, const po
   POB_CUDA(cudaMemcpyAsync(alen.data(), d_alen, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   POB_CUDA(cudaMemcpyAsync(matches.data(), d_matches, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   POB_CUDA(cudaStreamSynchronize(ctx->stream));
+  stage_done("NW + envelope + read-back");
   // ---- stage 4: joint beam search inside the envelope (BeamSearch.h:262-397 / :110-172)
   POB_CUDA(cudaMemsetAsync(d_clen, 0, (size_t)n * 4, ctx->stream));
   POB_CUDA(cudaMemsetAsync(d_score, 0, (size_t)n * 8, ctx->stream));
   POB_TRY(run_search(ctx, d1, &d2, g1, &g2, d_env, d_envoff, d_skip, &skip, beam_width, model,
                      method == POB_METHOD_ROW ? POB_MODE_ROW : POB_MODE_ROWCOL, d_consoff, d_cons, d_clen, d_score,
                      d_status));
+  stage_done("search enqueued");
   // stats: len1, len2, matches, columns
   std::vector<int32_t> stats((size_t)n * 4);
   for (int p = 0; p < n; ++p) {
@@ -341,6 +359,7 @@ int pob_pair_decode(pob_ctx* ctx, int where, const pob_reads_t* reads1, const po
     POB_CUDA(cudaMemcpyAsync(out_stats, stats.data(), stats.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   }
   POB_CUDA(cudaStreamSynchronize(ctx->stream));
+  stage_done("copy back + sync");
   return POB_OK;
 }
 
