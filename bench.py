@@ -356,12 +356,15 @@ def run_pairs(args):
         return float(t.item())
 
     step_no = [0]
+    store_lock = threading.Lock()  # one store round trip at a time per process (queue pulls and record hand-over)
+    last_bounds = [None]
 
     def drain(decode_chunk):
         """One step of the job: this rank's share of the queue.  Returns the chunks it decoded."""
         step_no[0] += 1
         q = multigpu.WorkQueue(G, chunk, store, key="pob_bench_q%d" % step_no[0])
-        return multigpu.drain_queue(q, decode_chunk, len(lanes))
+        last_bounds[0] = q.bounds
+        return multigpu.drain_queue(q, decode_chunk, len(lanes), lock=store_lock)
 
     # ---------------- device-resident leg: the job's inputs already in HBM when the timed region starts
     def dev_reads(b):
@@ -429,6 +432,7 @@ def run_pairs(args):
     value = G * args.steps / (ms_max / 1e3)
     # every pair decoded exactly once, and to the same consensus length as a single-GPU pass over the whole job
     check_rec = None
+    one_gpu = None
     lens_mine = np.full(G, -1, np.int64)
     for lo, hi, _ in mine:
         lens_mine[lo:hi] = cons_len[lo:hi]
@@ -491,9 +495,17 @@ def run_pairs(args):
         check(L.pob_pair_decode(lanes[lane].h, _lib.HOST, C.byref(v1), C.byref(v2), kind, args.beam_width, pad, 500, method,
                                 A(hs1), A(hl1) + 4 * lo, A(hs2), A(hl2) + 4 * lo, A(hc), A(hlc) + 4 * lo,
                                 A(hsc) + 8 * lo, A(hstats) + 16 * lo, A(hst) + 4 * lo), "pob_pair_decode(host)")
-        # the chunk's records: consensus strings + lengths + status, as the command line would hand them to its writer
+        # the chunk's records: consensus strings + lengths + status, as the command line would hand them to its writer.
+        # Other ranks hand them to rank 0 through the host store as soon as the chunk is done (bytes under a per-chunk
+        # key), so the hand-over overlaps the decoding of the next chunks; rank 0 collects them after its own share.
         c0, c1 = int(coff[lo]), int(coff[hi])
-        return (hlc[lo:hi].copy(), hst[lo:hi].copy(), hc[c0:c1].tobytes())
+        rec = (hlc[lo:hi].copy(), hst[lo:hi].copy(), hc[c0:c1].tobytes())
+        if use_dist and rank != 0:
+            blob = rec[0].tobytes() + rec[1].tobytes() + rec[2]
+            with store_lock:
+                store.set("pob_rec_%d_%d" % (step_no[0], lo), blob)
+            return None
+        return rec
 
     e2e_parts = {"drain_s": 0.0, "gather_s": 0.0}
 
@@ -502,11 +514,20 @@ def run_pairs(args):
         got = drain(decode_host)
         tb = time.perf_counter()
         e2e_parts["drain_s"] += tb - ta
-        if use_dist:
-            out = [None] * world if rank == 0 else None
-            dist.gather_object(got, out, dst=0, group=host_group)
+        if use_dist and rank == 0:
+            # results gathered on the host: every chunk rank 0 did not decode itself arrives through the store
+            have = {lo for lo, _, _ in got}
+            bounds = last_bounds[0]
+            for k in range(len(bounds) - 1):
+                lo, hi = bounds[k], bounds[k + 1]
+                if lo in have:
+                    continue
+                key = "pob_rec_%d_%d" % (step_no[0], lo)
+                blob = store.get(key)  # blocks until the owning rank has set it
+                store.delete_key(key)
+                m = 4 * (hi - lo)
+                got.append((lo, hi, (np.frombuffer(blob[:m], np.int32), np.frombuffer(blob[m:2 * m], np.int32), blob[2 * m:])))
             e2e_parts["gather_s"] += time.perf_counter() - tb
-            return out
         return [got]
 
     for _ in range(0 if heavy else max(1, min(args.warmup, 2))):

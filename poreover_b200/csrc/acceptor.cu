@@ -148,13 +148,15 @@ int pob_acceptor_launch(pob_ctx* ctx, const pob_reads& rd, const uint8_t* labels
   const size_t smem = (size_t)3 * SZ * sizeof(double);
   if (smem > 200 * 1024) return POB_EUNSUPPORTED;
   pob_prof_scope ps(ctx, POB_K_ACCEPTOR);
+  // the attribute is a limit shared by all host threads of the process: always the same (largest) value, so two
+  // threads launching at once cannot lower it under each other
   if (rd.dtype == POB_F32) {
-    POB_CUDA(cudaFuncSetAttribute(acceptor_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    POB_CUDA(cudaFuncSetAttribute(acceptor_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     acceptor_kernel<float><<<rd.n, ACC_THREADS, smem, ctx->stream>>>((const float*)rd.data, rd.row_off, rd.row_len, rd.rc,
                                                                       rd.n_states, rd.layout, labels, lab_off, band, SZ,
                                                                       bp_off, bp, cum, out_path, out_status);
   } else {
-    POB_CUDA(cudaFuncSetAttribute(acceptor_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    POB_CUDA(cudaFuncSetAttribute(acceptor_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     acceptor_kernel<double><<<rd.n, ACC_THREADS, smem, ctx->stream>>>((const double*)rd.data, rd.row_off, rd.row_len,
                                                                        rd.rc, rd.n_states, rd.layout, labels, lab_off,
                                                                        band, SZ, bp_off, bp, cum, out_path, out_status);

@@ -415,8 +415,8 @@ int pob_nw_launch(pob_ctx* ctx, const uint8_t* seq1, const int64_t* off1, const 
   if (n <= 0) return POB_OK;
   const int smem = pob_nw_smem_bytes(SZ);
   if (smem > 200 * 1024) return POB_EUNSUPPORTED;
-  if (smem > 48 * 1024)
-    POB_CUDA(cudaFuncSetAttribute(nw_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  // a limit shared by all host threads of the process: always the same (largest) value (see acceptor.cu)
+  POB_CUDA(cudaFuncSetAttribute(nw_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   {
     pob_prof_scope ps(ctx, POB_K_NW_FILL);
     static const bool generic = getenv("POB_DEBUG_NW_GENERIC") != nullptr;

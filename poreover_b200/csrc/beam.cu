@@ -35,6 +35,8 @@
 // with compute-sanitizer racecheck / synccheck on tools/sanitize_case.py (all traversals, trees and widths).
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "launch.cuh"
 
@@ -179,6 +181,7 @@ enum { SH_NB = 0, SH_NUSED, SH_FQH, SH_FQT, SH_AFREE, SH_ORDER, SH_TID, SH_STAMP
 // to LDS/STS (a pointer loaded from memory would be a generic pointer and cost a second, slower load).
 struct EngState {
   int W, NP, RQ, EMAX, mode, noreclaim, inspect_every, longq;
+  int nbase;  // letters of the alphabet (states - 1): children per node
   NodeHdr* hdr;
   char* win[2];
   int32_t* freelist;
@@ -1099,7 +1102,7 @@ struct Engine {
     // -- phase X1: classify the children of the beam.  A retired child that comes back is marked active right
     //    away so that the queue inspection of the next phase sees its queue entry as stale.
     const int xb = tid >> 2, xc = tid & 3;
-    const bool xmine = tid < 4 * nb;
+    const bool xmine = tid < 4 * nb && xc < g_es.nbase;  // alphabets of fewer than four letters leave child threads idle
     int a = -1, kind = KID_ACTIVE;
     if (xmine) {
       a = beam[xb];
@@ -1188,7 +1191,7 @@ struct Engine {
     }
     if (xmine) {
       const int my_tid = first ? sh[SH_TID] + fbase : a_tid[a];  // trace id of the beam node (my parent)
-      if (tid == 4 * nb - 1) { sh[SH_TOTALLOC] = obase + (kind == KID_FRESH); sh[SH_TOTFIRST] = fbase + first; }
+      if (tid == 4 * (nb - 1) + g_es.nbase - 1) { sh[SH_TOTALLOC] = obase + (kind == KID_FRESH); sh[SH_TOTFIRST] = fbase + first; }
       if (kind != KID_ACTIVE) {
         const int ai = atomicSub(&sh[SH_AFREE], 1) - 1;
         int pi = -1;
@@ -1238,7 +1241,7 @@ struct Engine {
           a_tid[a] = sh[SH_TID]++;
           trace[a_tid[a]] = ((uint32_t)a_ptid[a] << 2) | (uint32_t)a_last[a];
         }
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < g_es.nbase; ++c) {
           const int ks = a_kid[4 * a + c];
           int ka = -1;
           if (ks >= 0) { const int x = slot2e[ks]; if (x >= 0 && a_order[x] == a_kido[4 * a + c]) ka = x; }
@@ -1292,6 +1295,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
   if (tid == 0) {
     g_es.W = G.W; g_es.NP = G.NP; g_es.RQ = G.RQ; g_es.EMAX = G.EMAX; g_es.mode = G.mode;
     g_es.noreclaim = G.dbg_noreclaim; g_es.inspect_every = G.inspect_every; g_es.longq = G.dbg_long;
+    g_es.nbase = G.r[0].n_states - 1;
     g_es.mir_off = G.mir_off; g_es.mdepth = G.mir_depth; g_es.mdmask = G.mir_depth - 1;
     g_es.cap[0] = G.CAP0; g_es.cap[1] = G.CAP1; g_es.mask[0] = G.CAP0 - 1; g_es.mask[1] = G.CAP1 - 1;
     g_es.rv[0] = make_view(G.r[0], item);
@@ -1633,8 +1637,9 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
                     const int64_t* out_off, uint8_t* out_seq, int32_t* out_len, double* out_score,
                     int32_t* out_status) {
   if (n_total <= 0) return POB_OK;
-  if (W < 4 || W > 100) return POB_EUNSUPPORTED;
-  if (r1.n_states != 5 || (r2 && r2->n_states != 5)) return POB_EUNSUPPORTED;
+  if (W < 1) return POB_EINVAL;
+  if (W > 100) return POB_EUNSUPPORTED;  // one thread per (node, read) of the expanded beam: 2 * 5 W <= 1024
+  if (r1.n_states < 2 || r1.n_states > 5 || (r2 && r2->n_states != r1.n_states)) return POB_EUNSUPPORTED;
   BeamParams P;
   memset(&P, 0, sizeof(P));
   P.r[0] = r1;
@@ -1643,7 +1648,8 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   P.n_items = n_items; P.W = W; P.mode = mode;
   // active slots: the expanded beam (W nodes and their 4 W children), rounded so that the (node, read) threads fill
   // whole warps (W = 25: 128 slots, 256 threads, 85 registers per thread at three CTAs per SM)
-  P.EMAX = ((5 * W > 8 ? 5 * W : 8) + 15) / 16 * 16;
+  // (the first step expands all four seeds whatever W is: at least 4 + 16 slots)
+  P.EMAX = ((5 * W > 20 ? 5 * W : 20) + 15) / 16 * 16;
   // Node pool: the expanded beam (5W) plus retired nodes whose windows can still be read.  About W nodes
   // retire per step and stay readable for one band width, so the pool scales with W x widest band; an
   // overflow is flagged per item (POB_ST_POOL_OVERFLOW), never silent.
@@ -1731,6 +1737,11 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   }
   else if (threads <= 512) { kern = ctc ? beam_kernel<M0, 512, 1> : beam_kernel<M1, 512, 1>; }
   else { kern = ctc ? beam_kernel<M0, 1024, 1> : beam_kernel<M1, 1024, 1>; }
+  // The dynamic-shared-memory size and carve-out are attributes of the kernel FUNCTION, shared by every host thread of
+  // the process (the command line keeps two GPU calls in flight): set them and launch under one lock, so that another
+  // thread's smaller setting cannot land between this call's cudaFuncSetAttribute and its launch.
+  static std::mutex launch_mu;
+  std::unique_lock<std::mutex> launch_lock(launch_mu);
   POB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // leave most of the unified L1/shared array to L1 (window entries are served from it) but make sure the
   // shared-memory carve-out does not cap residency
@@ -1786,6 +1797,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
     kern<<<grid, threads, smem, ctx->stream>>>(P);
   }
   POB_CUDA(cudaGetLastError());
+  launch_lock.unlock();
   {
     pob_prof_scope ps(ctx, POB_K_BACKTRACE);
     backtrace_kernel<<<(n_total + 127) / 128, 128, 0, ctx->stream>>>(trace, trace_off, top, out_off, n_total, out_seq,

@@ -118,9 +118,9 @@ int search_entry(pob_ctx* ctx, int where, const pob_reads_t* r1, const pob_reads
                  const int64_t* env_off, int W, int model, int mode, const int64_t* out_off, uint8_t* out_seq,
                  int32_t* out_len, double* out_score, int32_t* out_status) {
   if (!ctx) return POB_EINVAL;
-  POB_TRY(check_reads(r1, 5, 5));
+  POB_TRY(check_reads(r1, 2, 5));
   if (r2) {
-    POB_TRY(check_reads(r2, 5, 5));
+    POB_TRY(check_reads(r2, 2, 5));
     if (r2->n != r1->n || r2->dtype != r1->dtype) return POB_EINVAL;
   }
   if (r1->dtype != POB_F32 && r1->dtype != POB_F64) return POB_EINVAL;
@@ -270,16 +270,20 @@ int pob_pair_decode(pob_ctx* ctx, int where, const pob_reads_t* reads1, const po
   POB_CUDA(cudaStreamSynchronize(ctx->stream));
   stage_done("viterbi + read-back");
   // ---- host: who is skipped before alignment, scratch geometry of the rest
-  std::vector<int32_t> skip(n, 0), status(n, 0);
+  std::vector<int32_t> skip(n, 0), status(n, 0), one_empty(n, 0);
   const int SZ = pob_nw_slots(band_width);
   std::vector<int64_t> m_off(n + 1), rb_off(n + 1), aln_off(n + 1), env_off(n + 1), cons_off(n + 1);
   m_off[0] = rb_off[0] = aln_off[0] = env_off[0] = 0;
   for (int p = 0; p < n; ++p) {
     int st = (st1[p] | st2[p]) & (POB_ST_MAPPING_WRAP | POB_ST_EMPTY);
     const int64_t l1 = len1[p], l2 = len2[p];
-    if (l1 == 0 || l2 == 0) st |= POB_ST_EMPTY;
     const int64_t dl = l1 > l2 ? l1 - l2 : l2 - l1;
     if (dl > 1000) st |= POB_ST_SKIPPED_LENGTH;  // pair_decode.py:372-375
+    // An empty basecall: the banded aligner's row loop never runs (align.pyx:120) and its traceback only drains the
+    // other sequence, so the alignment is all gaps, the identity 0 and the pair is skipped by identity
+    // (pair_decode.py:391-398).  Two empty basecalls divide 0 by 0: that pool task dies (POB_ST_EMPTY).
+    if (l1 == 0 && l2 == 0) st |= POB_ST_EMPTY;
+    else if ((l1 == 0 || l2 == 0) && !(st & POB_ST_SKIPPED_LENGTH)) { st |= POB_ST_SKIPPED_IDENTITY; one_empty[p] = 1; }
     status[p] = st;
     skip[p] = st != 0;
     const int64_t D = skip[p] ? 0 : l1 + l2 - 1;
@@ -343,7 +347,7 @@ int pob_pair_decode(pob_ctx* ctx, int where, const pob_reads_t* reads1, const po
     stats[4 * p] = len1[p]; stats[4 * p + 1] = len2[p];
     const bool aligned = !(status[p] != 0);
     stats[4 * p + 2] = aligned ? matches[p] : 0;
-    stats[4 * p + 3] = aligned ? alen[p] : 0;
+    stats[4 * p + 3] = aligned ? alen[p] : (one_empty[p] ? len1[p] + len2[p] : 0);  // all-gap alignment: 0 matches of l columns
   }
   if (where == POB_HOST) {
     if (out_stats) memcpy(out_stats, stats.data(), stats.size() * 4);

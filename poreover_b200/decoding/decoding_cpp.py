@@ -13,14 +13,22 @@ def _prep(y_):
 
 
 def _check_alphabet(alphabet_, y):
-    if len(alphabet_) != 4 or y.shape[1] != 5:
-        raise NotImplementedError(
-            "the GPU searches are built for the 4-letter alphabet (5 states); got alphabet %r, %d states"
-            % (alphabet_, y.shape[1]))
+    """The reference takes any alphabet (decoding_cpp.pyx:88, :107: the gap state is column len(alphabet_)); the GPU
+    searches handle one to four letters (two to five states)."""
+    if y.ndim != 2 or y.shape[1] != len(alphabet_) + 1:
+        raise ValueError("alphabet %r needs %d states (letters + blank), the matrix has %s"
+                         % (alphabet_, len(alphabet_) + 1, y.shape[1:] if y.ndim > 1 else y.shape))
+    if not 1 <= len(alphabet_) <= 4:
+        raise NotImplementedError("the GPU searches handle alphabets of one to four letters; got %r" % (alphabet_,))
 
 
 def _spell(seq, alphabet_):
-    return seq if alphabet_ == "ACGT" else seq.translate(str.maketrans("ACGT", alphabet_))
+    """the kernels spell base index k as "ACGT"[k]; translate to the caller's alphabet"""
+    return seq if alphabet_ == "ACGT" else seq.translate(str.maketrans("ACGT"[:len(alphabet_)], alphabet_))
+
+
+def _indices(label_, alphabet_):
+    return label_ if alphabet_ == "ACGT" else label_.translate(str.maketrans(alphabet_, "ACGT"[:len(alphabet_)]))
 
 
 def cpp_beam_search(y_, beam_width_=25, alphabet_="ACGT", model_="ctc"):
@@ -46,8 +54,7 @@ def cpp_forward(y_, label_, alphabet_="ACGT", model_="ctc"):
     """decoding_cpp.pyx:49-65 -> forward (PrefixTree.h:710-759): log-probability of `label_` given y_."""
     y = _prep(y_)
     _check_alphabet(alphabet_, y)
-    lab = label_ if alphabet_ == "ACGT" else label_.translate(str.maketrans(alphabet_, "ACGT"))
-    return float(batch.forward_batch([y], [lab], model_)[0])
+    return float(batch.forward_batch([y], [_indices(label_, alphabet_)], model_)[0])
 
 
 def cpp_viterbi_acceptor(y_, label_, band_size=1000, alphabet_="ACGT"):
@@ -55,8 +62,7 @@ def cpp_viterbi_acceptor(y_, label_, band_size=1000, alphabet_="ACGT"):
     len(alphabet_) for blank or the index of the base emitted there."""
     y = _prep(y_)
     _check_alphabet(alphabet_, y)
-    lab = label_ if alphabet_ == "ACGT" else label_.translate(str.maketrans(alphabet_, "ACGT"))
-    paths, st = batch.viterbi_acceptor_batch([y], [lab], band_size)
+    paths, st = batch.viterbi_acceptor_batch([y], [_indices(label_, alphabet_)], band_size)
     if st[0] & batch._lib.ST_UNSET_BAND:
         raise RuntimeError("viterbi_acceptor: the label cannot be placed inside the band "
                            "(the reference's traceback does not terminate here, Forward.h:107-116)")

@@ -151,15 +151,19 @@ def _decode_pairs_staged(args, meta, m1, m2, kind, device):
         # the basecaller), then the banded acceptor turns each basecall into a path; mapping on the host
         seq1 = batch.beam_search_batch(m1, 25, "ctc", device=device)[0]
         seq2 = batch.beam_search_batch(m2, 25, "ctc", rc=rc2, device=device)[0]
-        if any(len(x) == 0 for x in seq1 + seq2):
-            raise IndexError("viterbi_acceptor: empty basecall (the reference reads label_int[0], Forward.h:51)")
-        pth1, sa1 = batch.viterbi_acceptor_batch(m1, seq1, 1000, device=device)
-        pth2, sa2 = batch.viterbi_acceptor_batch(m2, seq2, 1000, rc=rc2, device=device)
+        # an empty basecall makes the reference's acceptor read label_int[0] (Forward.h:51): that pool task dies and
+        # only its pair is lost (pair_decode.py:295 has no error callback); the acceptor gets a placeholder label and
+        # the pair is dropped below
+        dead = [len(a) == 0 or len(b) == 0 for a, b in zip(seq1, seq2)]
+        if any(dead):
+            _warn("%d pair(s) dropped: empty --single beam basecall" % sum(dead))
+        pth1, sa1 = batch.viterbi_acceptor_batch(m1, [s or "A" for s in seq1], 1000, device=device)
+        pth2, sa2 = batch.viterbi_acceptor_batch(m2, [s or "A" for s in seq2], 1000, rc=rc2, device=device)
         map1 = [np.asarray(get_sequence_mapping(p, kind)[0], dtype=np.int64) for p in pth1]
         map2 = [np.asarray(get_sequence_mapping(p, kind)[0], dtype=np.int64) for p in pth2]
         wrap = batch._lib.ST_MAPPING_WRAP
-        st1 = np.array([wrap if (len(m) != len(s) or (a & batch._lib.ST_UNSET_BAND)) else 0
-                        for m, s, a in zip(map1, seq1, sa1)])
+        st1 = np.array([wrap if (len(m) != len(s) or (a & batch._lib.ST_UNSET_BAND) or d) else 0
+                        for m, s, a, d in zip(map1, seq1, sa1, dead)])
         st2 = np.array([wrap if (len(m) != len(s) or (a & batch._lib.ST_UNSET_BAND)) else 0
                         for m, s, a in zip(map2, seq2, sa2)])
     else:
@@ -167,13 +171,15 @@ def _decode_pairs_staged(args, meta, m1, m2, kind, device):
         seq2, map2, _, st2 = batch.viterbi_batch(m2, kind, rc=rc2, device=device)
     live = []
     for k, (in_path, path1, path2, _) in enumerate(meta):
-        if (st1[k] | st2[k]) & batch._lib.ST_MAPPING_WRAP:
-            continue  # the reference's assertion (pair_decode.py:379 / :382) fires and the pool drops the pair
         summary = {'read1': in_path[0], 'read2': in_path[1], 'length1': len(seq1[k]), 'length2': len(seq2[k])}
-        if abs(len(seq1[k]) - len(seq2[k])) > 1000:
+        if abs(len(seq1[k]) - len(seq2[k])) > 1000:  # checked before the mapping assertions (pair_decode.py:372-375)
             summary['skipped'] = 1
             out[k] = [summary]
             continue
+        if (st1[k] | st2[k]) & batch._lib.ST_MAPPING_WRAP:
+            continue  # the reference's assertion (pair_decode.py:379 / :382) fires and the pool drops the pair
+        if len(seq1[k]) == 0 and len(seq2[k]) == 0:
+            continue  # 0 / 0 identity: the task dies in the reference
         live.append(k)
     if not live:
         return out
@@ -208,28 +214,60 @@ def _decode_pairs_staged(args, meta, m1, m2, kind, device):
         if not getattr(args, "skip_matches", False):
             it1.append(m1[k]); it2.append(m2[k]); itenv.append(env); owner.append((k, 0))
             continue
-        anchors, boxes = _boxes_and_anchors(arrs[k], map1[k], map2[k], U[k], V[k], args.skip_threshold)
+        # a pair without anchors (assertion, pair_decode.py:431) or with an empty box (IndexError, :516) kills its own
+        # pool task in the reference and nothing else: the pair is dropped, the rest of the chunk goes on
+        try:
+            anchors, boxes = _boxes_and_anchors(arrs[k], map1[k], map2[k], U[k], V[k], args.skip_threshold)
+            mine = []
+            y2 = m2[k]
+            for b in boxes:
+                e = env[b[0]:b[1]].copy()
+                if len(e) == 0:
+                    raise IndexError("index 0 is out of bounds for axis 0 with size 0")  # pair_decode.py:516
+                v0, v1 = int(e[0, 0]), int(e[-1, 1])
+                # read 2 is a reverse-complement VIEW here: logical rows [v0, v1) are physical rows [V-v1, V-v0)
+                y2_ = y2[V[k] - v1:V[k] - v0] if args.reverse_complement else y2[v0:v1]
+                mine.append((m1[k][b[0]:b[1]], y2_, e - v0, (k, b[0])))
+        except (AssertionError, IndexError) as e:
+            _warn("pair %s %s dropped: %s" % (meta[k][0][0], meta[k][0][1], e))
+            out[k] = None
+            pieces.pop(k)
+            continue
         pieces[k].extend(anchors)
-        y2 = m2[k]
-        for b in boxes:
-            e = env[b[0]:b[1]].copy()
-            if len(e) == 0:
-                raise IndexError("index 0 is out of bounds for axis 0 with size 0")  # pair_decode.py:516 on an empty box
-            v0, v1 = int(e[0, 0]), int(e[-1, 1])
-            # read 2 is a reverse-complement VIEW here: logical rows [v0, v1) are physical rows [V-v1, V-v0)
-            y2_ = y2[V[k] - v1:V[k] - v0] if args.reverse_complement else y2[v0:v1]
-            it1.append(m1[k][b[0]:b[1]]); it2.append(y2_); itenv.append(e - v0); owner.append((k, b[0]))
-    seqs, _, _ = batch.beam_search_2d_batch(it1, it2, itenv, args.beam_width, model, method,
-                                            rc2=np.full(len(it1), 1 if args.reverse_complement else 0, dtype=np.uint8),
-                                            device=device)
+        for a_, b_, e_, o_ in mine:
+            it1.append(a_); it2.append(b_); itenv.append(e_); owner.append(o_)
+    if not it1:
+        return out
+    seqs, _, st_search = batch.beam_search_2d_batch(it1, it2, itenv, args.beam_width, model, method,
+                                                    rc2=np.full(len(it1), 1 if args.reverse_complement else 0, dtype=np.uint8),
+                                                    device=device)
+    for (k, _), s_ in zip(owner, st_search):
+        _warn_status(meta[k][0], int(s_))
     for (k, start), sq in zip(owner, seqs):
         pieces[k].append((start, sq))
     for k in todo:
+        if k not in pieces:
+            continue
         in_path, path1, path2, _ = meta[k]
         joined = ''.join(x[1] for x in sorted(pieces[k]))  # by first signal index, then sequence (:522)
         out[k] = (fasta_format(in_path[0], seq1[k]) + fasta_format(in_path[1], seq2[k]),
                   fasta_format('consensus;{};{}'.format(path1.stem, path2.stem), joined), out[k])
     return out
+
+
+def _warn(msg):
+    logging.getLogger("poreover_b200").warning("WARNING: " + msg)
+
+
+def _warn_status(in_path, status):
+    """The searches flag what they could not do the reference's way; none of it may pass silently."""
+    L = batch._lib
+    if status & L.ST_POOL_OVERFLOW:
+        _warn("pair %s %s: the search's node pool overflowed (very wide envelope): its consensus may deviate from the "
+              "reference's" % (in_path[0], in_path[1]))
+    if status & (L.ST_SHORT_BEAM_SKIP | L.ST_UNSET_BAND):
+        _warn("pair %s %s: the envelope drives the reference's search into undefined behaviour (BeamSearch.h:309, "
+              ":317); a defined rule was used instead" % (in_path[0], in_path[1]))
 
 
 def _paths(args, in_path):
@@ -243,7 +281,32 @@ def _paths(args, in_path):
 
 def load_pairs(args, sub):
     """Host stage of a chunk of pairs: the files of both reads -> packed log-probability batches (or, for the staged
-    flags, per-read arrays).  No GPU work; runs on the loader threads while the previous chunk is being decoded."""
+    flags, per-read arrays).  No GPU work; runs on the loader threads while the previous chunk is being decoded.
+    A pair whose files cannot be loaded (missing, corrupt, wrong shape) is dropped with a warning, like the pool task
+    that dies alone in the reference (pair_decode.py:295); the payload carries the chunk positions that survived."""
+    try:
+        return _load_pairs(args, sub) + (list(range(len(sub))), len(sub))
+    except NotImplementedError:
+        raise
+    except Exception as e:  # noqa: BLE001 -- find the pair(s) that cannot be loaded
+        if len(sub) == 1:
+            _warn("pair %s dropped: %s: %s" % (" ".join(sub[0][:2]), type(e).__name__, e))
+            return [], [], [], None, [], 1
+        keep = []
+        for k, in_path in enumerate(sub):
+            try:
+                _load_pairs(args, [in_path])
+                keep.append(k)
+            except NotImplementedError:
+                raise
+            except Exception as e1:  # noqa: BLE001
+                _warn("pair %s dropped: %s: %s" % (" ".join(in_path[:2]), type(e1).__name__, e1))
+        if not keep:
+            return [], [], [], None, [], len(sub)
+        return _load_pairs(args, [sub[k] for k in keep]) + (keep, len(sub))
+
+
+def _load_pairs(args, sub):
     from .. import ingest
     meta, files1, files2 = [], [], []
     for in_path in sub:
@@ -267,6 +330,13 @@ def load_pairs(args, sub):
         raise NotImplementedError("flip-flop pair decoding is out of scope (README.md:97 of the reference)")
     for x, y in zip(b1.kinds, b2.kinds):
         assert x == y
+    if b1.dtype != b2.dtype:
+        # one side came from float64 files: widen the other (the reference widens everything, transducer.py:16)
+        wide = lambda b: b if b.np_dtype == np.float64 else batch.ReadBatch(  # noqa: E731
+            [b.data[o:o + l].astype(np.float64) for o, l in zip(b.row_off[:-1], b.lens)], rc=b.rc, layout=b.layout)
+        k1, k2 = b1.kinds, b2.kinds
+        b1, b2 = wide(b1), wide(b2)
+        b1.kinds, b2.kinds = k1, k2
     kind = b1.kinds[0] if b1.kinds else None
     return [m + (kind,) for m in meta], b1, b2, kind
 
@@ -274,18 +344,30 @@ def load_pairs(args, sub):
 def decode_loaded(args, payload, device=None, fmt=True):
     """GPU stage of a chunk: load_pairs' payload -> pair_decode_helper-style results, in the chunk's order.
     With fmt=False the records are returned raw, for format_decoded on another thread."""
-    meta, m1, m2, kind = payload
+    meta, m1, m2, kind = payload[:4]
+    keep, total = (payload[4], payload[5]) if len(payload) > 4 else (list(range(len(meta))), len(meta))
     if len(meta) == 0:
-        return []
+        raw = ("done", [None] * total)
+        return raw[1] if fmt else raw
     if kind == 'flipflop':
         raise NotImplementedError("flip-flop pair decoding is out of scope (README.md:97 of the reference)")
     if _staged(args):
-        done = _decode_pairs_staged(args, meta, m1, m2, kind, device)
+        done = _scatter(_decode_pairs_staged(args, meta, m1, m2, kind, device), keep, total)
         return done if fmt else ("done", done)
     res = batch.pair_decode_batch(m1, m2, kind=kind, beam_width=args.beam_width, padding=args.padding,
                                   method=args.beam_search_method, device=device)  # rc and layout travel in the batches
-    raw = ("raw", meta, res)
+    raw = ("raw", meta, res, keep, total)
     return format_decoded(args, raw) if fmt else raw
+
+
+def _scatter(results, keep, total):
+    """results of the pairs that loaded -> the chunk's order, None where a pair was dropped"""
+    if len(keep) == total:
+        return results
+    out = [None] * total
+    for k, r in zip(keep, results):
+        out[k] = r
+    return out
 
 
 def format_decoded(args, raw):
@@ -295,16 +377,18 @@ def format_decoded(args, raw):
         return []
     if raw[0] == "done":
         return raw[1]
-    _, meta, res = raw
+    _, meta, res = raw[:3]
+    keep, total = (raw[3], raw[4]) if len(raw) > 3 else (list(range(len(meta))), len(meta))
     results = [None] * len(meta)
     for k, (r, (in_path, path1, path2, _)) in enumerate(zip(res, meta)):
-        if r["status"] & (batch._lib.ST_MAPPING_WRAP | batch._lib.ST_EMPTY):
-            continue  # the reference's assertion fires and the pool drops the pair silently
         summary = {'read1': in_path[0], 'read2': in_path[1], 'length1': r["length1"], 'length2': r["length2"]}
-        if r["status"] & batch._lib.ST_SKIPPED_LENGTH:
+        if r["status"] & batch._lib.ST_SKIPPED_LENGTH:  # checked before the mapping assertions (pair_decode.py:372-375)
             summary['skipped'] = 1
             results[k] = [summary]
             continue
+        if r["status"] & (batch._lib.ST_MAPPING_WRAP | batch._lib.ST_EMPTY):
+            continue  # the reference's assertion fires and the pool drops the pair silently
+        _warn_status(in_path, r["status"])
         summary['sequence_identity'] = r["identity"]
         if r["skipped"]:
             summary['skipped'] = 1
@@ -315,7 +399,7 @@ def format_decoded(args, raw):
             fasta_format(in_path[0], r["basecall1"]) + fasta_format(in_path[1], r["basecall2"]),
             fasta_format('consensus;{};{}'.format(path1.stem, path2.stem), r["consensus"]),
             summary)
-    return results
+    return _scatter(results, keep, total)
 
 
 def decode_pairs(args, pair_list, device=None, chunk=4096):

@@ -45,13 +45,13 @@ class WorkQueue:
         return self.bounds[k], self.bounds[k + 1]
 
 
-def drain_queue(queue, work, lanes=2):
+def drain_queue(queue, work, lanes=2, lock=None):
     """Empty this rank's share of `queue` with `lanes` host threads (GPU calls in flight): each thread pulls the next
     chunk (lo, hi) and runs work(lo, hi, lane).  Returns [(lo, hi, result)] in the order this rank pulled them.  The
     queue is shared by all ranks of the job (fetch-and-add on the store), so a rank that finishes early simply pulls
     more; an exception in any lane stops the others after their current chunk and is re-raised here."""
     import threading
-    lock, out, errs = threading.Lock(), [], []
+    lock, out, errs = lock or threading.Lock(), [], []  # pass `lock` to share the store connection with other users
 
     def lane_loop(lane):
         try:
@@ -109,18 +109,32 @@ def run_sharded(items, cost, process_chunk, chunk=256, group=None, store=None, l
     else:
         stream = Lookahead(q.next, lambda c: load_chunk([items[i] for i in order[c[0]:c[1]]]), process_chunk,
                            workers=workers)
-    for c, res in stream:
-        if finish_chunk is not None:
-            res = finish_chunk(res)
-        for i, r in zip(order[c[0]:c[1]], res):
-            mine[i] = r
+    failure = None
+    try:
+        for c, res in stream:
+            if finish_chunk is not None:
+                res = finish_chunk(res)
+            for i, r in zip(order[c[0]:c[1]], res):
+                mine[i] = r
+    except BaseException as e:  # noqa: BLE001
+        if world == 1:
+            raise
+        # the other ranks are (or will be) waiting in the gather below: join it with the error instead of leaving them
+        # blocked until the process group times out, then re-raise here; rank 0 raises for everyone
+        failure = e
+        mine = {"__error__": "rank %d: %s: %s" % (rank, type(e).__name__, e)}
     if world == 1:
         return [mine.get(i) for i in range(len(items))]
     import torch.distributed as dist
     gathered = [None] * world if rank == 0 else None
     dist.gather_object(mine, gathered, dst=0, group=group)
+    if failure is not None:
+        raise failure
     if rank != 0:
         return None
+    errors = [part["__error__"] for part in gathered if "__error__" in part]
+    if errors:
+        raise RuntimeError("decoding failed on another rank: " + "; ".join(errors))
     out = [None] * len(items)
     for part in gathered:
         for i, r in part.items():

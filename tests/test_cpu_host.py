@@ -127,6 +127,22 @@ def test_work_queue_two_ranks_gloo(tmp_path):
     assert {x[2] for x in r["out"]} == {0, 1}  # both ranks pulled work from the shared queue
 
 
+def test_strong_scaling_step_and_failure_two_ranks_gloo(tmp_path):
+    """bench.py's strong-scaling step on the host side (two lanes per rank on one queue, records to rank 0 through the
+    store), run_sharded when a rank fails (nobody hangs) and a second queue in the same process group."""
+    res = tmp_path / "strong.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "tests", "_strong_worker.py"), str(res)]
+    subprocess.run(cmd, check=True, timeout=300, capture_output=True)
+    rep = json.load(open(res))
+    assert len(rep["steps"]) == 3
+    for s in rep["steps"]:
+        assert s["covered"] == 1000 and 0 < s["own_chunks"] < s["chunks"]  # every pair once; both ranks pulled work
+    assert rep["errors"][1].startswith("ValueError: boom")
+    assert rep["errors"][0].startswith("RuntimeError: decoding failed on another rank") and "boom" in rep["errors"][0]
+    assert rep["second_run"] == [2 * x for x in range(23)]
+
+
 def test_get_anchors_matches_reference_loop():
     """The vectorised get_anchors against a literal transcription of the reference loop's rules on random alignments."""
     from poreover_b200.decoding.pair_decode import get_anchors

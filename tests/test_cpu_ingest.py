@@ -259,14 +259,24 @@ def test_load_pairs_host_stage(tmp_path):
     pairs = [list(synth.save_pair(str(tmp_path), k, 150 + 10 * k)) for k in range(3)]
     args = Namespace(dir=str(tmp_path), basecaller="bonito", reverse_complement=True, alignment="banded",
                      skip_matches=False, diagonal_envelope=False, single="viterbi")
-    meta, b1, b2, kind = gpd.load_pairs(args, pairs)
+    meta, b1, b2, kind, keep, total = gpd.load_pairs(args, pairs)
+    assert keep == [0, 1, 2] and total == 3
     assert kind == "bonito" and b1.n == b2.n == 3 and b1.rc is None and b2.rc.tolist() == [1, 1, 1]
     assert b1.layout == b2.layout == _lib.BLANK_FIRST
     assert [m[0] for m in meta] == pairs and meta[0][3] == "bonito"
     args.skip_matches = True  # staged flags: per-read arrays in the reference's column order
-    meta, m1, m2, kind = gpd.load_pairs(args, pairs)
+    meta, m1, m2, kind, keep, total = gpd.load_pairs(args, pairs)
     ref = _reference_arrays([os.path.join(str(tmp_path), p[0]) for p in pairs], "bonito")
     assert all(np.array_equal(a, b) for a, b in zip(m1, ref)) and len(m2) == 3
+    # a pair whose file is missing or corrupt is dropped alone (the reference's pool task dies alone, pair_decode.py:295)
+    args.skip_matches = False
+    (tmp_path / "broken_1.npy").write_bytes(b"not an npy file")
+    bad = pairs[:1] + [["broken_1.npy", pairs[1][1]], ["missing_1.npy", "missing_2.npy"]] + pairs[1:]
+    meta, b1, b2, kind, keep, total = gpd.load_pairs(args, bad)
+    assert keep == [0, 3, 4] and total == 5 and b1.n == 3 and [m[0] for m in meta] == pairs
+    assert gpd._scatter(["a", "b", "c"], keep, total) == ["a", None, None, "b", "c"]
+    meta, b1, b2, kind, keep, total = gpd.load_pairs(args, [["missing_1.npy", "missing_2.npy"]])
+    assert keep == [] and total == 1 and len(meta) == 0
 
 
 def test_real_logits_fixture_through_the_batched_loader(tmp_path):
