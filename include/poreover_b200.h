@@ -47,7 +47,7 @@ enum {
   POB_ECUDA = -2,       /* CUDA runtime error; pob_last_cuda_error() has the text */
   POB_ENOMEM = -3,      /* device or host allocation failed */
   POB_EALIGN = -4,      /* reserved */
-  POB_EUNSUPPORTED = -5 /* legal in the reference but outside this build (e.g. beam width > 400) */
+  POB_EUNSUPPORTED = -5 /* legal in the reference but outside this build (beam width > 100, more than 5 states) */
 };
 
 /* per-item status bits written by the searches (out_status) */
@@ -218,6 +218,21 @@ int pob_pair_decode(pob_ctx* ctx, int where, const pob_reads_t* reads1, const po
                     int beam_width, int padding, int band_width, int method, uint8_t* out_seq1, int32_t* out_len1,
                     uint8_t* out_seq2, int32_t* out_len2, uint8_t* out_cons, int32_t* out_cons_len,
                     double* out_score, int32_t* out_stats, int32_t* out_status);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-side batched reader of .npy probability tables (no GPU work; native threads instead of one Python-level
+ * np.load per file).
+ * replaces: the np.load of decode.load_logits (decode.py:41-51) / model_from_trace's bonito branch (decode.py:76-80)
+ *           for plain 2-D little-endian float32 C-order files; the logarithm (decode.py:45) stays with the caller.
+ * pob_npy_probe: per file, rows / cols / byte offset of the data and a flag (POB_NPY_*); first_row_sum[i] (may be NULL)
+ *   is the float32 left-to-right sum of the first row, what np.isclose(np.sum(row), 1) looks at (decode.py:43).
+ * pob_npy_read : copies file i's rows[i] x cols float32 payload to dst + row_off[i] * cols and zeroes the alignment
+ *   rows up to row_off[i + 1]; ok[i] (may be NULL) = 1 when the whole payload was read. */
+enum { POB_NPY_F32_2D = 0, POB_NPY_OTHER = 1, POB_NPY_UNREADABLE = 2 };
+int pob_npy_probe(const char* const* paths, int n, int threads, int64_t* rows, int64_t* cols, int64_t* data_off,
+                  int32_t* flags, float* first_row_sum);
+int pob_npy_read(const char* const* paths, int n, int threads, const int64_t* rows, int64_t cols, const int64_t* data_off,
+                 const int64_t* row_off, float* dst, int32_t* ok);
 
 /* Counters of the last pob_pair_decode / pob_beam_search_2d call on this context (for roofline math):
  * [0] forward cell updates (update_prob calls), [1] search steps, [2] kernels launched since reset. */

@@ -61,6 +61,8 @@ SIGNATURES = {
     "pob_viterbi_acceptor": (i32, [vp, i32, vp, vp, vp, i32, vp, vp]),
     "pob_pair_decode": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "pob_counters": (i32, [vp, vp]),
+    "pob_npy_probe": (i32, [vp, i32, i32, vp, vp, vp, vp, vp]),
+    "pob_npy_read": (i32, [vp, i32, i32, vp, i64, vp, vp, vp, vp]),
 }
 
 

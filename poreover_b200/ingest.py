@@ -114,6 +114,63 @@ def _chunks(n, parts):
     return [(i, min(n, i + step)) for i in range(0, n, step)]
 
 
+def _load_reads_native(paths, basecaller, rc, alloc):
+    """The common case -- every file a plain 2-D float32 .npy table of probabilities -- without a Python-level step
+    per file: headers and payloads are read by native threads (pob_npy_probe / pob_npy_read, csrc/hostio.cu) straight
+    into the packed buffer, then numpy's own log runs in place over it (decode.py:45: same ufunc, same values).
+    Returns None when some file is anything else: the caller takes the general path."""
+    n = len(paths)
+    if n == 0 or basecaller not in ('poreover', 'bonito') or any(os.path.splitext(p)[1] != '.npy' for p in paths):
+        return None
+    L = _lib.lib()
+    cpaths = (C.c_char_p * n)(*[os.fsencode(p) for p in paths])
+    rows, cols, doff = (np.zeros(n, np.int64) for _ in range(3))
+    flags, sums = np.zeros(n, np.int32), np.zeros(n, np.float32)
+    nt = n_threads()
+    _lib.check(L.pob_npy_probe(cpaths, n, nt, _lib.ptr(rows), _lib.ptr(cols), _lib.ptr(doff), _lib.ptr(flags),
+                               _lib.ptr(sums)), "pob_npy_probe")
+    bad = np.flatnonzero(flags == 2)
+    if len(bad):
+        raise OSError("cannot read %s" % paths[int(bad[0])])
+    if (flags != 0).any() or (cols != 5).any() or (rows <= 0).any():
+        return None
+    # np.isclose(np.sum(arr[0]), 1) of decode.py:43: clear cases decided on the float32 sums, the rest by numpy itself
+    d = np.abs(sums.astype(np.float64) - 1.0)
+    prob = d < 5e-6
+    unclear = ~prob & ~(d > 2e-5) & ~np.isnan(d)
+    if unclear.any():
+        prob |= unclear & np.isclose(sums, 1)
+    if not prob.all():
+        return None  # logits: the reference's log-softmax path (decode.py:47-50)
+    b = ReadBatch.__new__(ReadBatch)
+    b.np_dtype = np.dtype(np.float32)
+    b.dtype, b.n, b.n_states = _lib.F32, n, 5
+    b.kinds = [basecaller] * n
+    b.layout = _lib.BLANK_FIRST if basecaller == 'bonito' else _lib.BLANK_LAST
+    b.lens = rows.astype(np.int32)
+    padded = (rows + ALIGN_ROWS - 1) // ALIGN_ROWS * ALIGN_ROWS
+    b.row_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(padded, out=b.row_off[1:])
+    b.total_rows = int(b.row_off[-1])
+    b.data = (alloc or np.empty)((b.total_rows, 5), b.np_dtype)
+    ok = np.zeros(n, np.int32)
+    _lib.check(L.pob_npy_read(cpaths, n, nt, _lib.ptr(rows), 5, _lib.ptr(doff), _lib.ptr(b.row_off), _lib.ptr(b.data),
+                              _lib.ptr(ok)), "pob_npy_read")
+    if not ok.all():
+        raise OSError("cannot read %s" % paths[int(np.flatnonzero(ok == 0)[0])])
+    data, off, lens = b.data, b.row_off, b.lens
+
+    def logs(lohi):
+        with np.errstate(divide="ignore"):
+            for i in range(*lohi):
+                v = data[off[i]:off[i] + lens[i]]
+                np.log(v, out=v)  # the ufunc loop runs without the interpreter lock
+
+    list(pool().map(logs, _chunks(n, 4 * nt)))
+    b.rc = None if rc is None else np.ascontiguousarray(np.broadcast_to(np.asarray(rc, dtype=np.uint8), (n,)))
+    return b
+
+
 def load_reads(paths, basecaller, rc=None, alloc=None):
     """Load many files of one basecaller into one packed ReadBatch (host memory).
 
@@ -123,6 +180,10 @@ def load_reads(paths, basecaller, rc=None, alloc=None):
     The batch also carries .kinds, the transducer kind of every read."""
     paths = list(paths)
     n = len(paths)
+    if os.environ.get("POREOVER_B200_NATIVE_LOADER", "1") != "0":
+        fast = _load_reads_native(paths, basecaller, rc, alloc)
+        if fast is not None:
+            return fast
     ex = pool()
     parts = _chunks(n, 4 * n_threads())
     raws = [None] * n

@@ -19,6 +19,7 @@ store = dist.distributed_c10d._get_default_store()
 lock = threading.Lock()
 G, chunk = 1000, 61
 report = {"steps": []}
+dist.barrier()  # both ranks at the starting line
 for step in range(3):
     q = multigpu.WorkQueue(G, chunk, store, key="strong_q%d" % step)
 
