@@ -115,17 +115,18 @@ def align_banded_batch(seqs1, seqs2, band_width=500, match=2, mismatch=-1, gap_c
     n = len(seqs1)
     # align.pyx:120-171 with l1 == 0: the row loop never runs (no division happens), the traceback only drains seq2,
     # so the alignment is all gaps against seq2; those pairs never reach the kernel
-    empty = [k for k, s in enumerate(seqs1) if len(s) == 0]
+    empty = [k for k in range(n) if len(seqs1[k]) == 0 or len(seqs2[k]) == 0]
     if empty:
-        keep = [k for k in range(n) if len(seqs1[k]) > 0]
+        keep = [k for k in range(n) if k not in set(empty)]
         rest = align_banded_batch([seqs1[k] for k in keep], [seqs2[k] for k in keep], band_width, match, mismatch,
                                   gap_cost, device) if keep else []
         out = [None] * n
         for k, r in zip(keep, rest):
             out[k] = r
+        text = lambda s: s if isinstance(s, str) else bytes(s).decode()  # noqa: E731
         for k in empty:
-            s2 = seqs2[k] if isinstance(seqs2[k], str) else bytes(seqs2[k]).decode()
-            out[k] = ('-' * len(s2), s2, 0)
+            s1, s2 = text(seqs1[k]), text(seqs2[k])
+            out[k] = ('-' * len(s2), s2, 0) if not s1 else (s1, '-' * len(s1), 0)
         return out
     ctx = get_ctx(device)
     b1, o1 = _pack_bytes(seqs1)

@@ -47,6 +47,7 @@ for step in range(3):
 def bad_work(items):
     if rank == 1:
         raise ValueError("boom")
+    time.sleep(0.2)  # rank 0 is slow: rank 1 is sure to pull a chunk (and fail on it)
     return [x for x in items]
 
 try:
