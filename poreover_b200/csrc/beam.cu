@@ -67,6 +67,7 @@ struct __align__(16) NodeHdr {  // 128 bytes, home record of a node in the globa
   int32_t lo[2], hi[2];         // window of valid time keys per read: lo <= t < hi
   double maxp[2];               // max_prob[] of the reference nodes (linear domain) ...
   int32_t maxk[2];              // ... and the scale (power of two) they are expressed in
+  int32_t aslot;                // active slot while state == 0
 };
 
 template <int MODEL>
@@ -123,6 +124,12 @@ __device__ __forceinline__ double scale2(double x, int dk) {
   dk = max(-1000, min(1000, dk));
   return x * __longlong_as_double((long long)(1023 + dk) << 52);
 }
+
+// a_kid entries: the child's pool slot in the low 16 bits and, while the child is in the expanded beam, its active slot
+// + 1 above them (the pool has at most 65536 slots); -1 = the child was never created
+__device__ __forceinline__ int kid_slot(int v) { return v < 0 ? -1 : (v & 0xffff); }
+__device__ __forceinline__ int kid_act(int v) { return v < 0 ? -1 : (v >> 16) - 1; }
+__device__ __forceinline__ int kid_pack(int slot, int act) { return slot | ((act + 1) << 16); }
 
 __device__ __forceinline__ unsigned sign_acc(unsigned d, unsigned acc) {
   unsigned r;
@@ -218,11 +225,10 @@ __device__ unsigned long long g_exact_prunes;  // how often the ranking needed i
 extern __shared__ __align__(128) char pob_smem[];
 
 // Shared-memory arrays of the active slots (index a in [0, EMAX)); a_slot[a] < 0 = unused.
-//   slot2e  [NP]      pool slot -> active slot or -1
 //   a_slot            pool slot                 a_order / a_porder   creation order of the node / its parent
 //   a_par             active slot of the parent when a_pstat == PS_INE
 //   a_pslot           pool slot of the parent (window base when frozen)
-//   a_kid/a_kido [4]  pool slots / orders of the children, -1 = never created
+//   a_kid/a_kido [4]  children: pool slot | (active slot + 1) << 16 (kid_slot() / kid_act()), -1 = never created; orders
 //   a_lo/a_hi [2]     window bounds per read;   a_plo/a_phi [2] bounds of a frozen parent
 //   a_che [2]         clean end per read (see sweep)
 //   a_maxp [2]        max_prob[] of the reference nodes;  a_last0 value of read 0 at its last written t
@@ -258,8 +264,7 @@ extern __shared__ __align__(128) char pob_smem[];
   int32_t* const a_che = (int32_t*)(sm_ + 216 * EMAX);                                              \
   int32_t* const beam = (int32_t*)(sm_ + 224 * EMAX);                                               \
   int32_t* const sh = beam + ((W + 3) & ~3);                                                        \
-  int16_t* const slot2e = (int16_t*)(sh + SH_COUNT);                                                \
-  uint8_t* const a_last = (uint8_t*)(slot2e + NP);                                                  \
+  uint8_t* const a_last = (uint8_t*)(sh + SH_COUNT);                                                \
   const int eb_ = (EMAX + 15) & ~15;                                                                \
   uint8_t* const a_pstat = a_last + eb_;                                                            \
   uint8_t* const a_same = a_pstat + eb_;                                                            \
@@ -621,6 +626,12 @@ struct Engine {
   // Band maxima are kept in the scale of the band's newest column (SwItem::kref), the same for every node.
   __device__ __noinline__ void sweep(int reads_mask, int s0, int e0, int s1, int e1, bool full,
                                      unsigned long long& n_updates) {
+    // algorithmic count (what the reference evaluates): every used slot over every swept band; kept by thread 0 alone
+    if (threadIdx.x == 0) {
+      POB_VIEWS
+      n_updates += (unsigned long long)sh[SH_NUSED] *
+                   (unsigned long long)(((reads_mask & 1) ? max(e0 - s0, 0) : 0) + ((reads_mask & 2) ? max(e1 - s1, 0) : 0));
+    }
     POB_VIEWS
     const int tid = threadIdx.x;
     const int a = tid >> 1, r = tid & 1;
@@ -857,7 +868,6 @@ struct Engine {
         maxv = scale2(a_maxp[2 * a + r], a_maxk[2 * a + r] - kmax);
         if (a == 0) sh[SH_KREF0 + r] = kmax;
       }
-      n_updates += (unsigned long long)max(te - ts, 0);  // algorithmic count: what the reference evaluates
     }
     // ranking keys: row_col = max0 * max1 (PrefixTree.h:111, :397); row = value(0, u) * max1 (:107, :393); every
     // factor is in a scale shared by all nodes of this step
@@ -1031,14 +1041,20 @@ struct Engine {
     const int slot = a_slot[a];
     NodeHdr& h = hdr[slot];
     h.tid = a_tid[a];
-    for (int c = 0; c < 4; ++c) { h.kid_slot[c] = a_kid[4 * a + c]; h.kid_order[c] = a_kido[4 * a + c]; }
+    for (int c = 0; c < 4; ++c) { h.kid_slot[c] = kid_slot(a_kid[4 * a + c]); h.kid_order[c] = a_kido[4 * a + c]; }
     h.lo[0] = a_lo[2 * a]; h.lo[1] = a_lo[2 * a + 1]; h.hi[0] = a_hi[2 * a]; h.hi[1] = a_hi[2 * a + 1];
     h.maxp[0] = a_maxp[2 * a]; h.maxp[1] = a_maxp[2 * a + 1]; h.maxk[0] = a_maxk[2 * a]; h.maxk[1] = a_maxk[2 * a + 1];
     const int stamp = atomicAdd(&sh[SH_STAMP], 1) + 1;
     h.state = stamp;
     const int pos = atomicAdd(&sh[SH_RQT], 1);
     retq[pos % RQ] = make_int2(slot, stamp);
-    slot2e[slot] = -1;
+    h.aslot = -1;
+    // a live parent that stays in the expanded beam forgets where this child was active (a parent that retires in
+    // this same phase writes only the pool slots home, see above)
+    if (a_pstat[a] == PS_INE) {
+      const int pa = a_par[a];
+      if (a_needed[pa]) a_kid[4 * pa + a_last[a]] = slot;
+    }
     a_slot[a] = -1;
     clear_key(a);
     a_free[atomicAdd(&sh[SH_AFREE], 1)] = a;
@@ -1053,6 +1069,7 @@ struct Engine {
     n.parent_tid = parent_tid; n.tid = -1; n.depth = a_depth[pa] + 1; n.last = last;
     for (int q = 0; q < 4; ++q) { n.kid_slot[q] = -1; n.kid_order[q] = 0; }
     n.lo[0] = n.lo[1] = 0; n.hi[0] = n.hi[1] = 0; n.maxp[0] = n.maxp[1] = 0.0; n.maxk[0] = n.maxk[1] = 0;
+    n.aslot = a;
     hdr[slot] = n;
     a_slot[a] = slot; a_order[a] = order; a_par[a] = pa; a_pslot[a] = n.parent_slot; a_porder[a] = n.parent_order;
     a_depth[a] = n.depth; a_tid[a] = -1; a_ptid[a] = n.parent_tid;
@@ -1063,23 +1080,30 @@ struct Engine {
     a_last[a] = (uint8_t)last; a_pstat[a] = PS_INE; a_same[a] = (a_last[pa] == last);
     a_inbeam[a] = 0; a_needed[a] = 1;
     clear_key(a);
-    slot2e[slot] = (int16_t)a;
   }
 
   __device__ void activate_revived(int a, int slot, int pa) {
     POB_VIEWS
     NodeHdr& h = hdr[slot];
     h.state = 0;
+    h.aslot = a;
     a_slot[a] = slot; a_order[a] = h.order; a_par[a] = pa; a_pslot[a] = h.parent_slot; a_porder[a] = h.parent_order;
     a_depth[a] = h.depth; a_tid[a] = h.tid; a_ptid[a] = h.parent_tid;
     for (int q = 0; q < 4; ++q) {
       const int ks = h.kid_slot[q];
-      a_kid[4 * a + q] = ks; a_kido[4 * a + q] = h.kid_order[q];
+      int link = ks;
+      a_kido[4 * a + q] = h.kid_order[q];
       if (ks >= 0) {
-        // a child that stayed in the expanded beam (it is a beam member) reads this node live again
-        const int ka = slot2e[ks];
-        if (ka >= 0 && a_order[ka] == h.kid_order[q]) { a_par[ka] = a; a_pstat[ka] = PS_INE; }
+        // a child that stayed in the expanded beam (it is a beam member) reads this node live again; whether it did is
+        // in its home record (state 0 = active, with its active slot)
+        const NodeHdr& hk = hdr[ks];
+        if (hk.order == h.kid_order[q] && hk.state == 0) {
+          const int ka = hk.aslot;
+          a_par[ka] = a; a_pstat[ka] = PS_INE;
+          link = kid_pack(ks, ka);
+        }
       }
+      a_kid[4 * a + q] = link;
     }
     a_lo[2 * a] = h.lo[0]; a_lo[2 * a + 1] = h.lo[1]; a_hi[2 * a] = h.hi[0]; a_hi[2 * a + 1] = h.hi[1];
     a_maxp[2 * a] = h.maxp[0]; a_maxp[2 * a + 1] = h.maxp[1]; a_maxk[2 * a] = h.maxk[0]; a_maxk[2 * a + 1] = h.maxk[1];
@@ -1088,7 +1112,6 @@ struct Engine {
     a_last[a] = (uint8_t)h.last; a_pstat[a] = PS_INE; a_same[a] = (a_last[pa] == h.last);
     a_inbeam[a] = 0; a_needed[a] = 1;
     clear_key(a);
-    slot2e[slot] = (int16_t)a;
   }
 
   // ---- expansion of the new beam + retirement + reclamation: three phases, three barriers ----------
@@ -1107,10 +1130,11 @@ struct Engine {
     if (xmine) {
       a = beam[xb];
       kind = KID_FRESH;
-      const int ks = a_kid[4 * a + xc];
+      const int link = a_kid[4 * a + xc];
+      const int ks = kid_slot(link);
       if (ks >= 0) {
-        const int ka = slot2e[ks];
-        if (ka >= 0 && a_order[ka] == a_kido[4 * a + xc]) { kind = KID_ACTIVE; a_needed[ka] = 1; }
+        const int ka = kid_act(link);
+        if (ka >= 0) { kind = KID_ACTIVE; a_needed[ka] = 1; }
         else if (hdr[ks].order == a_kido[4 * a + xc]) { kind = KID_REVIVE; hdr[ks].state = 0; }  // line now in L1 for X3
       }
       if (xc == 0) a_needed[a] = 1;
@@ -1207,9 +1231,11 @@ struct Engine {
             const int slot = freelist[pi % NP];
             const uint32_t order = (uint32_t)(sh[SH_ORDER] + obase);
             activate_fresh(na, slot, order, a, xc, my_tid);
-            a_kid[4 * a + xc] = slot; a_kido[4 * a + xc] = order;
+            a_kid[4 * a + xc] = kid_pack(slot, na); a_kido[4 * a + xc] = order;
           } else {
-            activate_revived(na, a_kid[4 * a + xc], a);
+            const int ks = kid_slot(a_kid[4 * a + xc]);
+            activate_revived(na, ks, a);
+            a_kid[4 * a + xc] = kid_pack(ks, na);
           }
           atomicAdd(&sh[SH_NUSED], 1);
         }
@@ -1242,17 +1268,18 @@ struct Engine {
           trace[a_tid[a]] = ((uint32_t)a_ptid[a] << 2) | (uint32_t)a_last[a];
         }
         for (int c = 0; c < g_es.nbase; ++c) {
-          const int ks = a_kid[4 * a + c];
-          int ka = -1;
-          if (ks >= 0) { const int x = slot2e[ks]; if (x >= 0 && a_order[x] == a_kido[4 * a + c]) ka = x; }
+          const int ks = kid_slot(a_kid[4 * a + c]);
+          int ka = kid_act(a_kid[4 * a + c]);
           if (ka < 0 && sh[SH_AFREE] > 0 && sh[SH_FQT] - sh[SH_FQH] > 0) {
             ka = a_free[--sh[SH_AFREE]];
-            if (ks >= 0 && hdr[ks].order == a_kido[4 * a + c]) activate_revived(ka, ks, a);
-            else {
+            if (ks >= 0 && hdr[ks].order == a_kido[4 * a + c]) {
+              activate_revived(ka, ks, a);
+              a_kid[4 * a + c] = kid_pack(ks, ka);
+            } else {
               const int slot = freelist[(sh[SH_FQH]++) % NP];
               const uint32_t order = (uint32_t)sh[SH_ORDER]++;
               activate_fresh(ka, slot, order, a, c, a_tid[a]);
-              a_kid[4 * a + c] = slot; a_kido[4 * a + c] = order;
+              a_kid[4 * a + c] = kid_pack(slot, ka); a_kido[4 * a + c] = order;
             }
             sh[SH_NUSED]++;
           }
@@ -1326,7 +1353,6 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
   for (int s = tid; s < NP; s += NT) {
     hdr[s].order = 0; hdr[s].state = -1;
     freelist[s] = s;  // FIFO ring of free pool slots
-    slot2e[s] = -1;
   }
   for (int a = tid; a < EMAX; a += NT) {
     a_slot[a] = -1; a_free[a] = EMAX - 1 - a; clear_key(a);
@@ -1354,6 +1380,7 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     n.depth = 1; n.last = tid;
     for (int q = 0; q < 4; ++q) { n.kid_slot[q] = -1; n.kid_order[q] = 0; }
     n.lo[0] = n.lo[1] = 0; n.hi[0] = n.hi[1] = 0; n.maxp[0] = n.maxp[1] = 0.0; n.maxk[0] = n.maxk[1] = 0;
+    n.aslot = a;
     hdr[slot] = n;
     a_slot[a] = slot; a_order[a] = n.order; a_par[a] = -1; a_pslot[a] = -1; a_porder[a] = 0; a_depth[a] = 1;
     a_tid[a] = -1; a_ptid[a] = 0;
@@ -1362,7 +1389,6 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
     a_maxp[2 * a] = a_maxp[2 * a + 1] = 0.0; a_maxk[2 * a] = a_maxk[2 * a + 1] = 0; a_last0[a] = 0.0;
     a_che[2 * a] = a_che[2 * a + 1] = -1;
     a_last[a] = (uint8_t)tid; a_pstat[a] = PS_ROOT; a_same[a] = 0; a_inbeam[a] = 1; a_needed[a] = 1;
-    slot2e[slot] = (int16_t)a;
     beam[tid] = a;
     n_updates += (mode != MODE_1D) ? 2 : 1;
   }
@@ -1615,7 +1641,7 @@ size_t ws_bytes(int model, int NP, int CAP0, int CAP1, int RQ, int CAPC0, int CA
 
 size_t smem_bytes(int W, int NP, int EMAX) {
   // must match POB_VIEWS
-  size_t b = 224 * (size_t)EMAX + 4 * ((W + 3) & ~3) + 4 * SH_COUNT + 2 * (size_t)NP + 5 * ((EMAX + 15) & ~15);
+  size_t b = 224 * (size_t)EMAX + 4 * ((W + 3) & ~3) + 4 * SH_COUNT + 5 * ((EMAX + 15) & ~15);
   b += 4 * (size_t)((EMAX + 3) & ~3);  // k32
   return pob_align_up(b, 16);
 }

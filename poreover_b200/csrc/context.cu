@@ -214,9 +214,13 @@ pob_prof_scope::~pob_prof_scope() {
   if (idx >= 0) cudaEventRecord(ctx->prof_pending[idx].b, ctx->stream);
 }
 
+// Start a new API call: every block becomes free again.  Blocks are kept as they are: a call makes the same requests
+// in the same order as the previous one of its size, so first-fit over the existing blocks serves it without touching
+// the allocator; only a larger call adds a block.  (Blocks used to be merged into one here: cudaFree synchronises the
+// whole device -- stalling the other GPU call in flight -- and re-allocating tens of GB cost the command line about a
+// second per context.)  When the blocks have become many small ones, they are merged once.
 int pob_arena_reset(pob_ctx* c) {
-  if (c->blocks.size() > 1) {
-    // steady state is one block: merge what the previous call needed
+  if (c->blocks.size() > 24) {
     size_t total = 0;
     for (auto& b : c->blocks) total += b.size;
     POB_CUDA(cudaStreamSynchronize(c->stream));
