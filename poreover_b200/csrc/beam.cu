@@ -47,7 +47,10 @@ namespace {
 
 enum { MODE_1D = 0, MODE_ROW = 1, MODE_ROWCOL = 2 };
 #ifndef POB_MIR_DEPTH
-#define POB_MIR_DEPTH 8
+#define POB_MIR_DEPTH 16
+#endif
+#ifndef POB_MIRROR_PARENT
+#define POB_MIRROR_PARENT 0  // children read a live parent's prob from its shared-memory mirror
 #endif
 enum { MIR_DEPTH = POB_MIR_DEPTH };  // newest `prob` values of every (active slot, read) mirrored in shared memory
 enum { PS_ROOT = 0, PS_INE = 1, PS_FROZEN = 2, PS_DEAD = 3 };  // where a node's parent values come from
@@ -491,6 +494,7 @@ struct Engine {
     const Ent* pwb;
     const Col* cb;   // column ring of the read
     int lo, hi, plo, phi, pstat, pa, wmask, cmask, last, kref;
+    int pmlo, pmhi;  // timesteps of the parent's prob values that may be read from its shared-memory mirror
     bool same, mixed;
   };
 
@@ -507,9 +511,18 @@ struct Engine {
     I.pstat = a_pstat[a];
     I.same = a_same[a] != 0;
     I.pa = 0; I.plo = 0; I.phi = 0; I.pwb = nullptr;
+    I.pmlo = I.pmhi = 0;
     if (I.pstat == PS_INE) {
       I.pa = a_par[a];
       I.plo = a_lo[2 * I.pa + r]; I.phi = a_hi[2 * I.pa + r]; I.pwb = wbase(a_pslot[a], r);
+      // A live parent's prob values of the last MIR_DEPTH timesteps are in its shared-memory mirror (a child whose last
+      // base differs from the parent's reads prob; the others read gap, which only the window holds).  The parent may
+      // write up to te - 1 during this sweep, which recycles the ring slots of the timesteps below te - MIR_DEPTH; a
+      // parent that has just taken its slot (che < 0) has no mirror yet.
+      if (POB_MIRROR_PARENT && g_es.mir_off >= 0 && !I.same && a_che[2 * I.pa + r] >= 0) {
+        I.pmlo = max(max(mir_lo()[2 * I.pa + r], te - MIR_DEPTH), I.plo);
+        I.pmhi = min(mir_hi()[2 * I.pa + r], I.phi);
+      }
     } else if (I.pstat == PS_FROZEN) {
       I.plo = a_plo[2 * a + r]; I.phi = a_phi[2 * a + r]; I.pwb = wbase(a_pslot[a], r);
     }
@@ -521,6 +534,7 @@ struct Engine {
   }
 
   __device__ __forceinline__ double parent_at(const SwItem& I, int r, int t) const {
+    if (POB_MIRROR_PARENT && t - 1 >= I.pmlo && t - 1 < I.pmhi) return mir_base(I.pa, r)[t & (MIR_DEPTH - 1)];
     if (I.pstat == PS_INE || I.pstat == PS_FROZEN) return frozen_at(I.pwb, t, I.wmask, I.plo, I.phi, I.same);
     if (I.pstat == PS_ROOT) return root_prob(r, t - 1);
     return 0.0;
@@ -645,7 +659,7 @@ struct Engine {
     SwItem I;
     ChainIn C;
     C.p_prev = C.ng_prev = C.yl = C.yb = C.pv = C.yl_n = C.yb_n = C.pv_n = 0.0;
-    I.lo = I.hi = I.plo = I.phi = I.pa = I.wmask = I.cmask = I.last = I.kref = 0; I.pstat = PS_DEAD; I.same = I.mixed = false;
+    I.lo = I.hi = I.plo = I.phi = I.pa = I.wmask = I.cmask = I.last = I.kref = I.pmlo = I.pmhi = 0; I.pstat = PS_DEAD; I.same = I.mixed = false;
     I.wb = nullptr; I.pwb = nullptr; I.cb = nullptr;
     PCLK(12);
     deferred_finalize();
