@@ -183,6 +183,42 @@ def cpu_reference(kind, data, beam_width, n_items, steps, warmup, n_data, cores=
             "sample": "%d items per step x %d steps (same synthetic inputs as the GPU arm)" % (n_items, len(times))}
 
 
+def cpu_reference_python(n_pairs, T, beam_width, cores=None):
+    """BASELINE.md section 3, literally: the UNMODIFIED reference package's own driver, pair_decode.pair_decode(Namespace(
+    ..., threads=cores)) with its multiprocessing.Pool, on .npy files of the same synthetic pairs -- run by
+    oracle/ref_python_driver.py from the build outputs under oracle/_ref/ (the package byte-compiled into refpkg.zip, its
+    three Cython extensions compiled from the sources where they lay).  One pass over n_pairs pairs; None when those
+    outputs were not built."""
+    import shutil
+    import tempfile
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not (os.path.exists(os.path.join(ref, "refpkg.zip")) and os.path.isdir(os.path.join(ref, "refext"))):
+        return None
+    cores = cores or os.cpu_count() or 1
+    d = tempfile.mkdtemp(prefix="pob_refpy_")
+    try:
+        names = [synth.save_pair(d, k, T) for k in range(n_pairs)]
+        with open(os.path.join(d, "pairs.txt"), "w") as f:
+            for a, b in names:
+                f.write("%s %s\n" % (a, b))
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_python_driver.py"), os.path.join(d, "pairs.txt"),
+                            d, os.path.join(d, "ref"), str(cores), str(beam_width)], capture_output=True, text=True,
+                           timeout=1800)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not line:
+            return {"error": (r.stderr or r.stdout)[-300:]}
+        res = json.loads(line[-1])
+        return {"value": n_pairs / res["seconds"], "unit": "pairs/s", "cores": cores, "kind": "reference",
+                "kind_detail": "the unmodified reference package end to end: poreover.decoding.pair_decode.pair_decode("
+                               "Namespace(..., threads=%d)) on .npy files, its own multiprocessing.Pool, loaders, numpy "
+                               "Viterbi, Cython aligner and C++ search (oracle/_ref/refpkg.zip + refext/)" % cores,
+                "sample": "%d pairs, one pass (pairs 0..%d of the GPU arm's synthetic set, T~%d, beam %d)"
+                          % (n_pairs, n_pairs - 1, T, beam_width),
+                "consensus_mbases_per_s": res["consensus_bases"] / res["seconds"] / 1e6, "seconds": res["seconds"]}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 # --------------------------------------------------------------------------------------- workloads
 CONFIGS = {
     "cfg3_pairs": "BASELINE configs[2]: pair-decode of 10k synthetic bonito pairs (T~5000, beam_width 25, --reverse_complement, "
@@ -590,7 +626,7 @@ def run_pairs(args):
         if args.config == "cfg3_pairs":
             roof_v, _ = viterbi_roofline(ctx, L, l1[:min(G, 2500)], args.viterbi_reads, args.T)
 
-    cpu = None
+    cpu = cpu_py = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         npairs = min(G, max(4 * cores, 4)) if args.config == "cfg3_pairs" else min(G, max(cores // 4, 2))
@@ -598,6 +634,8 @@ def run_pairs(args):
         r = cpu_reference("pair", (l1[:nd], l2[:nd], pad), args.beam_width, npairs, 1, 0, nd)
         cpu = {"value": r["items_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": r["kind"],
                "kind_detail": r["kind_detail"], "sample": r["sample"], "consensus_mbases_per_s": r["bases_per_s"] / 1e6}
+        if args.config == "cfg3_pairs":
+            cpu_py = cpu_reference_python(min(G, 4 * cores), args.T, args.beam_width, cores)
 
     if rank == 0:
         line = {
@@ -609,7 +647,8 @@ def run_pairs(args):
                 "gpu_calls_in_flight_per_rank": len(lanes), "padding": pad,
                 "cache": "inputs per step (%.0f MB) exceed the 126 MB L2" % ((rows1 + rows2) * 20 / 1e6)}),
             "consensus_mbases_per_s": mbases, "e2e": e2e, "gpu_launches": int(launches_step * args.steps), "clocks": clocks,
-            "roofline": roof, "roofline_viterbi": roof_v, "cpu_baseline": cpu, "weak": weak, "check": check_rec,
+            "roofline": roof, "roofline_viterbi": roof_v, "cpu_baseline": cpu, "cpu_baseline_python": cpu_py, "weak": weak,
+            "check": check_rec,
             "kernels_ms_per_step_rank0": {k: v["ms"] for k, v in prof.items()},
             "kernels_note": "per-kernel CUDA-event times of rank 0's share of one step, re-run one call at a time after the timed region",
             "pairs_skipped": int(((status & (16 | 32 | 8 | 64)) != 0).sum()),
@@ -757,6 +796,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    cpu_py = None
     if args.config in ("cfg3_pairs", "cfg4_long"):
         n_items = args.ref_pairs or (4 * cores if args.config == "cfg3_pairs" else max(cores // 4, 2))
         uniq = min(max(n_items, 8), 256)
@@ -773,6 +813,8 @@ def run_reference(args):
             pad = 5
         r = cpu_reference("pair", (l1, l2, pad), args.beam_width, n_items, args.steps, args.warmup, len(l1))
         metric, unit = "pair_decode_pairs_per_s", "pairs/s"
+        if args.config == "cfg3_pairs":
+            cpu_py = cpu_reference_python(n_items, args.T, args.beam_width, cores)
     else:
         W = {"cfg2_beam25": 25, "cfg2_beam100": 100}.get(args.config, args.beam_width)
         kind = {"cfg2_viterbi": "viterbi", "cfg5_flipflop": "flipflop"}.get(args.config, "beam")
@@ -793,6 +835,7 @@ def run_reference(args):
         "cpu_baseline": {"value": r["items_per_s"], "unit": unit, "cores": r["cores"], "kind": r["kind"],
                          "kind_detail": r["kind_detail"], "native_loaded_in_parent": r["native_loaded_in_parent"],
                          "sample": r["sample"]},
+        "cpu_baseline_python": cpu_py,
         "e2e": {"value": r["items_per_s"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
