@@ -869,6 +869,7 @@ def main():
         args.pairs = 1000 if args.config == "cfg4_long" else 10000
     if args.config == "cfg4_long":
         args.unique_pairs = min(args.unique_pairs, 64)
+        args.lanes = 1  # the node pools of wide-band pairs take tens of GB per context: one GPU call at a time
     if args.warmup < 3 and args.impl == "ours" and args.config != "cfg4_long":
         args.warmup = 3
     if args.impl == "reference":

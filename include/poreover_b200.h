@@ -9,13 +9,21 @@
  *   - plain pointers and sizes only; no C++ / torch types.
  *   - `where` selects the memory space of EVERY data pointer of that call:
  *       POB_HOST   : host memory.  The library stages H2D, runs, stages D2H and synchronises.
- *       POB_DEVICE : device memory of the context's GPU.  The call only enqueues work on the
- *                    context's stream; use pob_ctx_sync() before reading results.
+ *       POB_DEVICE : device memory of the context's GPU.  Work is enqueued on the context's stream; use
+ *                    pob_ctx_sync() before reading results.  The single-stage calls (pob_viterbi, pob_align_*,
+ *                    pob_build_envelope, pob_forward, pob_viterbi_acceptor) only enqueue.  The searches and
+ *                    pob_pair_decode also read small per-item arrays back (read lengths, skip decisions, the widest
+ *                    envelope band, which size the search's windows) and therefore synchronise the stream up to
+ *                    three times inside the call; run two calls on two contexts to keep the GPU busy across them.
  *   - log-probability matrices ("reads") travel as a pob_reads_t descriptor (below).
  *   - `layout` tells where the blank column is stored: POB_BLANK_LAST (reference in-memory order,
  *     A C G T blank) or POB_BLANK_FIRST (bonito .npy file order; replaces decode.py:79).
  *   - rc[r] != 0 asks for the reverse-complement VIEW of read r (time reversed, A<->T, C<->G;
  *     replaces transducer.py:68-70, :79-81, :104-106) without materialising it.  rc may be NULL.
+ *   - a slice [lo, hi) of a packed batch is itself a batch: row_off + lo, row_len + lo, rc + lo, n = hi - lo, the
+ *     same data pointer (row offsets stay absolute).  Packed outputs are addressed by the same absolute offsets, so
+ *     the caller passes the full-size output buffers and the per-item arrays offset by lo.
+ *   - the searches take alphabets of one to four letters (n_states = letters + blank, 2..5) and beam widths 1..100.
  *   - every function returns POB_OK (0) or a negative POB_E* status; pob_strerror() names it.
  *   - the caller owns all inputs and pre-sized outputs; device scratch is owned by the context and
  *     reused across calls.
