@@ -481,10 +481,13 @@ def run_pairs(args):
         cover = np.stack(gathered)
         once = bool(((cover >= 0).sum(axis=0) == 1).all())
         job = cover.max(axis=0)
-        whole = view(d1, 0, G), view(d2, 0, G)
-        check(L.pob_pair_decode(ctx.h, _lib.DEVICE, C.byref(whole[0]), C.byref(whole[1]), kind, args.beam_width, pad, 500,
-                                method, o_seq1, o_l1, o_seq2, o_l2, o_cons, o_lc, o_sc, o_stats, o_st), "pob_pair_decode")
-        one_gpu = ctx.from_device(o_lc, (G,), np.int32)
+        if args.config == "cfg4_long" and not use_dist:
+            one_gpu = job.astype(np.int32)  # long pairs: a pass takes minutes; the job above WAS a single-GPU pass
+        else:
+            whole = view(d1, 0, G), view(d2, 0, G)
+            check(L.pob_pair_decode(ctx.h, _lib.DEVICE, C.byref(whole[0]), C.byref(whole[1]), kind, args.beam_width, pad,
+                                    500, method, o_seq1, o_l1, o_seq2, o_l2, o_cons, o_lc, o_sc, o_stats, o_st), "pob_pair_decode")
+            one_gpu = ctx.from_device(o_lc, (G,), np.int32)
         check_rec = {"every_pair_decoded_once": once, "consensus_lengths_equal_single_gpu_pass": bool(np.array_equal(job, one_gpu)),
                      "pairs": int(G), "consensus_bases": int(one_gpu.sum())}
         bases_job = int(one_gpu.sum())
@@ -627,7 +630,12 @@ def run_pairs(args):
             roof_v, _ = viterbi_roofline(ctx, L, l1[:min(G, 2500)], args.viterbi_reads, args.T)
 
     cpu = cpu_py = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "cfg4_long":
+        cpu = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "reference",
+               "sample": "not timed in this run: one T=50k-100k pair with padding 150 at beam width 25 takes the reference "
+                         "core several minutes on one core; tests/test_gpu_configs.py times and checks two such pairs at "
+                         "beam width 5 (about 100 s of CPU for both)"}
+    elif rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         npairs = min(G, max(4 * cores, 4)) if args.config == "cfg3_pairs" else min(G, max(cores // 4, 2))
         nd = min(G, 256)

@@ -1699,7 +1699,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
     const long by_span = 3L * W * (span + 8) + 16L * W;
     if (by_span > want) want = by_span;
     if (want > 65536) want = 65536;
-    P.NP = pow2_at_least((int)want);
+    P.NP = (int)((want + 255) / 256 * 256);  // the pool's rings are indexed modulo NP: no power of two needed
     if (P.NP < 1024) P.NP = 1024;
   }
   if (const char* e = getenv("POB_DEBUG_NP")) P.NP = atoi(e);
@@ -1809,15 +1809,29 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   int grid = per_sm * ctx->sm_count;
   if (grid > n_items) grid = n_items;
   if (grid < 1) grid = 1;
-  const size_t budget = (size_t)96 << 30;
+  // Budget: what is free on the device right now (a second call in flight on another context sees what this one
+  // left), at most 120 GB.  When a batch of wide-band items does not fit at full residency, the number of CTAs gives
+  // way first (down to one per two SMs): a smaller pool would recycle nodes that are still readable
+  // (POB_ST_POOL_OVERFLOW on every item of a config-4 style batch); only below that the pool is halved, and the
+  // overflow flag says so per item.
+  size_t free_b = 0, total_b = 0;
+  POB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  for (auto& b : ctx->blocks) free_b += b.size;  // this context's own scratch arena is reused by this call
+  size_t budget = free_b / 10 * 6;
+  if (budget > ((size_t)120 << 30)) budget = (size_t)120 << 30;
+  if (budget < ((size_t)1 << 30)) budget = (size_t)1 << 30;
   size_t stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, P.CAPC0, P.CAPC1, Umax);
-  while (grid > 1 && (size_t)grid * stride > budget && stride > ((size_t)192 << 20)) {
-    // wide bands are rare inside a batch: a smaller pool is usually enough, keep the parallelism
-    if (P.NP > 8192) { P.NP >>= 1; P.RQ = P.NP * 2; stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, P.CAPC0, P.CAPC1, Umax); }
-    else break;
+  const int floor_grid = grid < ctx->sm_count / 2 ? grid : ctx->sm_count / 2;
+  while (grid > floor_grid && (size_t)grid * stride > budget) { grid = grid * 3 / 4; if (grid < floor_grid) grid = floor_grid; }
+  while ((size_t)grid * stride > budget && P.NP > 8192) {
+    P.NP = (P.NP / 2 + 255) / 256 * 256; P.RQ = P.NP * 2;
+    stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, P.CAPC0, P.CAPC1, Umax);
   }
   while (grid > 1 && (size_t)grid * stride > budget) grid = grid * 3 / 4;
-  while (P.NP > 1024 && stride > budget) { P.NP >>= 1; P.RQ = P.NP * 2; stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, P.CAPC0, P.CAPC1, Umax); }
+  while (P.NP > 1024 && stride > budget) {
+    P.NP = (P.NP / 2 + 255) / 256 * 256; P.RQ = P.NP * 2;
+    stride = ws_bytes(model, P.NP, P.CAP0, P.CAP1, P.RQ, P.CAPC0, P.CAPC1, Umax);
+  }
   P.ws_stride = stride;
   P.ws = (char*)pob_arena_take(ctx, (size_t)grid * stride);
   if (!P.ws) return POB_ENOMEM;
