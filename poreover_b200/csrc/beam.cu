@@ -239,7 +239,8 @@ extern __shared__ __align__(128) char pob_smem[];
 //   a_same            parent's last base == own last base (merge-repeats reads the parent's gap value)
 //   beam [W]          active slots in rank order;  a_free stack of unused active slots;  sh scalars SH_*
 #define POB_VIEWS                                                                                   \
-  const int EMAX = g_es.EMAX, W = g_es.W, NP = g_es.NP, RQ = g_es.RQ, mode = g_es.mode;             \
+  const int EMAX = EM_CT ? EM_CT : g_es.EMAX, W = W_CT ? W_CT : g_es.W;                             \
+  const int NP = g_es.NP, RQ = g_es.RQ, mode = g_es.mode;                                           \
   char* const sm_ = pob_smem;                                                                       \
   double2* const pub = (double2*)sm_;                                                               \
   double* const key = (double*)(sm_ + 64 * EMAX);                                                   \
@@ -281,9 +282,18 @@ extern __shared__ __align__(128) char pob_smem[];
   int2* const retq = g_es.retq;                                                                     \
   uint32_t* const trace = g_es.trace;
 
-template <int MODEL>
+// EM_CT / W_CT: active-slot count and beam width known at compile time (0 = read from the engine state): the
+// benchmark's configuration (beam width 25, 128 slots) gets its own instantiation, in which the offsets of the
+// shared-memory arrays and the trip counts of the ranking loop are constants.
+template <int MODEL, int EM_CT = 0, int W_CT = 0>
 struct Engine {
   typedef Entry<MODEL> Ent;
+
+  // byte offset of the prob mirror in shared memory: in the specialised instantiation it follows from the layout
+  // (must match smem_bytes(); the launcher only picks that instantiation when the mirror is on and sits there)
+  static constexpr int MIR_OFF_CT =
+      EM_CT ? (int)(((224 * EM_CT + 4 * ((W_CT + 3) & ~3) + 4 * SH_COUNT + 5 * ((EM_CT + 15) & ~15) + 4 * ((EM_CT + 3) & ~3)) + 15) / 16 * 16) : -2;
+  __device__ __forceinline__ static int mir_off() { return EM_CT ? MIR_OFF_CT : g_es.mir_off; }
 
   __device__ __forceinline__ Ent* wbase(int slot, int r) const {
     return reinterpret_cast<Ent*>(g_es.win[r]) + (size_t)slot * g_es.cap[r];
@@ -295,10 +305,10 @@ struct Engine {
   // just taken its active slot (a_che < 0: nothing written yet) has an empty mirror whatever the bounds say.
   __device__ __forceinline__ double* mir_base(int a, int r) const {
     // rows are mdepth + 1 apart: an odd stride in 8-byte units keeps lanes that read the same timestep on distinct banks
-    return reinterpret_cast<double*>(pob_smem + g_es.mir_off) + (size_t)(2 * a + r) * (MIR_DEPTH + 1);
+    return reinterpret_cast<double*>(pob_smem + mir_off()) + (size_t)(2 * a + r) * (MIR_DEPTH + 1);
   }
   __device__ __forceinline__ int* mir_lo() const {
-    return reinterpret_cast<int*>(pob_smem + g_es.mir_off + (size_t)g_es.EMAX * 2 * (MIR_DEPTH + 1) * 8);
+    return reinterpret_cast<int*>(pob_smem + mir_off() + (size_t)(EM_CT ? EM_CT : g_es.EMAX) * 2 * (MIR_DEPTH + 1) * 8);
   }
   __device__ __forceinline__ int* mir_hi() const { return mir_lo() + 2 * g_es.EMAX; }
 
@@ -437,7 +447,7 @@ struct Engine {
       out.prob = prob;
     }
     *(wbase(a_slot[a], r) + ((t + 1) & g_es.mask[r])) = out;
-    if (g_es.mir_off >= 0) {
+    if (mir_off() >= 0) {
       mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
       int mlo = mir_lo()[2 * a + r], mhi = mir_hi()[2 * a + r];
       if (a_che[2 * a + r] < 0) mlo = mhi = 0;  // first write since the node took this slot: the bounds are its predecessor's
@@ -519,7 +529,7 @@ struct Engine {
       // base differs from the parent's reads prob; the others read gap, which only the window holds).  The parent may
       // write up to te - 1 during this sweep, which recycles the ring slots of the timesteps below te - MIR_DEPTH; a
       // parent that has just taken its slot (che < 0) has no mirror yet.
-      if (POB_MIRROR_PARENT && g_es.mir_off >= 0 && !I.same && a_che[2 * I.pa + r] >= 0) {
+      if (POB_MIRROR_PARENT && mir_off() >= 0 && !I.same && a_che[2 * I.pa + r] >= 0) {
         I.pmlo = max(max(mir_lo()[2 * I.pa + r], te - MIR_DEPTH), I.plo);
         I.pmhi = min(mir_hi()[2 * I.pa + r], I.phi);
       }
@@ -663,7 +673,7 @@ struct Engine {
     I.wb = nullptr; I.pwb = nullptr; I.cb = nullptr;
     PCLK(12);
     deferred_finalize();
-    const bool mirror = g_es.mir_off >= 0;
+    const bool mirror = mir_off() >= 0;
     PCLK(13);
     if (on && te > ts) {
       load_item(a, r, ts, te, I);
@@ -1325,8 +1335,8 @@ struct Engine {
   __device__ void run_item(const BeamParams& G, int item, char* ws);
 };
 
-template <int MODEL>
-__device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws) {
+template <int MODEL, int EM_CT, int W_CT>
+__device__ void Engine<MODEL, EM_CT, W_CT>::run_item(const BeamParams& G, int item, char* ws) {
   const int tid = threadIdx.x, NT = blockDim.x;
   unsigned long long n_updates = 0;
 #ifdef POB_PHASE_CLOCKS
@@ -1570,11 +1580,11 @@ __device__ void Engine<MODEL>::run_item(const BeamParams& G, int item, char* ws)
   __syncthreads();
 }
 
-template <int MODEL, int MAXT, int MINB>
+template <int MODEL, int MAXT, int MINB, int EM_CT = 0, int W_CT = 0>
 __global__ void __launch_bounds__(MAXT, MINB) beam_kernel(BeamParams P) {
   __shared__ int s_item;
   char* ws = P.ws + (size_t)blockIdx.x * P.ws_stride;
-  Engine<MODEL> eng;
+  Engine<MODEL, EM_CT, W_CT> eng;
   for (;;) {
     if (threadIdx.x == 0) s_item = atomicAdd(P.work_counter, 1);
     __syncthreads();
@@ -1763,10 +1773,17 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   void (*kern)(BeamParams);
   const bool ctc = model == POB_MODEL_CTC;
   constexpr int M0 = POB_MODEL_CTC, M1 = POB_MODEL_CTC_MERGE_REPEATS;
-  if (threads <= 64) { threads = 64; kern = ctc ? beam_kernel<M0, 64, 12> : beam_kernel<M1, 64, 12>; }
+  if (threads <= 64) {
+    threads = 64;
+    kern = ctc ? beam_kernel<M0, 64, 12> : beam_kernel<M1, 64, 12>;
+    if (W == 5 && P.EMAX == 32 && P.mir_off == (int)smem_bytes(5, 0, 32) && !getenv("POB_DEBUG_NO_CT"))
+      kern = ctc ? beam_kernel<M0, 64, 12, 32, 5> : beam_kernel<M1, 64, 12, 32, 5>;
+  }
   else if (threads <= 128) { kern = ctc ? beam_kernel<M0, 128, 6> : beam_kernel<M1, 128, 6>; }
   else if (threads <= 256) {
     kern = ctc ? beam_kernel<M0, 256, 3> : beam_kernel<M1, 256, 3>;
+    if (W == 25 && P.EMAX == 128 && P.mir_off == (int)smem_bytes(25, 0, 128) && !getenv("POB_DEBUG_NO_CT"))
+      kern = ctc ? beam_kernel<M0, 256, 3, 128, 25> : beam_kernel<M1, 256, 3, 128, 25>;
     if (max_cta_sm == 2) kern = ctc ? beam_kernel<M0, 256, 2> : beam_kernel<M1, 256, 2>;
     if (max_cta_sm == 4) kern = ctc ? beam_kernel<M0, 256, 4> : beam_kernel<M1, 256, 4>;
   }
