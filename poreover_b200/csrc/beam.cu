@@ -240,7 +240,7 @@ extern __shared__ __align__(128) char pob_smem[];
 //   beam [W]          active slots in rank order;  a_free stack of unused active slots;  sh scalars SH_*
 #define POB_VIEWS                                                                                   \
   const int EMAX = EM_CT ? EM_CT : g_es.EMAX, W = W_CT ? W_CT : g_es.W;                             \
-  const int NP = g_es.NP, RQ = g_es.RQ, mode = g_es.mode;                                           \
+  const int NP = g_es.NP, RQ = g_es.RQ, mode = MODE_CT >= 0 ? MODE_CT : g_es.mode;                  \
   char* const sm_ = pob_smem;                                                                       \
   double2* const pub = (double2*)sm_;                                                               \
   double* const key = (double*)(sm_ + 64 * EMAX);                                                   \
@@ -285,7 +285,7 @@ extern __shared__ __align__(128) char pob_smem[];
 // EM_CT / W_CT: active-slot count and beam width known at compile time (0 = read from the engine state): the
 // benchmark's configuration (beam width 25, 128 slots) gets its own instantiation, in which the offsets of the
 // shared-memory arrays and the trip counts of the ranking loop are constants.
-template <int MODEL, int EM_CT = 0, int W_CT = 0>
+template <int MODEL, int EM_CT = 0, int W_CT = 0, int MODE_CT = -1>
 struct Engine {
   typedef Entry<MODEL> Ent;
 
@@ -294,6 +294,8 @@ struct Engine {
   static constexpr int MIR_OFF_CT =
       EM_CT ? (int)(((224 * EM_CT + 4 * ((W_CT + 3) & ~3) + 4 * SH_COUNT + 5 * ((EM_CT + 15) & ~15) + 4 * ((EM_CT + 3) & ~3)) + 15) / 16 * 16) : -2;
   __device__ __forceinline__ static int mir_off() { return EM_CT ? MIR_OFF_CT : g_es.mir_off; }
+  // letters of the alphabet: the specialised instantiations are only launched on five-state reads
+  __device__ __forceinline__ static int nbase() { return EM_CT ? 4 : g_es.nbase; }
 
   __device__ __forceinline__ Ent* wbase(int slot, int r) const {
     return reinterpret_cast<Ent*>(g_es.win[r]) + (size_t)slot * g_es.cap[r];
@@ -648,8 +650,12 @@ struct Engine {
   //   * clean entries only contribute to the band maximum (max_prob is reset every step in the reference).
   // `full` disables the reuse (every node recomputed from s): the literal reference schedule.
   // Band maxima are kept in the scale of the band's newest column (SwItem::kref), the same for every node.
-  __device__ __noinline__ void sweep(int reads_mask, int s0, int e0, int s1, int e1, bool full,
+  __device__ __noinline__ void sweep(int reads_mask_, int s0, int e0, int s1, int e1, bool full_,
                                      unsigned long long& n_updates) {
+    // the row_col instantiation sweeps both reads incrementally: constants (the launcher keeps the debug switch that
+    // turns the reuse off on the generic instantiation)
+    const int reads_mask = MODE_CT == MODE_ROWCOL ? 3 : reads_mask_;
+    const bool full = MODE_CT == MODE_ROWCOL ? false : full_;
     // algorithmic count (what the reference evaluates): every used slot over every swept band; kept by thread 0 alone
     if (threadIdx.x == 0) {
       POB_VIEWS
@@ -1149,7 +1155,7 @@ struct Engine {
     // -- phase X1: classify the children of the beam.  A retired child that comes back is marked active right
     //    away so that the queue inspection of the next phase sees its queue entry as stale.
     const int xb = tid >> 2, xc = tid & 3;
-    const bool xmine = tid < 4 * nb && xc < g_es.nbase;  // alphabets of fewer than four letters leave child threads idle
+    const bool xmine = tid < 4 * nb && xc < nbase();  // alphabets of fewer than four letters leave child threads idle
     int a = -1, kind = KID_ACTIVE;
     if (xmine) {
       a = beam[xb];
@@ -1239,7 +1245,7 @@ struct Engine {
     }
     if (xmine) {
       const int my_tid = first ? sh[SH_TID] + fbase : a_tid[a];  // trace id of the beam node (my parent)
-      if (tid == 4 * (nb - 1) + g_es.nbase - 1) { sh[SH_TOTALLOC] = obase + (kind == KID_FRESH); sh[SH_TOTFIRST] = fbase + first; }
+      if (tid == 4 * (nb - 1) + nbase() - 1) { sh[SH_TOTALLOC] = obase + (kind == KID_FRESH); sh[SH_TOTFIRST] = fbase + first; }
       if (kind != KID_ACTIVE) {
         const int ai = atomicSub(&sh[SH_AFREE], 1) - 1;
         int pi = -1;
@@ -1291,7 +1297,7 @@ struct Engine {
           a_tid[a] = sh[SH_TID]++;
           trace[a_tid[a]] = ((uint32_t)a_ptid[a] << 2) | (uint32_t)a_last[a];
         }
-        for (int c = 0; c < g_es.nbase; ++c) {
+        for (int c = 0; c < nbase(); ++c) {
           const int ks = kid_slot(a_kid[4 * a + c]);
           int ka = kid_act(a_kid[4 * a + c]);
           if (ka < 0 && sh[SH_AFREE] > 0 && sh[SH_FQT] - sh[SH_FQH] > 0) {
@@ -1335,8 +1341,8 @@ struct Engine {
   __device__ void run_item(const BeamParams& G, int item, char* ws);
 };
 
-template <int MODEL, int EM_CT, int W_CT>
-__device__ void Engine<MODEL, EM_CT, W_CT>::run_item(const BeamParams& G, int item, char* ws) {
+template <int MODEL, int EM_CT, int W_CT, int MODE_CT>
+__device__ void Engine<MODEL, EM_CT, W_CT, MODE_CT>::run_item(const BeamParams& G, int item, char* ws) {
   const int tid = threadIdx.x, NT = blockDim.x;
   unsigned long long n_updates = 0;
 #ifdef POB_PHASE_CLOCKS
@@ -1580,11 +1586,11 @@ __device__ void Engine<MODEL, EM_CT, W_CT>::run_item(const BeamParams& G, int it
   __syncthreads();
 }
 
-template <int MODEL, int MAXT, int MINB, int EM_CT = 0, int W_CT = 0>
+template <int MODEL, int MAXT, int MINB, int EM_CT = 0, int W_CT = 0, int MODE_CT = -1>
 __global__ void __launch_bounds__(MAXT, MINB) beam_kernel(BeamParams P) {
   __shared__ int s_item;
   char* ws = P.ws + (size_t)blockIdx.x * P.ws_stride;
-  Engine<MODEL, EM_CT, W_CT> eng;
+  Engine<MODEL, EM_CT, W_CT, MODE_CT> eng;
   for (;;) {
     if (threadIdx.x == 0) s_item = atomicAdd(P.work_counter, 1);
     __syncthreads();
@@ -1776,14 +1782,20 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   if (threads <= 64) {
     threads = 64;
     kern = ctc ? beam_kernel<M0, 64, 12> : beam_kernel<M1, 64, 12>;
-    if (W == 5 && P.EMAX == 32 && P.mir_off == (int)smem_bytes(5, 0, 32) && !getenv("POB_DEBUG_NO_CT"))
+    if (W == 5 && P.EMAX == 32 && P.mir_off == (int)smem_bytes(5, 0, 32) && r1.n_states == 5 && !getenv("POB_DEBUG_NO_CT")) {
       kern = ctc ? beam_kernel<M0, 64, 12, 32, 5> : beam_kernel<M1, 64, 12, 32, 5>;
+      if (mode == MODE_ROWCOL && !P.dbg_noreuse)
+        kern = ctc ? beam_kernel<M0, 64, 12, 32, 5, MODE_ROWCOL> : beam_kernel<M1, 64, 12, 32, 5, MODE_ROWCOL>;
+    }
   }
   else if (threads <= 128) { kern = ctc ? beam_kernel<M0, 128, 6> : beam_kernel<M1, 128, 6>; }
   else if (threads <= 256) {
     kern = ctc ? beam_kernel<M0, 256, 3> : beam_kernel<M1, 256, 3>;
-    if (W == 25 && P.EMAX == 128 && P.mir_off == (int)smem_bytes(25, 0, 128) && !getenv("POB_DEBUG_NO_CT"))
+    if (W == 25 && P.EMAX == 128 && P.mir_off == (int)smem_bytes(25, 0, 128) && r1.n_states == 5 && !getenv("POB_DEBUG_NO_CT")) {
       kern = ctc ? beam_kernel<M0, 256, 3, 128, 25> : beam_kernel<M1, 256, 3, 128, 25>;
+      if (mode == MODE_ROWCOL && !P.dbg_noreuse && !getenv("POB_DEBUG_NO_CTMODE"))
+        kern = ctc ? beam_kernel<M0, 256, 3, 128, 25, MODE_ROWCOL> : beam_kernel<M1, 256, 3, 128, 25, MODE_ROWCOL>;
+    }
     if (max_cta_sm == 2) kern = ctc ? beam_kernel<M0, 256, 2> : beam_kernel<M1, 256, 2>;
     if (max_cta_sm == 4) kern = ctc ? beam_kernel<M0, 256, 4> : beam_kernel<M1, 256, 4>;
   }
