@@ -717,10 +717,16 @@ struct Engine {
           const double* mb = mir_base(a, r);
           if (!I.mixed) {
             // predicated and unrolled: all loads of a round are in flight together
+            // four predicated loads in flight per round; a round past the end of the range is skipped
 #pragma unroll
-            for (int q = 0; q < MIR_DEPTH; ++q) {
-              const int t = g1 + q;
-              if (t < m1) maxv = fmax(maxv, mb[(t + 1) & (MIR_DEPTH - 1)]);
+            for (int q0 = 0; q0 < MIR_DEPTH; q0 += 4) {
+              if (g1 + q0 < m1) {
+#pragma unroll
+                for (int q = q0; q < q0 + 4; ++q) {
+                  const int t = g1 + q;
+                  if (t < m1) maxv = fmax(maxv, mb[(t + 1) & (MIR_DEPTH - 1)]);
+                }
+              }
             }
           } else {
             for (int t = g1; t < m1; ++t) maxv = fmax(maxv, in_band_scale(I, mb[(t + 1) & (MIR_DEPTH - 1)], t));

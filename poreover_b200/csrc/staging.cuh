@@ -102,7 +102,7 @@ int upload(pob_ctx* ctx, const std::vector<T>& h, const T** dev) {
 // anti-diagonal-major matrix of a T~5000 pair is 16 MB, so a 10k-pair batch is aligned in chunks that reuse one
 // scratch matrix (same stream, so a chunk's traceback finishes before the next fill overwrites it).
 // cells[p] = matrix size of pair p (0 = skipped); all other per-pair arrays are device pointers indexed by pair.
-constexpr int64_t NW_CELL_BUDGET = (int64_t)2 << 30;  // 8 GB = 512 pairs of T ~ 5000 per fill + traceback launch (32 GB
+constexpr int64_t NW_CELL_BUDGET = (int64_t)4 << 30;  // 16 GB = 1024 pairs of T ~ 5000 per fill + traceback launch (32 GB
                                                       // made the scratch arena of every context twice as large for nothing)
 int nw_run_chunked(pob_ctx* ctx, const uint8_t* s1, const int64_t* off1, const int32_t* len1, const uint8_t* s2,
                    const int64_t* off2, const int32_t* len2, const int32_t* skip, int n, int band, int match,
