@@ -953,7 +953,9 @@ struct Engine {
     POB_VIEWS
     const double sc = key[a];
     if (!(sc > 0.0)) return;
-    sh[SH_EBASE] = max(0, (int)((__double_as_longlong(sc) >> 52) & 0x7ff) - 127);
+    // atomic stores: when the fast ranking ties at the top, two threads come here (the exact pass then runs, and its
+    // single rank-0 thread has the last word)
+    atomicExch(&sh[SH_EBASE], max(0, (int)((__double_as_longlong(sc) >> 52) & 0x7ff) - 127));
     for (int r = 0; r < 2; ++r) {
       double m; int k;
       if (mode == MODE_ROWCOL || (mode == MODE_ROW && r == 1)) { m = a_maxp[2 * a + r]; k = a_maxk[2 * a + r]; }
@@ -961,7 +963,7 @@ struct Engine {
       else continue;
       if (!(m > 0.0)) continue;
       const int e = (int)((__double_as_longlong(m) >> 52) & 0x7ff) - 1023 + (k - sh[SH_KLAST0 + r]);
-      sh[SH_PEND0 + r] = (e >= 64 || e <= -64) ? e : 0;
+      atomicExch(&sh[SH_PEND0 + r], (e >= 64 || e <= -64) ? e : 0);
     }
   }
 
@@ -1044,7 +1046,7 @@ struct Engine {
       inb = cand && rank < W;
       a_inbeam[a] = inb;
       if (inb) {
-        beam[rank] = a;
+        atomicExch(&beam[rank], a);  // two candidates may share a rank here (a tie in the 31-bit keys): the exact pass follows
         dmin_mine = a_depth[a];
         if (rank == 0) top_feedback(a);
       }
