@@ -48,7 +48,12 @@ def build_parser():
 
 
 def main(argv=None):
-    args = build_parser().parse_args(argv)
+    parser = build_parser()
+    args = parser.parse_args(argv)
+    # the reference takes any width; the GPU searches run one thread per (node, read) of the expanded beam
+    uses_beam = args.command == 'pair-decode' or getattr(args, 'algorithm', None) == 'beam'
+    if uses_beam and not 1 <= args.beam_width <= 100:
+        parser.error("--beam_width must be between 1 and 100 on the B200 backend (got %d)" % args.beam_width)
     if args.command == 'decode':
         from .decoding.decode import decode
         decode(args)
