@@ -363,17 +363,15 @@ class PinnedPool:
 
 
 _pinned = None
-# set by the command-line drivers for runs long enough that pinning pays (it costs ~0.2 s per GB once, in the
-# background; a chunk's host-to-device copy from pageable memory costs that every time)
-LONG_RUN = False
 
 
 def packed_alloc():
-    """Allocator of load_reads' packed buffers: the pinned pool when POREOVER_B200_PINNED=1 -- or, by default, when the
-    run is long (LONG_RUN) --, else numpy's."""
+    """Allocator of load_reads' packed buffers: the pinned pool when POREOVER_B200_PINNED=1, else numpy's.  Opt-in:
+    measured again in round 2 on a 40,960-pair run (10 chunks), the pool on by default did 4,077 pairs/s against 5,197
+    with pageable batches -- cudaMallocHost in the background stalls the GPU threads' launches for longer than the
+    faster copies save."""
     global _pinned
-    want = os.environ.get("POREOVER_B200_PINNED", "auto")
-    if want == "0" or (want != "1" and not LONG_RUN):
+    if os.environ.get("POREOVER_B200_PINNED", "0") != "1":
         return None
     with _pool_lock:
         if _pinned is None:

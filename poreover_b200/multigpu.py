@@ -225,8 +225,6 @@ def decode_pairs_all_gpus(args, pair_list, chunk=4096):
     # 444 pairs in flight, so a batch should be several waves; the next batch is loaded while this one is decoded)
     pd._check_args(args)
     chunk = max(8, min(chunk, -(-len(pair_list) // (4 * world))))
-    from . import ingest
-    ingest.LONG_RUN = len(pair_list) // world >= 16384  # several seconds of GPU work per rank: pinned batches pay
     from . import _lib
 
     def gpu_stage(payload):
