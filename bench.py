@@ -398,7 +398,8 @@ def run_pairs(args):
     def drain(decode_chunk):
         """One step of the job: this rank's share of the queue.  Returns the chunks it decoded."""
         step_no[0] += 1
-        q = multigpu.WorkQueue(G, chunk, store, key="pob_bench_q%d" % step_no[0])
+        q = multigpu.WorkQueue(G, chunk, store, key="pob_bench_q%d" % step_no[0],
+                               pullers=(world * len(lanes)) if (use_dist and args.taper) else 0, min_chunk=args.min_chunk)
         last_bounds[0] = q.bounds
         return multigpu.drain_queue(q, decode_chunk, len(lanes), lock=store_lock)
 
@@ -652,6 +653,7 @@ def run_pairs(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, {
                 "pairs_per_step_whole_job": G, "unique_pairs": min(G, args.unique_pairs), "chunk_pairs": chunk,
+                "chunks_taper_to": (args.min_chunk if (use_dist and args.taper) else None),
                 "gpu_calls_in_flight_per_rank": len(lanes), "padding": pad,
                 "cache": "inputs per step (%.0f MB) exceed the 126 MB L2" % ((rows1 + rows2) * 20 / 1e6)}),
             "consensus_mbases_per_s": mbases, "e2e": e2e, "gpu_launches": int(launches_step * args.steps), "clocks": clocks,
@@ -869,6 +871,9 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=0, help="items per step of the reference arm (default: by config and cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-weak", action="store_true")
+    ap.add_argument("--taper", action="store_true", help="N > 1: chunks that shrink towards the end of the job (guided self-scheduling); "
+                    "measured slower (9.2k vs 10.9k pairs/s at N=2, 313-pair chunks): chunks below the ~444 resident pairs under-fill a GPU")
+    ap.add_argument("--min-chunk", type=int, default=96, help="smallest chunk of the tapered queue")
     ap.add_argument("--pageable-outputs", action="store_true", help="e2e leg: results into pageable instead of pinned host arrays")
     args = ap.parse_args()
     if args.pairs_per_gpu and not args.pairs:

@@ -15,9 +15,13 @@ def dist_info():
 class WorkQueue:
     """Chunked dynamic queue over range(n_items) shared by all ranks of a torch.distributed job.  The first `ramp`
     chunks are a quarter of the size: a pipelined consumer starts its first GPU call sooner.  With `weights` (one
-    per item, in queue order) a chunk also ends once it holds `weight_budget`: batches of long reads stay small."""
+    per item, in queue order) a chunk also ends once it holds `weight_budget`: batches of long reads stay small.
+    With `pullers` (how many consumers pull concurrently: ranks x calls in flight) the chunks taper towards the end of
+    the queue (guided self-scheduling: at most 1 / (2 pullers) of what is left, never below `min_chunk`), so that the
+    consumers finish within a small chunk of each other instead of a full one."""
 
-    def __init__(self, n_items, chunk, store=None, key="poreover_b200_queue", ramp=0, weights=None, weight_budget=None):
+    def __init__(self, n_items, chunk, store=None, key="poreover_b200_queue", ramp=0, weights=None, weight_budget=None,
+                 pullers=0, min_chunk=64):
         self.n, self.chunk, self.store, self.key = n_items, max(1, chunk), store, key
         self._local = 0
         self.bounds = [0]  # the same on every rank: chunk k = [bounds[k], bounds[k+1])
@@ -25,7 +29,11 @@ class WorkQueue:
             lo = self.bounds[-1]
             small = len(self.bounds) - 1 < ramp
             step = max(1, self.chunk // 4) if small else self.chunk
+            if pullers > 0:
+                step = max(min(min_chunk, self.chunk), min(step, -(-(n_items - lo) // (2 * pullers))))
             hi = min(n_items, lo + step)
+            if pullers > 0 and weights is None and n_items - hi < min_chunk // 2:
+                hi = n_items  # no crumb at the end
             if weights is not None and weight_budget:
                 budget, acc, k = (weight_budget / 4 if small else weight_budget), 0, lo
                 while k < hi and (k == lo or acc + weights[k] <= budget):

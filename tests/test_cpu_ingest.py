@@ -305,13 +305,20 @@ def test_work_queue_bounds_partition_the_items():
         ramp = int(rng.integers(0, 4))
         weights = sorted((int(x) for x in rng.integers(0, 50, size=n)), reverse=True) if rng.random() < 0.7 else None
         budget = int(rng.integers(1, 200)) if weights is not None else None
-        q = multigpu.WorkQueue(n, chunk, ramp=ramp, weights=weights, weight_budget=budget)
+        pullers = int(rng.integers(1, 17)) if rng.random() < 0.5 else 0  # tapering towards the end of the queue
+        min_chunk = int(rng.integers(1, 32))
+        q = multigpu.WorkQueue(n, chunk, ramp=ramp, weights=weights, weight_budget=budget, pullers=pullers,
+                               min_chunk=min_chunk)
         got = list(iter(q.next, None))
         assert all(lo < hi for lo, hi in got)
         assert [lo for lo, _ in got] == [0] * bool(got) + [hi for _, hi in got[:-1]]
         assert (got[-1][1] if got else 0) == n
-        assert all(hi - lo <= chunk for lo, hi in got)
-        if weights is not None:
+        assert all(hi - lo <= chunk for lo, hi in got[:-1])
+        assert not got or got[-1][1] - got[-1][0] <= chunk + (min_chunk // 2 if pullers else 0)
+        if pullers and weights is None and ramp == 0:  # guided: sizes never grow (but for the crumb merged at the end)
+            sizes = [hi - lo for lo, hi in got[:-1]]
+            assert sizes == sorted(sizes, reverse=True)
+        if weights is not None and not pullers:
             for lo, hi in got:  # within the budget, except for a single item that alone exceeds it
                 assert hi - lo == 1 or sum(weights[lo:hi]) <= budget
 
