@@ -266,20 +266,24 @@ def beam_roofline(prof, counters, n_pairs_per_launch, launches, clocks, alg_byte
             "cell_updates_per_s": counters["cell_updates"] / max(1e-9, beam_ms / 1e3),
             "share_of_step": bk["ms"] / tot_ms if tot_ms else None}
     if nb and nb.get("grid"):
-        per_pair_inst = float(nb["warp_instructions"]) / float(nb["grid"])
-        issued = per_pair_inst * n_pairs_per_launch / max(1e-9, beam_ms / 1e3)
-        per_pair_dram = (nb["dram_read"] + nb["dram_write"]) * 1e9 / nb["grid"]
-        upd_per_pair = counters["cell_updates"] / max(1, n_pairs_per_launch)
+        # the capture is one wave of T=5000 pairs: scale it by forward cell updates (the unit of work both runs count),
+        # so that other read lengths and envelope widths use the same per-update figures
+        cap_upd = float(nb.get("cell_updates") or 0.0)
+        scale = (counters["cell_updates"] / cap_upd) if cap_upd else n_pairs_per_launch / float(nb["grid"])
+        inst = float(nb["warp_instructions"]) * scale
+        dram = (nb["dram_read"] + nb["dram_write"]) * 1e9 * scale
+        issued = inst / max(1e-9, beam_ms / 1e3)
         roof.update({
             "achieved": issued / 1e9, "frac": issued / peak_issue,
-            "traffic": per_pair_dram * n_pairs_per_launch,
-            "warp_instructions_per_cell_update": per_pair_inst / max(1.0, upd_per_pair),
-            "dram_to_algorithmic": per_pair_dram * n_pairs_per_launch / max(1.0, alg_bytes),
+            "traffic": dram,
+            "warp_instructions_per_cell_update": inst / max(1.0, counters["cell_updates"]),
+            "dram_to_algorithmic": dram / max(1.0, alg_bytes),
             "pipe_fp64_frac": nb.get("pipe_fp64_pct", 0) / 100.0, "pipe_fma_frac": nb.get("pipe_fma_pct", 0) / 100.0,
             "pipe_alu_frac": nb.get("pipe_alu_pct", 0) / 100.0, "pipe_xu_frac": nb.get("pipe_xu_pct", 0) / 100.0,
             "smem_wavefront_frac": nb.get("smem_wavefronts_pct", 0) / 100.0,
             "source": "%s: smsp__inst_executed.sum, dram__bytes_{read,write}.sum and pipe utilisations of one ncu --set full "
-                      "capture (%d pairs), per pair x pairs per step / this run's kernel time" % (ns_src, int(nb["grid"]))})
+                      "capture (%d pairs, %.3g cell updates), scaled per %s to this step / this run's kernel time"
+                      % (ns_src, int(nb["grid"]), cap_upd, "cell update" if cap_upd else "pair")})
     roof["hbm_frame"] = {"algorithmic_bytes_per_step": alg_bytes, "achieved": alg_bytes / max(1e-9, beam_ms / 1e3) / 1e9,
                          "peak": hbm, "unit": "GB/s", "frac": alg_bytes / max(1e-9, beam_ms / 1e3) / 1e9 / hbm,
                          "peak_source": hbm_src}

@@ -76,8 +76,8 @@ struct __align__(16) NodeHdr {  // 128 bytes, home record of a node in the globa
 template <int MODEL>
 struct Entry;
 template <>
-struct __align__(32) Entry<POB_MODEL_CTC_MERGE_REPEATS> {
-  double prob, gap, nogap, pad;
+struct __align__(16) Entry<POB_MODEL_CTC_MERGE_REPEATS> {
+  double gap, nogap;  // prob = gap + nogap (one rounding, PrefixTree.h:128): recomputed by the reader, bit for bit
 };
 template <>
 struct __align__(8) Entry<POB_MODEL_CTC> {
@@ -297,6 +297,27 @@ struct Engine {
   // letters of the alphabet: the specialised instantiations are only launched on five-state reads
   __device__ __forceinline__ static int nbase() { return EM_CT ? 4 : g_es.nbase; }
 
+  // window entries: what is stored and what a reader gets back
+  struct EV { double prob, gap, nogap; };
+  __device__ __forceinline__ static EV ld_ent(const Ent* e) {
+    EV v;
+    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
+      const double2 q = *reinterpret_cast<const double2*>(e);
+      v.gap = q.x; v.nogap = q.y; v.prob = __dadd_rn(q.x, q.y);
+    } else {
+      v.prob = e->prob; v.gap = 0.0; v.nogap = 0.0;
+    }
+    return v;
+  }
+  __device__ __forceinline__ static double ld_prob(const Ent* e) { return ld_ent(e).prob; }
+  __device__ __forceinline__ static void st_ent(Ent* o, double prob, double gp, double ng) {
+    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
+      double2 q; q.x = gp; q.y = ng;
+      *reinterpret_cast<double2*>(o) = q;
+    } else {
+      o->prob = prob;
+    }
+  }
   __device__ __forceinline__ Ent* wbase(int slot, int r) const {
     return reinterpret_cast<Ent*>(g_es.win[r]) + (size_t)slot * g_es.cap[r];
   }
@@ -412,9 +433,8 @@ struct Engine {
     in.lo = a_lo[2 * a + r]; in.hi = a_hi[2 * a + r];
     const bool self_ok = (t - 1 >= in.lo && t - 1 < in.hi);
     const Ent* se = wbase(slot, r) + (t & g_es.mask[r]);
-    in.p_prev = self_ok ? se->prob : 0.0;
-    in.ng_prev = 0.0;
-    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.ng_prev = self_ok ? se->nogap : 0.0;
+    in.p_prev = 0.0; in.ng_prev = 0.0;
+    if (self_ok) { const EV v = ld_ent(se); in.p_prev = v.prob; in.ng_prev = v.nogap; }
     const Col* c = colp(r, t);
     in.ylast = c->y[last];
     in.yblank = c->y[4];
@@ -430,8 +450,8 @@ struct Engine {
       else { plo = a_plo[2 * a + r]; phi = a_phi[2 * a + r]; }
       if (t - 1 >= plo && t - 1 < phi) {
         const Ent* pe = wbase(a_pslot[a], r) + (t & g_es.mask[r]);
-        if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) in.pv = a_same[a] ? pe->gap : pe->prob;
-        else in.pv = pe->prob;
+        const EV v = ld_ent(pe);
+        in.pv = (MODEL == POB_MODEL_CTC_MERGE_REPEATS && a_same[a]) ? v.gap : v.prob;
       } else {
         in.pv = 0.0;
       }
@@ -440,15 +460,9 @@ struct Engine {
 
   __device__ __forceinline__ double update_commit(int a, int r, int t, const UpdIn& in) {
     POB_VIEWS
-    Ent out;
     double prob, gp, ng;
     cell(in.p_prev, in.ng_prev, in.pv, in.ylast, in.yblank, prob, gp, ng);
-    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
-      out.prob = prob; out.gap = gp; out.nogap = ng; out.pad = 0;
-    } else {
-      out.prob = prob;
-    }
-    *(wbase(a_slot[a], r) + ((t + 1) & g_es.mask[r])) = out;
+    st_ent(wbase(a_slot[a], r) + ((t + 1) & g_es.mask[r]), prob, gp, ng);
     if (mir_off() >= 0) {
       mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
       int mlo = mir_lo()[2 * a + r], mhi = mir_hi()[2 * a + r];
@@ -494,8 +508,8 @@ struct Engine {
   __device__ __forceinline__ double frozen_at(const Ent* pwb, int t, int wmask, int plo, int phi, bool same) const {
     if (t - 1 < plo || t - 1 >= phi) return 0.0;
     const Ent* q = pwb + (t & wmask);
-    if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) return same ? q->gap : q->prob;
-    else return q->prob;
+    const EV v = ld_ent(q);
+    return (MODEL == POB_MODEL_CTC_MERGE_REPEATS && same) ? v.gap : v.prob;
   }
 
   // Everything a thread needs to recompute cells of one (active slot, read): views of the node's window, of its
@@ -569,8 +583,8 @@ struct Engine {
     C.p_prev = 0.0; C.ng_prev = 0.0;
     if (cs - 1 >= I.lo && cs - 1 < I.hi) {
       const Ent* se = I.wb + (cs & I.wmask);
-      C.p_prev = se->prob;
-      if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { C.ng_prev = se->nogap; }
+      const EV v = ld_ent(se);
+      C.p_prev = v.prob; C.ng_prev = v.nogap;
     }
     load_y(I, cs, C.yl, C.yb);
     C.pv = parent_at(I, r, cs);
@@ -591,13 +605,8 @@ struct Engine {
       double prob, gp, ng;
       cell(p_prev, ng_prev, pv, yl, yb, prob, gp, ng);
       Ent* o = I.wb + ((t + 1) & I.wmask);
-      if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
-        double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
-        *reinterpret_cast<double4*>(o) = v4;
-        ng_prev = ng; g_prev = gp;
-      } else {
-        o->prob = prob;
-      }
+      st_ent(o, prob, gp, ng);
+      if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { ng_prev = ng; g_prev = gp; }
       if (mirror) mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
       p_prev = prob;
       maxv = fmax(maxv, in_band_scale(I, prob, t));
@@ -738,14 +747,14 @@ struct Engine {
           if (!I.mixed) {
             for (int t = b0; t < b1; t += 4) {
               double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-              v0 = (I.wb + ((t + 1) & I.wmask))->prob;
-              if (t + 1 < b1) v1 = (I.wb + ((t + 2) & I.wmask))->prob;
-              if (t + 2 < b1) v2 = (I.wb + ((t + 3) & I.wmask))->prob;
-              if (t + 3 < b1) v3 = (I.wb + ((t + 4) & I.wmask))->prob;
+              v0 = ld_prob(I.wb + ((t + 1) & I.wmask));
+              if (t + 1 < b1) v1 = ld_prob(I.wb + ((t + 2) & I.wmask));
+              if (t + 2 < b1) v2 = ld_prob(I.wb + ((t + 3) & I.wmask));
+              if (t + 3 < b1) v3 = ld_prob(I.wb + ((t + 4) & I.wmask));
               maxv = fmax(fmax(maxv, v0), fmax(fmax(v1, v2), v3));
             }
           } else {
-            for (int t = b0; t < b1; ++t) maxv = fmax(maxv, in_band_scale(I, (I.wb + ((t + 1) & I.wmask))->prob, t));
+            for (int t = b0; t < b1; ++t) maxv = fmax(maxv, in_band_scale(I, ld_prob(I.wb + ((t + 1) & I.wmask)), t));
           }
         }
       }
@@ -786,8 +795,8 @@ struct Engine {
         if (longi && computing) {
           // the chain ran on another thread: its last values are in the window
           const Ent* se = I.wb + (Tb & I.wmask);
-          p_prev = se->prob;
-          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { g_prev = se->gap; ng_prev = se->nogap; }
+          const EV v = ld_ent(se);
+          p_prev = v.prob; g_prev = v.gap; ng_prev = v.nogap;
         }
         // publish the node's value at Tb-1: computed in phase A, or a stored clean entry
         double2 pb; pb.x = 0.0; pb.y = 0.0;
@@ -795,8 +804,8 @@ struct Engine {
         if (computing) { pb.x = p_prev; pb.y = g_prev; }
         else if (tp >= I.lo && tp < I.hi) {
           const Ent* se = I.wb + ((tp + 1) & I.wmask);
-          pb.x = se->prob;
-          if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pb.y = se->gap;
+          const EV v = ld_ent(se);
+          pb.x = v.prob; pb.y = v.gap;
         }
         pub[a * 2 + r] = pb;
         pchg[a * 2 + r] = computing;
@@ -835,30 +844,24 @@ struct Engine {
               p_prev = 0.0; ng_prev = 0.0;
               if (t - 1 >= I.lo && t - 1 < I.hi) {
                 const Ent* se = I.wb + (t & I.wmask);
-                p_prev = se->prob;
-                if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_prev = se->nogap;
+                const EV v = ld_ent(se);
+                p_prev = v.prob; ng_prev = v.nogap;
               }
               if (t < cs) {
                 // dirtied inside its clean range: the clean maximum may include entries that change now
                 cs = t;
                 maxv = 0.0;
                 for (int q = ts; q < t; ++q) {
-                  if (q >= I.lo && q < I.hi) maxv = fmax(maxv, in_band_scale(I, (I.wb + ((q + 1) & I.wmask))->prob, q));
+                  if (q >= I.lo && q < I.hi) maxv = fmax(maxv, in_band_scale(I, ld_prob(I.wb + ((q + 1) & I.wmask)), q));
                 }
               }
             }
             double prob, gp, ng;
             cell(p_prev, ng_prev, pv, yl, yb, prob, gp, ng);
             Ent* o = I.wb + ((t + 1) & I.wmask);
-            if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) {
-              double4 v4; v4.x = prob; v4.y = gp; v4.z = ng; v4.w = 0;
-              *reinterpret_cast<double4*>(o) = v4;
-              ng_prev = ng;
-              pb.x = prob; pb.y = gp;
-            } else {
-              o->prob = prob;
-              pb.x = prob; pb.y = 0.0;
-            }
+            st_ent(o, prob, gp, ng);
+            if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_prev = ng;
+            pb.x = prob; pb.y = gp;
             if (mirror) mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
             p_prev = prob;
             maxv = fmax(maxv, in_band_scale(I, prob, t));
@@ -867,8 +870,8 @@ struct Engine {
             pb.x = 0.0; pb.y = 0.0;
             if (t >= I.lo && t < I.hi) {
               const Ent* se = I.wb + ((t + 1) & I.wmask);
-              pb.x = se->prob;
-              if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) pb.y = se->gap;
+              const EV v = ld_ent(se);
+              pb.x = v.prob; pb.y = v.gap;
             }
           }
           pub_wr[((it + 1) & 1) * pstride] = pb;
@@ -1670,7 +1673,7 @@ extern "C" int pob_debug_trace(pob_ctx* ctx, double* out, int n) {
 namespace {
 
 size_t ws_bytes(int model, int NP, int CAP0, int CAP1, int RQ, int CAPC0, int CAPC1, int Umax) {
-  const size_t es = model == POB_MODEL_CTC ? 8 : 32;
+  const size_t es = model == POB_MODEL_CTC ? sizeof(Entry<POB_MODEL_CTC>) : sizeof(Entry<POB_MODEL_CTC_MERGE_REPEATS>);
   size_t b = sizeof(NodeHdr) * (size_t)NP + es * (size_t)NP * ((size_t)CAP0 + CAP1) + 4 * (size_t)NP + 8 * (size_t)RQ;
   b += sizeof(Col) * ((size_t)CAPC0 + CAPC1);
   b += 4 * ((size_t)Umax + 2);
