@@ -715,6 +715,8 @@ struct Engine {
 #endif
       PCLK(14);
       // clean part of the band: only the maximum is needed (independent loads, four in flight)
+      // (measured: running this scan twice costs 6.7 % -- 6683 -> 6250 pairs/s -- so a constant-time band maximum could
+      // gain about that much, no more: the loads are independent and pipeline well)
       {
         const int c0 = max(ts, I.lo), c1 = min(cs, I.hi);
         // [c0, g1) from the window, [g1, m1) from the shared-memory mirror, [m1, c1) from the window again (rare)
