@@ -50,6 +50,12 @@ enum { MODE_1D = 0, MODE_ROW = 1, MODE_ROWCOL = 2 };
 #define POB_MIR_DEPTH 16
 #endif
 #ifndef POB_MIRROR_PARENT
+#ifndef POB_USE_MIRROR
+#define POB_USE_MIRROR 0  // the clean-band maximum no longer scans (see sweep()): the mirror is compiled out
+#endif
+#ifndef POB_SCAN_WIDTH
+#define POB_SCAN_WIDTH 4
+#endif
 #define POB_MIRROR_PARENT 0  // children read a live parent's prob from its shared-memory mirror
 #endif
 enum { MIR_DEPTH = POB_MIR_DEPTH };  // newest `prob` values of every (active slot, read) mirrored in shared memory
@@ -225,6 +231,9 @@ __shared__ long long g_pclk_last;
 #define PCLK(i) do { } while (0)
 #endif
 __device__ unsigned long long g_exact_prunes;  // how often the ranking needed its exact pass (diagnostic)
+#ifdef POB_COUNT_RESCAN
+__device__ unsigned long long g_dbg[8];  // why clean ranges were scanned (diagnostic build)
+#endif
 extern __shared__ __align__(128) char pob_smem[];
 
 // Shared-memory arrays of the active slots (index a in [0, EMAX)); a_slot[a] < 0 = unused.
@@ -276,6 +285,7 @@ extern __shared__ __align__(128) char pob_smem[];
   uint8_t* const a_needed = a_inbeam + eb_;                                                         \
   const int E4 = (EMAX + 3) & ~3;                                                                   \
   uint32_t* const k32 = (uint32_t*)(a_needed + eb_);                                                \
+  int32_t* const a_maxt = (int32_t*)(k32 + E4);   /* [2] timestep that holds a_maxp, -1 = unknown */ \
   int16_t* const lst = (int16_t*)tmpb;   /* [2][EMAX] work lists of long_chains() */                                  \
   NodeHdr* const hdr = g_es.hdr;                                                                    \
   int32_t* const freelist = g_es.freelist;                                                          \
@@ -292,7 +302,7 @@ struct Engine {
   // byte offset of the prob mirror in shared memory: in the specialised instantiation it follows from the layout
   // (must match smem_bytes(); the launcher only picks that instantiation when the mirror is on and sits there)
   static constexpr int MIR_OFF_CT =
-      EM_CT ? (int)(((224 * EM_CT + 4 * ((W_CT + 3) & ~3) + 4 * SH_COUNT + 5 * ((EM_CT + 15) & ~15) + 4 * ((EM_CT + 3) & ~3)) + 15) / 16 * 16) : -2;
+      EM_CT ? (int)(((224 * EM_CT + 4 * ((W_CT + 3) & ~3) + 4 * SH_COUNT + 5 * ((EM_CT + 15) & ~15) + 4 * ((EM_CT + 3) & ~3) + 8 * EM_CT) + 15) / 16 * 16) : -2;
   __device__ __forceinline__ static int mir_off() { return EM_CT ? MIR_OFF_CT : g_es.mir_off; }
   // letters of the alphabet: the specialised instantiations are only launched on five-state reads
   __device__ __forceinline__ static int nbase() { return EM_CT ? 4 : g_es.nbase; }
@@ -463,7 +473,8 @@ struct Engine {
     double prob, gp, ng;
     cell(in.p_prev, in.ng_prev, in.pv, in.ylast, in.yblank, prob, gp, ng);
     st_ent(wbase(a_slot[a], r) + ((t + 1) & g_es.mask[r]), prob, gp, ng);
-    if (mir_off() >= 0) {
+    a_maxt[2 * a + r] = -1;  // a_maxp becomes a running maximum: the next sweep scans its clean entries
+    if (POB_USE_MIRROR && mir_off() >= 0) {
       mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
       int mlo = mir_lo()[2 * a + r], mhi = mir_hi()[2 * a + r];
       if (a_che[2 * a + r] < 0) mlo = mhi = 0;  // first write since the node took this slot: the bounds are its predecessor's
@@ -592,10 +603,16 @@ struct Engine {
     if (cs + 1 < te) { load_y(I, cs + 1, C.yl_n, C.yb_n); C.pv_n = parent_at(I, r, cs + 1); }
   }
 
+  // band maximum and the (latest) timestep that holds it
+  __device__ __forceinline__ static void fold_max(double& maxv, int& maxt, double x, int t) {
+    if (x >= maxv) { maxv = x; maxt = t; }
+  }
+
+
   // Private recomputation of the cells [cs, lim) of one (node, read), cs < lim: every parent entry read here is
   // final.  Leaves the node's values at lim - 1 in p_prev / ng_prev / g_prev and folds the new values into maxv.
   __device__ __forceinline__ void chain(const SwItem& I, int a, int r, int cs, int lim, bool mirror, const ChainIn& C,
-                                        double& p_prev, double& ng_prev, double& g_prev, double& maxv) const {
+                                        double& p_prev, double& ng_prev, double& g_prev, double& maxv, int& maxt) const {
     p_prev = C.p_prev; ng_prev = C.ng_prev;
     // inputs are requested two timesteps ahead of their use
     double yl = C.yl, yb = C.yb, pv = C.pv, yl_n = C.yl_n, yb_n = C.yb_n, pv_n = C.pv_n;
@@ -608,8 +625,8 @@ struct Engine {
       st_ent(o, prob, gp, ng);
       if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { ng_prev = ng; g_prev = gp; }
       if (mirror) mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
+      fold_max(maxv, maxt, in_band_scale(I, prob, t), t);
       p_prev = prob;
-      maxv = fmax(maxv, in_band_scale(I, prob, t));
       yl = yl_n; yb = yb_n; pv = pv_n;
       yl_n = yl_n2; yb_n = yb_n2; pv_n = pv_n2;
     }
@@ -634,10 +651,11 @@ struct Engine {
       SwItem I;
       load_item(a, r, ts, te, I);
       double p_prev, ng_prev, g_prev = 0.0, maxv = 0.0;
+      int maxt = -1;
       if (ts < lim) {
         ChainIn C;
         chain_preload(I, r, ts, te, C);
-        chain(I, a, r, ts, lim, mirror, C, p_prev, ng_prev, g_prev, maxv);
+        chain(I, a, r, ts, lim, mirror, C, p_prev, ng_prev, g_prev, maxv, maxt);
       }
       a_maxp[2 * a + r] = maxv;
     }
@@ -680,6 +698,11 @@ struct Engine {
     int cs = 0;
     bool was_fresh = true, longi = false;
     double p_prev = 0.0, ng_prev = 0.0, g_prev = 0.0, maxv = 0.0;
+    int maxt = -1;  // timestep of maxv
+#ifdef POB_COUNT_RESCAN
+    bool dbg_rescan = false;
+    int dbg_c0 = -1;
+#endif
     const int ts = r ? s1 : s0, te = r ? e1 : e0;
     SwItem I;
     ChainIn C;
@@ -688,7 +711,7 @@ struct Engine {
     I.wb = nullptr; I.pwb = nullptr; I.cb = nullptr;
     PCLK(12);
     deferred_finalize();
-    const bool mirror = mir_off() >= 0;
+    const bool mirror = POB_USE_MIRROR && mir_off() >= 0;
     PCLK(13);
     if (on && te > ts) {
       load_item(a, r, ts, te, I);
@@ -714,53 +737,58 @@ struct Engine {
       }
 #endif
       PCLK(14);
-      // clean part of the band: only the maximum is needed (independent loads, four in flight)
-      // (measured: running this scan twice costs 6.7 % -- 6683 -> 6250 pairs/s -- so a constant-time band maximum could
-      // gain about that much, no more: the loads are independent and pipeline well)
+      // Clean part of the band, [c0, c1): its entries are final and only their maximum is needed.  The band maximum of
+      // the node's previous sweep (a_maxp, in the scale a_maxk, found at timestep a_maxt) is that maximum whenever its
+      // timestep is still inside: the entries that left the band since (band starts only move forward) were not larger,
+      // and the rest are the same values in the same scale.  Otherwise -- the maximum has left the band, the scale of
+      // the band changed, single updates came in between -- the entries are scanned (four independent loads in flight).
+      // Measured (444 pairs): 9 % of the (node, read) steps still scan, nearly all of them decaying prefixes whose
+      // maximum is the first entry of the band at every step.  Scanning at every step (with the newest 16 values
+      // mirrored in shared memory) was 33 % of the kernel's instructions; this is 7.6 % fewer instructions at the same
+      // speed (the step waits for the warps that recompute whole bands, not for the scans).  Also tracking where the
+      // non-increasing tail of the values starts (then the maximum is the first entry: one load) halves the scans left
+      // but costs more than it saves: 6363 against 6665 pairs/s.
       {
         const int c0 = max(ts, I.lo), c1 = min(cs, I.hi);
-        // [c0, g1) from the window, [g1, m1) from the shared-memory mirror, [m1, c1) from the window again (rare)
-        int g1 = c0, m1 = c0;
-        if (mirror && che >= 0) {
-          const int mlo = mir_lo()[2 * a + r], mhi = mir_hi()[2 * a + r];
-          g1 = min(c1, max(c0, mlo));
-          m1 = min(c1, max(g1, mhi));
-          const double* mb = mir_base(a, r);
-          if (!I.mixed) {
-            // predicated and unrolled: all loads of a round are in flight together
-            // four predicated loads in flight per round; a round past the end of the range is skipped
-#pragma unroll
-            for (int q0 = 0; q0 < MIR_DEPTH; q0 += 4) {
-              if (g1 + q0 < m1) {
-#pragma unroll
-                for (int q = q0; q < q0 + 4; ++q) {
-                  const int t = g1 + q;
-                  if (t < m1) maxv = fmax(maxv, mb[(t + 1) & (MIR_DEPTH - 1)]);
-                }
-              }
-            }
-          } else {
-            for (int t = g1; t < m1; ++t) maxv = fmax(maxv, in_band_scale(I, mb[(t + 1) & (MIR_DEPTH - 1)], t));
+        const int pt = a_maxt[2 * a + r];
+        if (pt >= c0 && pt < c1 && a_maxk[2 * a + r] == I.kref) {
+          maxv = a_maxp[2 * a + r]; maxt = pt;
+        } else {
+#ifdef POB_COUNT_RESCAN
+          dbg_rescan = c1 - c0 >= 4;
+          if (dbg_rescan) {
+            const int why = pt < 0 ? 0 : (a_maxk[2 * a + r] != I.kref ? 1 : (pt < c0 ? 2 : 3));
+            atomicAdd(&g_dbg[why], 1ULL);
+            dbg_c0 = c0;
           }
-        }
-#pragma unroll 1
-        for (int part = 0; part < 2; ++part) {
-          const int b0 = part ? m1 : c0, b1 = part ? c1 : g1;
-          if (!I.mixed) {
-            for (int t = b0; t < b1; t += 4) {
-              double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-              v0 = ld_prob(I.wb + ((t + 1) & I.wmask));
-              if (t + 1 < b1) v1 = ld_prob(I.wb + ((t + 2) & I.wmask));
-              if (t + 2 < b1) v2 = ld_prob(I.wb + ((t + 3) & I.wmask));
-              if (t + 3 < b1) v3 = ld_prob(I.wb + ((t + 4) & I.wmask));
-              maxv = fmax(fmax(maxv, v0), fmax(fmax(v1, v2), v3));
+#endif
+          // POB_SCAN_WIDTH independent loads per round trip to L1 / L2
+          for (int t = c0; t < c1; t += POB_SCAN_WIDTH) {
+            double v[POB_SCAN_WIDTH];
+#pragma unroll
+            for (int q = 0; q < POB_SCAN_WIDTH; ++q) {
+              v[q] = 0.0;
+              if (t + q < c1) v[q] = ld_prob(I.wb + ((t + q + 1) & I.wmask));
             }
-          } else {
-            for (int t = b0; t < b1; ++t) maxv = fmax(maxv, in_band_scale(I, ld_prob(I.wb + ((t + 1) & I.wmask)), t));
+#pragma unroll
+            for (int q = 0; q < POB_SCAN_WIDTH; ++q)
+              if (t + q < c1) fold_max(maxv, maxt, in_band_scale(I, v[q], t + q), t + q);
           }
         }
       }
     }
+#ifdef POB_COUNT_RESCAN
+    if (dbg_rescan) {
+      // where the scan found the maximum: first entry (4), first four (5), elsewhere (6)
+      atomicAdd(&g_dbg[maxt == dbg_c0 ? 4 : (maxt < dbg_c0 + 4 ? 5 : 6)], 1ULL);
+      if (maxv == 0.0) atomicAdd(&g_dbg[7], 1ULL);
+    }
+    {  // diagnostic build: lanes (low 40 bits) and warps (high bits) that scanned a clean range of >= 4 entries
+      const unsigned m = __ballot_sync(0xffffffffu, dbg_rescan);
+      if ((threadIdx.x & 31) == 0 && m)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&g_exact_prunes), (1ULL << 40) + (unsigned long long)__popc(m));
+    }
+#endif
     PCLK(15);
     __syncthreads();
     PCLK(1);
@@ -777,7 +805,7 @@ struct Engine {
 #ifndef POB_HOIST
       chain_preload(I, r, cs, te, C);
 #endif
-      if (!longi) chain(I, a, r, cs, limA, mirror, C, p_prev, ng_prev, g_prev, maxv);
+      if (!longi) chain(I, a, r, cs, limA, mirror, C, p_prev, ng_prev, g_prev, maxv, maxt);
     }
 #ifdef POB_LONGQ
     if (nl0 + nl1 > 0) {
@@ -852,10 +880,9 @@ struct Engine {
               if (t < cs) {
                 // dirtied inside its clean range: the clean maximum may include entries that change now
                 cs = t;
-                maxv = 0.0;
-                for (int q = ts; q < t; ++q) {
-                  if (q >= I.lo && q < I.hi) maxv = fmax(maxv, in_band_scale(I, ld_prob(I.wb + ((q + 1) & I.wmask)), q));
-                }
+                maxv = 0.0; maxt = -1;
+                for (int q = max(ts, I.lo); q < min(t, I.hi); ++q)
+                  fold_max(maxv, maxt, in_band_scale(I, ld_prob(I.wb + ((q + 1) & I.wmask)), q), q);
               }
             }
             double prob, gp, ng;
@@ -865,8 +892,8 @@ struct Engine {
             if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_prev = ng;
             pb.x = prob; pb.y = gp;
             if (mirror) mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
+            fold_max(maxv, maxt, in_band_scale(I, prob, t), t);
             p_prev = prob;
-            maxv = fmax(maxv, in_band_scale(I, prob, t));
           } else {
             // still clean at t: hand the stored value to the children
             pb.x = 0.0; pb.y = 0.0;
@@ -902,6 +929,7 @@ struct Engine {
         }
         a_maxp[2 * a + r] = maxv;  // reset + max over the band
         a_maxk[2 * a + r] = kmax;
+        a_maxt[2 * a + r] = maxt;
         if (a == 0) sh[SH_KREF0 + r] = kmax;  // for the debug trace only
       } else {
         // empty band: max_prob left stale (A.6b); brought to a scale every node shares (that of the newest column)
@@ -1119,6 +1147,7 @@ struct Engine {
     for (int q = 0; q < 4; ++q) { a_kid[4 * a + q] = -1; a_kido[4 * a + q] = 0; }
     a_lo[2 * a] = a_lo[2 * a + 1] = 0; a_hi[2 * a] = a_hi[2 * a + 1] = 0;
     a_maxp[2 * a] = a_maxp[2 * a + 1] = 0.0; a_maxk[2 * a] = a_maxk[2 * a + 1] = 0; a_last0[a] = 0.0;
+    a_maxt[2 * a] = a_maxt[2 * a + 1] = -1;
     a_che[2 * a] = a_che[2 * a + 1] = -1;
     a_last[a] = (uint8_t)last; a_pstat[a] = PS_INE; a_same[a] = (a_last[pa] == last);
     a_inbeam[a] = 0; a_needed[a] = 1;
@@ -1151,6 +1180,7 @@ struct Engine {
     a_lo[2 * a] = h.lo[0]; a_lo[2 * a + 1] = h.lo[1]; a_hi[2 * a] = h.hi[0]; a_hi[2 * a + 1] = h.hi[1];
     a_maxp[2 * a] = h.maxp[0]; a_maxp[2 * a + 1] = h.maxp[1]; a_maxk[2 * a] = h.maxk[0]; a_maxk[2 * a + 1] = h.maxk[1];
     a_last0[a] = 0.0;
+    a_maxt[2 * a] = a_maxt[2 * a + 1] = -1;
     a_che[2 * a] = a_che[2 * a + 1] = -1;  // retained entries are stale with respect to the live parent
     a_last[a] = (uint8_t)h.last; a_pstat[a] = PS_INE; a_same[a] = (a_last[pa] == h.last);
     a_inbeam[a] = 0; a_needed[a] = 1;
@@ -1430,6 +1460,7 @@ __device__ void Engine<MODEL, EM_CT, W_CT, MODE_CT>::run_item(const BeamParams& 
     for (int q = 0; q < 4; ++q) { a_kid[4 * a + q] = -1; a_kido[4 * a + q] = 0; }
     a_lo[2 * a] = a_lo[2 * a + 1] = 0; a_hi[2 * a] = a_hi[2 * a + 1] = 0;
     a_maxp[2 * a] = a_maxp[2 * a + 1] = 0.0; a_maxk[2 * a] = a_maxk[2 * a + 1] = 0; a_last0[a] = 0.0;
+    a_maxt[2 * a] = a_maxt[2 * a + 1] = -1;
     a_che[2 * a] = a_che[2 * a + 1] = -1;
     a_last[a] = (uint8_t)tid; a_pstat[a] = PS_ROOT; a_same[a] = 0; a_inbeam[a] = 1; a_needed[a] = 1;
     beam[tid] = a;
@@ -1647,6 +1678,14 @@ __global__ void backtrace_kernel(const uint32_t* __restrict__ trace, const int64
 }  // namespace
 // debug export (not part of the ABI): cycles per engine phase, only in builds with -DPOB_PHASE_CLOCKS
 extern "C" int pob_debug_exact_prunes(unsigned long long* out, int reset) {
+#ifdef POB_COUNT_RESCAN
+  {
+    unsigned long long d[8];
+    POB_CUDA(cudaMemcpyFromSymbol(d, g_dbg, sizeof(d)));
+    fprintf(stderr, "[pob] scans: unknown %llu, scale %llu, left the band %llu, other %llu; maximum found at first entry %llu, "
+            "first four %llu, elsewhere %llu; all-zero %llu\n", d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
+  }
+#endif
   POB_CUDA(cudaMemcpyFromSymbol(out, g_exact_prunes, sizeof(unsigned long long)));
   if (reset) {
     unsigned long long z = 0;
@@ -1686,6 +1725,7 @@ size_t smem_bytes(int W, int NP, int EMAX) {
   // must match POB_VIEWS
   size_t b = 224 * (size_t)EMAX + 4 * ((W + 3) & ~3) + 4 * SH_COUNT + 5 * ((EMAX + 15) & ~15);
   b += 4 * (size_t)((EMAX + 3) & ~3);  // k32
+  b += 8 * (size_t)EMAX;               // a_maxt
   return pob_align_up(b, 16);
 }
 
@@ -1777,7 +1817,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   if (mode != MODE_1D) {
     const size_t budget_cta = (max_cta_sm == 2 ? 227 * 1024 / 2 : max_cta_sm == 1 ? 200 * 1024 : 227 * 1024 / 3) - 1024;
     const size_t mir = (size_t)P.EMAX * 2 * (MIR_DEPTH + 1) * 8 + (size_t)P.EMAX * 2 * 2 * 4;
-    bool on = smem + mir <= budget_cta;
+    bool on = POB_USE_MIRROR && smem + mir <= budget_cta;
     if (const char* e = getenv("POB_DEBUG_MIRROR")) on = on && atoi(e) != 0;
     if (on) { P.mir_off = (int)smem; P.mir_depth = MIR_DEPTH; smem = pob_align_up(smem + mir, 16); }
   }
@@ -1798,7 +1838,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   if (threads <= 64) {
     threads = 64;
     kern = ctc ? beam_kernel<M0, 64, 12> : beam_kernel<M1, 64, 12>;
-    if (W == 5 && P.EMAX == 32 && P.mir_off == (int)smem_bytes(5, 0, 32) && r1.n_states == 5 && !getenv("POB_DEBUG_NO_CT")) {
+    if (W == 5 && P.EMAX == 32 && (!POB_USE_MIRROR || P.mir_off == (int)smem_bytes(5, 0, 32)) && r1.n_states == 5 && !getenv("POB_DEBUG_NO_CT")) {
       kern = ctc ? beam_kernel<M0, 64, 12, 32, 5> : beam_kernel<M1, 64, 12, 32, 5>;
       if (mode == MODE_ROWCOL && !P.dbg_noreuse)
         kern = ctc ? beam_kernel<M0, 64, 12, 32, 5, MODE_ROWCOL> : beam_kernel<M1, 64, 12, 32, 5, MODE_ROWCOL>;
@@ -1807,7 +1847,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   else if (threads <= 128) { kern = ctc ? beam_kernel<M0, 128, 6> : beam_kernel<M1, 128, 6>; }
   else if (threads <= 256) {
     kern = ctc ? beam_kernel<M0, 256, 3> : beam_kernel<M1, 256, 3>;
-    if (W == 25 && P.EMAX == 128 && P.mir_off == (int)smem_bytes(25, 0, 128) && r1.n_states == 5 && !getenv("POB_DEBUG_NO_CT")) {
+    if (W == 25 && P.EMAX == 128 && (!POB_USE_MIRROR || P.mir_off == (int)smem_bytes(25, 0, 128)) && r1.n_states == 5 && !getenv("POB_DEBUG_NO_CT")) {
       kern = ctc ? beam_kernel<M0, 256, 3, 128, 25> : beam_kernel<M1, 256, 3, 128, 25>;
       if (mode == MODE_ROWCOL && !P.dbg_noreuse && !getenv("POB_DEBUG_NO_CTMODE"))
         kern = ctc ? beam_kernel<M0, 256, 3, 128, 25, MODE_ROWCOL> : beam_kernel<M1, 256, 3, 128, 25, MODE_ROWCOL>;
