@@ -68,7 +68,9 @@ enum {
                                  (pair_decode.py:136): the reference asserts and drops the pair */
   POB_ST_SKIPPED_LENGTH = 16, /* |len1-len2| > 1000 (pair_decode.py:372-375) */
   POB_ST_SKIPPED_IDENTITY = 32, /* alignment identity < 0.5 (pair_decode.py:395-398) */
-  POB_ST_EMPTY = 64           /* zero-length input */
+  POB_ST_EMPTY = 64,          /* zero-length input */
+  POB_ST_MAX_DEPTH = 128      /* legacy prefix search: the prefix outgrew the reads ("Max search depth exceeded",
+                                 prefix_search.py:279-281) */
 };
 
 typedef struct pob_ctx pob_ctx;
@@ -115,7 +117,8 @@ int pob_memcpy_d2h(pob_ctx* ctx, void* dst, const void* src, size_t bytes); /* a
 /* Per-kernel device timing with CUDA events on the context's stream.  ids: POB_K_* */
 enum {
   POB_K_VITERBI = 0, POB_K_FLIPFLOP = 1, POB_K_NW_FILL = 2, POB_K_NW_TRACE = 3, POB_K_ENVELOPE = 4,
-  POB_K_BEAM_2D = 5, POB_K_BEAM_1D = 6, POB_K_BACKTRACE = 7, POB_K_FORWARD = 8, POB_K_ACCEPTOR = 9, POB_K_COUNT = 10
+  POB_K_BEAM_2D = 5, POB_K_BEAM_1D = 6, POB_K_BACKTRACE = 7, POB_K_FORWARD = 8, POB_K_ACCEPTOR = 9,
+  POB_K_PREFIX_1D = 10, POB_K_PAIR_GAMMA = 11, POB_K_PREFIX_2D = 12, POB_K_COUNT = 13
 };
 /* whole-region device timing: CUDA events recorded on the context's stream */
 int pob_timer_start(pob_ctx* ctx);
@@ -241,6 +244,38 @@ int pob_npy_probe(const char* const* paths, int n, int threads, int64_t* rows, i
                   int32_t* flags, float* first_row_sum);
 int pob_npy_read(const char* const* paths, int n, int threads, const int64_t* rows, int64_t cols, const int64_t* data_off,
                  const int64_t* row_off, float* dst, int32_t* ok);
+
+/* ---------------------------------------------------------------------------------------------
+ * Legacy prefix search (decode --algorithm prefix; the functions of decoding/prefix_search.py).  Inputs are float64
+ * log-probabilities, row-major rows x n_states with the blank LAST, packed at row_off (row_off[0] = 0); letters are
+ * indices 0..n_states-2.  `flavour` selects the reference's arithmetic: POB_PREFIX_NUMPY (np.logaddexp, scipy
+ * logsumexp, LOG_0 = -inf: prefix_search_log, pair_gamma_log, pair_prefix_search_log) or POB_PREFIX_CY (the Cython
+ * helpers' log(exp(a) + exp(b)) and -9999: prefix_search_log_cy, decoding_cy.pair_gamma_log, pair_prefix_search_log_cy).
+ * Labels come back as letter indices packed at lab_off (capacity per item >= rows + 2, for pairs >= max(U, V) + 3).
+ *
+ * pob_prefix_search      replaces: prefix_search.prefix_search_log / _cy (prefix_search.py:116-174 / :176-238), one
+ *                        window per item; out_score = label probability of the returned label.
+ * pob_pair_gamma         replaces: prefix_search.pair_gamma_log (prefix_search.py:35-65) /
+ *                        decoding_cy.pair_gamma_log (decoding_cy.pyx:177-220): dense (U+1) x (V+1) matrix of pair p at
+ *                        gamma_off[p] (gamma_off[p+1] - gamma_off[p] = (U+1)(V+1)).
+ * pob_pair_prefix_search replaces: prefix_search.pair_prefix_search_log / _cy (prefix_search.py:247-310 / :312-385);
+ *                        POB_EUNSUPPORTED when a pair's dense matrix would exceed 1 GB (MEM_LIMIT, pair_decode.py:189).
+ * The C++ envelope variant (PairPrefixSearch.cpp:79-229) is not reproduced: it double-frees (Gamma.h:100).
+ * pob_forward_vec        replaces: prefix_search.forward_vec_log (prefix_search.py:81-97) /
+ *                        decoding_cy.forward_vec_log (decoding_cy.pyx:127-156): one column of the 1D forward algorithm
+ *                        for letter s (negative = counted from the end, -1 the blank) at label position i, from the
+ *                        previous column (NULL when i == 0). */
+enum { POB_PREFIX_NUMPY = 0, POB_PREFIX_CY = 1 };
+int pob_forward_vec(pob_ctx* ctx, int where, const double* y, int rows, int n_states, int flavour, int s, int i,
+                    const double* previous, double* out);
+int pob_prefix_search(pob_ctx* ctx, int where, const double* y, const int64_t* row_off, int n, int n_states,
+                      int flavour, const int64_t* lab_off, uint8_t* out_label, int32_t* out_len, double* out_score,
+                      int32_t* out_status);
+int pob_pair_gamma(pob_ctx* ctx, int where, const double* y1, const int64_t* off1, const double* y2,
+                   const int64_t* off2, int n, int n_states, int flavour, const int64_t* gamma_off, double* out_gamma);
+int pob_pair_prefix_search(pob_ctx* ctx, int where, const double* y1, const int64_t* off1, const double* y2,
+                           const int64_t* off2, int n, int n_states, int flavour, const int64_t* lab_off,
+                           uint8_t* out_label, int32_t* out_len, double* out_score, int32_t* out_status);
 
 /* Counters of the last pob_pair_decode / pob_beam_search_2d call on this context (for roofline math):
  * [0] forward cell updates (update_prob calls), [1] search steps, [2] kernels launched since reset. */

@@ -21,9 +21,11 @@ METHOD = {"row": 0, "row_col": 1}
 
 ST_SHORT_BEAM_SKIP, ST_UNSET_BAND, ST_POOL_OVERFLOW, ST_MAPPING_WRAP = 1, 2, 4, 8
 ST_SKIPPED_LENGTH, ST_SKIPPED_IDENTITY, ST_EMPTY = 16, 32, 64
+ST_MAX_DEPTH = 128
+PREFIX_NUMPY, PREFIX_CY = 0, 1  # arithmetic flavours of the legacy prefix search
 
 K_NAMES = ["viterbi_ctc", "viterbi_flipflop", "nw_band_fill", "nw_traceback", "envelope", "beam_pair",
-           "beam_single", "backtrace", "forward", "acceptor"]
+           "beam_single", "backtrace", "forward", "acceptor", "prefix_search", "pair_gamma", "pair_prefix_search"]
 
 vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
 
@@ -61,6 +63,10 @@ SIGNATURES = {
     "pob_viterbi_acceptor": (i32, [vp, i32, vp, vp, vp, i32, vp, vp]),
     "pob_pair_decode": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "pob_counters": (i32, [vp, vp]),
+    "pob_forward_vec": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp]),
+    "pob_prefix_search": (i32, [vp, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "pob_pair_gamma": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp]),
+    "pob_pair_prefix_search": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "pob_npy_probe": (i32, [vp, i32, i32, vp, vp, vp, vp, vp]),
     "pob_npy_read": (i32, [vp, i32, i32, vp, i64, vp, vp, vp, vp]),
 }

@@ -398,3 +398,104 @@ def align_global_batch(seqs1, seqs2, match=2, mismatch=-1, gap_cost=-1, return_d
             r = r + (dp[dp_off[p]:dp_off[p + 1]].reshape(l1 + 1, l2 + 1).copy(),)
         out.append(r)
     return out
+
+
+# ---- legacy prefix search (decoding/prefix_search.py of the reference) -------------------------------------------
+def _pack_f64(arrays):
+    """float64 log-probability tables (rows x S, blank last) packed row-wise; returns (data, row_off, S)."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in arrays]
+    if not arrs:
+        return np.zeros(8, np.float64), np.zeros(1, np.int64), 0
+    S = arrs[0].shape[1] if arrs[0].ndim == 2 else 0
+    for a in arrs:
+        if a.ndim != 2 or a.shape[1] != S:
+            raise ValueError("every table must be rows x %d" % S)
+    off = np.zeros(len(arrs) + 1, dtype=np.int64)
+    np.cumsum([a.shape[0] for a in arrs], out=off[1:])
+    data = np.zeros(int(off[-1]) * S + 8, dtype=np.float64)
+    if off[-1]:
+        data[:int(off[-1]) * S] = np.concatenate([a.reshape(-1) for a in arrs])
+    return data, off, S
+
+
+def _unpack_labels(lab, lab_off, lens, n):
+    return [lab[int(lab_off[i]):int(lab_off[i]) + int(lens[i])].copy() for i in range(n)]
+
+
+def prefix_search_batch(arrays, flavour=_lib.PREFIX_CY, device=None):
+    """Legacy 1D prefix search of every table (one window each).  Returns (labels, scores, status): letter-index
+    arrays, label log-probabilities, POB_ST_* bits.
+
+    replaces prefix_search.prefix_search_log / prefix_search_log_cy (prefix_search.py:116-174 / :176-238)."""
+    data, off, S = _pack_f64(arrays)
+    n = len(off) - 1
+    if n == 0:
+        return [], np.zeros(0), np.zeros(0, np.int32)
+    ctx = get_ctx(device)
+    lab_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.diff(off) + 2, out=lab_off[1:])
+    lab = np.zeros(int(lab_off[-1]) + 8, dtype=np.uint8)
+    lens = np.zeros(n, dtype=np.int32)
+    score = np.zeros(n, dtype=np.float64)
+    st = np.zeros(n, dtype=np.int32)
+    check(lib().pob_prefix_search(ctx.h, _lib.HOST, ptr(data), ptr(off), n, S, flavour, ptr(lab_off), ptr(lab), ptr(lens),
+                                  ptr(score), ptr(st)), "pob_prefix_search")
+    return _unpack_labels(lab, lab_off, lens, n), score, st
+
+
+def pair_gamma_batch(arrays1, arrays2, flavour=_lib.PREFIX_NUMPY, device=None):
+    """Dense (U+1) x (V+1) gamma matrix of every pair (prefix_search.py:35-65 / decoding_cy.pyx:177-220)."""
+    d1, o1, S = _pack_f64(arrays1)
+    d2, o2, S2 = _pack_f64(arrays2)
+    n = len(o1) - 1
+    if n != len(o2) - 1 or (n and S != S2):
+        raise ValueError("the two reads of a pair must have the same alphabet")
+    if n == 0:
+        return []
+    ctx = get_ctx(device)
+    goff = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum((np.diff(o1) + 1) * (np.diff(o2) + 1), out=goff[1:])
+    out = np.zeros(int(goff[-1]) + 8, dtype=np.float64)
+    check(lib().pob_pair_gamma(ctx.h, _lib.HOST, ptr(d1), ptr(o1), ptr(d2), ptr(o2), n, S, flavour, ptr(goff), ptr(out)),
+          "pob_pair_gamma")
+    return [out[int(goff[i]):int(goff[i + 1])].reshape(int(o1[i + 1] - o1[i]) + 1, int(o2[i + 1] - o2[i]) + 1).copy()
+            for i in range(n)]
+
+
+def pair_prefix_search_batch(arrays1, arrays2, flavour=_lib.PREFIX_NUMPY, device=None):
+    """Legacy dense 2D prefix search of every pair.  Returns (labels, scores, status).
+
+    replaces prefix_search.pair_prefix_search_log / _cy (prefix_search.py:247-310 / :312-385)."""
+    d1, o1, S = _pack_f64(arrays1)
+    d2, o2, S2 = _pack_f64(arrays2)
+    n = len(o1) - 1
+    if n != len(o2) - 1 or (n and S != S2):
+        raise ValueError("the two reads of a pair must have the same alphabet")
+    if n == 0:
+        return [], np.zeros(0), np.zeros(0, np.int32)
+    ctx = get_ctx(device)
+    lab_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.maximum(np.diff(o1), np.diff(o2)) + 3, out=lab_off[1:])
+    lab = np.zeros(int(lab_off[-1]) + 8, dtype=np.uint8)
+    lens = np.zeros(n, dtype=np.int32)
+    score = np.zeros(n, dtype=np.float64)
+    st = np.zeros(n, dtype=np.int32)
+    check(lib().pob_pair_prefix_search(ctx.h, _lib.HOST, ptr(d1), ptr(o1), ptr(d2), ptr(o2), n, S, flavour, ptr(lab_off),
+                                       ptr(lab), ptr(lens), ptr(score), ptr(st)), "pob_pair_prefix_search")
+    return _unpack_labels(lab, lab_off, lens, n), score, st
+
+
+def forward_vec(y, s, i, previous=None, flavour=_lib.PREFIX_NUMPY, device=None):
+    """One column of the 1D forward algorithm (prefix_search.py:81-97 / decoding_cy.pyx:127-156)."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    if y.ndim != 2:
+        raise ValueError("expected a (time, alphabet + blank) table")
+    assert i == 0 or previous is not None  # prefix_search.py:84
+    prev = None if previous is None else np.ascontiguousarray(previous, dtype=np.float64)
+    if prev is not None and len(prev) != len(y):
+        raise ValueError("previous must have one entry per timestep")
+    out = np.zeros(max(len(y), 1), dtype=np.float64)
+    ctx = get_ctx(device)
+    check(lib().pob_forward_vec(ctx.h, _lib.HOST, ptr(y), len(y), y.shape[1], flavour, int(s), int(i),
+                                ptr(prev) if prev is not None else None, ptr(out)), "pob_forward_vec")
+    return out[:len(y)].copy()

@@ -5,7 +5,8 @@ thread_local char g_pob_cuda_err[256] = "";
 
 static const char* k_names[POB_K_COUNT] = {"viterbi_ctc", "viterbi_flipflop", "nw_band_fill", "nw_traceback",
                                            "envelope",    "beam_pair",        "beam_single",  "backtrace",
-                                           "forward",     "acceptor"};
+                                           "forward",     "acceptor",         "prefix_search", "pair_gamma",
+                                           "pair_prefix_search"};
 
 extern "C" {
 

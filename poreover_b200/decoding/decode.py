@@ -115,8 +115,9 @@ MODEL_TYPE = {'poreover': 'ctc', 'bonito': 'ctc_merge_repeats', 'guppy': 'ctc_fl
               'flipflop': 'ctc_flipflop'}  # decode.py:172
 
 
-def decode_models(models, algorithm="viterbi", beam_width=25, device=None):
-    """Decode a list of transducers in as few GPU calls as possible (one per model kind)."""
+def decode_models(models, algorithm="viterbi", beam_width=25, device=None, window=400):
+    """Decode a list of transducers in as few GPU calls as possible (one per model kind).  `window`: rows per window of
+    --algorithm prefix (decode.py:180-188)."""
     out = [None] * len(models)
     by_kind = {}
     for i, m in enumerate(models):
@@ -133,7 +134,23 @@ def decode_models(models, algorithm="viterbi", beam_width=25, device=None):
                 raise NotImplementedError("flip-flop beam search is out of scope (the reference's own test fails)")
             seqs = batch.beam_search_batch(arrays, beam_width, MODEL_TYPE[kind], device=device)[0]
         else:
-            raise NotImplementedError("--algorithm prefix is the reference's legacy O(T^2) search; not on the GPU path")
+            # legacy prefix search, window by window (decode.py:179-188); every window of every read in one GPU call
+            assert kind == "poreover"  # decode.py:180
+            from . import prefix_search
+            cuts, owner = [], []
+            for j, a in enumerate(arrays):
+                a64 = np.asarray(a, dtype=np.float64)
+                k = 0
+                while k + window < len(a64):
+                    cuts.append(a64[k:k + window])
+                    owner.append(j)
+                    k += window
+                cuts.append(a64[k:])
+                owner.append(j)
+            labels = batch.prefix_search_batch(cuts, batch._lib.PREFIX_CY, device=device)[0]
+            seqs = [""] * len(arrays)
+            for j, lab in zip(owner, labels):
+                seqs[j] += "".join("ACGT"[int(c)] for c in lab)
         for i, s in zip(idx, seqs):
             out[i] = s
     return out
@@ -171,5 +188,5 @@ def decode(args):
 def decode_helper(in_path, args):
     """decode.py:169-192 for a single file."""
     model = model_from_trace(in_path, args.basecaller)
-    sequence = decode_models([model], args.algorithm, args.beam_width)[0]
+    sequence = decode_models([model], args.algorithm, args.beam_width, window=getattr(args, "window", 400))[0]
     return fasta_format(Path(in_path).stem, sequence)

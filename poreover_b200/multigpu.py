@@ -200,7 +200,8 @@ def decode_files_all_gpus(args, in_files, chunk=4096):
                 if args.algorithm == 'viterbi':
                     return batch.viterbi_batch(payload, args.basecaller, device=ctx, return_maps=False)[0]
                 return batch.beam_search_batch(payload, args.beam_width, dec.MODEL_TYPE[args.basecaller], device=ctx)[0]
-            return dec.decode_models(payload, args.algorithm, args.beam_width, device=ctx)
+            return dec.decode_models(payload, args.algorithm, args.beam_width, device=ctx,
+                                     window=getattr(args, "window", 400))
 
     chunk = max(8, min(chunk, -(-len(in_files) // (4 * world))))
     cost = [size_of(p) for p in in_files]

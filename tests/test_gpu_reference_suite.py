@@ -1,9 +1,9 @@
 """The reference's OWN unit tests, unmodified, against the GPU backend.
 
-`make -C oracle ref` byte-compiles the reference's tests/test_beam.py, test_forward.py, test_transducer.py and their
+`make -C oracle ref` byte-compiles the reference's tests/test_beam.py, test_forward.py, test_transducer.py, test_prefix.py and their
 fixture library tests/testing.py from where they lie into oracle/_ref/reftests/ (build outputs: they travel to the GPU
 box with the other oracle/_ref artefacts; no reference source is copied into the repository).  Here `poreover` and
-`poreover.decoding` are aliased to poreover_b200's drop-in modules in sys.modules and the three suites are run with
+`poreover.decoding` are aliased to poreover_b200's drop-in modules in sys.modules and the suites are run with
 unittest.  Expected failures, by name: the flip-flop *beam tree* cases, which are out of scope
 (the reference's own flip-flop 2D test fails in the reference itself).
 """
@@ -36,7 +36,7 @@ def aliased_reference_package(monkeypatch):
     pkg.align = __import__("poreover_b200.align", fromlist=["align"])
     monkeypatch.setitem(sys.modules, "poreover", pkg)
     monkeypatch.setitem(sys.modules, "poreover.decoding", dec)
-    for name in ("decoding_cpp", "decoding_cy", "transducer", "decode", "envelope"):
+    for name in ("decoding_cpp", "decoding_cy", "transducer", "decode", "envelope", "prefix_search"):
         monkeypatch.setitem(sys.modules, "poreover.decoding." + name, getattr(dec, name))
     monkeypatch.setitem(sys.modules, "poreover.align", pkg.align)
     if not hasattr(np, "product"):  # tests/testing.py:73 uses np.product, removed in NumPy 2
@@ -44,9 +44,9 @@ def aliased_reference_package(monkeypatch):
     # the byte-compiled modules, loaded under their own names ("testing" first: the suites import it)
     import importlib.machinery
     import importlib.util
-    for m in ("testing", "test_beam", "test_forward", "test_transducer"):
+    for m in ("testing", "test_beam", "test_forward", "test_transducer", "test_prefix"):
         monkeypatch.delitem(sys.modules, m, raising=False)
-    for m in ("testing", "test_beam", "test_forward", "test_transducer"):
+    for m in ("testing", "test_beam", "test_forward", "test_transducer", "test_prefix"):
         path = os.path.join(REFTESTS, m + ".pycode")
         loader = importlib.machinery.SourcelessFileLoader(m, path)
         spec = importlib.util.spec_from_loader(m, loader, origin=path)
@@ -55,11 +55,11 @@ def aliased_reference_package(monkeypatch):
         sys.modules[m] = mod
         loader.exec_module(mod)
     yield
-    for m in ("testing", "test_beam", "test_forward", "test_transducer"):
+    for m in ("testing", "test_beam", "test_forward", "test_transducer", "test_prefix"):
         sys.modules.pop(m, None)
 
 
-@pytest.mark.parametrize("suite", ["test_beam", "test_forward", "test_transducer"])
+@pytest.mark.parametrize("suite", ["test_beam", "test_forward", "test_transducer", "test_prefix"])
 def test_reference_suite(aliased_reference_package, suite):
     tests = unittest.defaultTestLoader.loadTestsFromName(suite)
     assert tests.countTestCases() > 0
