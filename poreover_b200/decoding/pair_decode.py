@@ -55,7 +55,9 @@ def get_sequence_mapping(path, kind):
 
 _UNSUPPORTED = (
     ("method", "envelope", "--method split/align are deprecated in the reference and not on the GPU path"),
-    ("algorithm", "beam", "--algorithm prefix is the legacy search and not on the GPU path"),
+    ("algorithm", "beam", "pair-decode --algorithm prefix cannot run in the reference either (pair_decode.py:224 asserts "
+                          "kind == 'poreover' on a value that is 'ctc'); the legacy searches themselves are in "
+                          "poreover_b200.decoding.prefix_search and `decode --algorithm prefix`"),
 )
 
 
