@@ -46,19 +46,9 @@
 namespace {
 
 enum { MODE_1D = 0, MODE_ROW = 1, MODE_ROWCOL = 2 };
-#ifndef POB_MIR_DEPTH
-#define POB_MIR_DEPTH 16
-#endif
-#ifndef POB_MIRROR_PARENT
-#ifndef POB_USE_MIRROR
-#define POB_USE_MIRROR 0  // the clean-band maximum no longer scans (see sweep()): the mirror is compiled out
-#endif
 #ifndef POB_SCAN_WIDTH
-#define POB_SCAN_WIDTH 4
+#define POB_SCAN_WIDTH 4  // independent loads in flight when a clean band has to be scanned (8: no change, 16: spills)
 #endif
-#define POB_MIRROR_PARENT 0  // children read a live parent's prob from its shared-memory mirror
-#endif
-enum { MIR_DEPTH = POB_MIR_DEPTH };  // newest `prob` values of every (active slot, read) mirrored in shared memory
 enum { PS_ROOT = 0, PS_INE = 1, PS_FROZEN = 2, PS_DEAD = 3 };  // where a node's parent values come from
 enum { KID_ACTIVE = 0, KID_REVIVE = 1, KID_FRESH = 2 };
 
@@ -111,8 +101,6 @@ struct BeamParams {
   int n_items, W, mode, NP, CAP0, CAP1, CAPC0, CAPC1, RQ, EMAX;
   int dbg_noreclaim, dbg_noreuse, dbg_long;
   int inspect_every;        // the retire queue is inspected every this many expansions (its headers are cold)
-  int mir_off;              // shared-memory prob mirror: byte offset, or -1 when it does not fit
-  int mir_depth;            // its depth: the newest mir_depth (power of two) values of every (active slot, read)
   int col_off;              // column records in shared memory: byte offset, or -1 (global workspace)
   int prefetch;             // pull the probability rows / envelope entries of coming steps towards the SM
   double* dbg_trace;        // optional: [step][2] = (top score, sum of beam scores) after each prune
@@ -208,8 +196,6 @@ struct EngState {
                     // build_envelope's repair pass clamps some rows far back, envelope.py:82-85)
   int cap[2], mask[2];
   ReadView rv[2];
-  int mir_off;  // byte offset in pob_smem of the prob mirror (mdepth newest values per active slot and read), -1 = off
-  int mdepth, mdmask;
   uint32_t* trace;
 };
 __shared__ EngState g_es;
@@ -299,11 +285,6 @@ template <int MODEL, int EM_CT = 0, int W_CT = 0, int MODE_CT = -1>
 struct Engine {
   typedef Entry<MODEL> Ent;
 
-  // byte offset of the prob mirror in shared memory: in the specialised instantiation it follows from the layout
-  // (must match smem_bytes(); the launcher only picks that instantiation when the mirror is on and sits there)
-  static constexpr int MIR_OFF_CT =
-      EM_CT ? (int)(((224 * EM_CT + 4 * ((W_CT + 3) & ~3) + 4 * SH_COUNT + 5 * ((EM_CT + 15) & ~15) + 4 * ((EM_CT + 3) & ~3) + 8 * EM_CT) + 15) / 16 * 16) : -2;
-  __device__ __forceinline__ static int mir_off() { return EM_CT ? MIR_OFF_CT : g_es.mir_off; }
   // letters of the alphabet: the specialised instantiations are only launched on five-state reads
   __device__ __forceinline__ static int nbase() { return EM_CT ? 4 : g_es.nbase; }
 
@@ -331,19 +312,6 @@ struct Engine {
   __device__ __forceinline__ Ent* wbase(int slot, int r) const {
     return reinterpret_cast<Ent*>(g_es.win[r]) + (size_t)slot * g_es.cap[r];
   }
-
-  // Shared-memory mirror of the newest MIR_DEPTH `prob` values of an active (slot, read): the clean-band maximum
-  // reads them from here instead of the window in global memory (which is served from L2 at best).  Valid for the
-  // time keys [mlo, mhi); every write of a window entry of an active node also writes the mirror.  A node that has
-  // just taken its active slot (a_che < 0: nothing written yet) has an empty mirror whatever the bounds say.
-  __device__ __forceinline__ double* mir_base(int a, int r) const {
-    // rows are mdepth + 1 apart: an odd stride in 8-byte units keeps lanes that read the same timestep on distinct banks
-    return reinterpret_cast<double*>(pob_smem + mir_off()) + (size_t)(2 * a + r) * (MIR_DEPTH + 1);
-  }
-  __device__ __forceinline__ int* mir_lo() const {
-    return reinterpret_cast<int*>(pob_smem + mir_off() + (size_t)(EM_CT ? EM_CT : g_es.EMAX) * 2 * (MIR_DEPTH + 1) * 8);
-  }
-  __device__ __forceinline__ int* mir_hi() const { return mir_lo() + 2 * g_es.EMAX; }
 
   // value of the root at time t (parent of depth-1 nodes), in the scale of column t (column -1 has scale 0)
   __device__ __forceinline__ double root_prob(int r, int t) const {
@@ -474,15 +442,6 @@ struct Engine {
     cell(in.p_prev, in.ng_prev, in.pv, in.ylast, in.yblank, prob, gp, ng);
     st_ent(wbase(a_slot[a], r) + ((t + 1) & g_es.mask[r]), prob, gp, ng);
     a_maxt[2 * a + r] = -1;  // a_maxp becomes a running maximum: the next sweep scans its clean entries
-    if (POB_USE_MIRROR && mir_off() >= 0) {
-      mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
-      int mlo = mir_lo()[2 * a + r], mhi = mir_hi()[2 * a + r];
-      if (a_che[2 * a + r] < 0) mlo = mhi = 0;  // first write since the node took this slot: the bounds are its predecessor's
-      if (mhi > mlo && t == mhi) mhi = t + 1;
-      else if (!(t >= mlo && t < mhi)) { mlo = t; mhi = t + 1; }
-      if (mhi - mlo > MIR_DEPTH) mlo = mhi - MIR_DEPTH;
-      mir_lo()[2 * a + r] = mlo; mir_hi()[2 * a + r] = mhi;
-    }
     int lo = in.lo, hi = in.hi;
     if (t >= hi) { if (t > hi) lo = t; hi = t + 1; }
     else if (t < lo) { lo = t; hi = t + 1; }
@@ -531,7 +490,6 @@ struct Engine {
     const Ent* pwb;
     const Col* cb;   // column ring of the read
     int lo, hi, plo, phi, pstat, pa, wmask, cmask, last, kref;
-    int pmlo, pmhi;  // timesteps of the parent's prob values that may be read from its shared-memory mirror
     bool same, mixed;
   };
 
@@ -548,18 +506,9 @@ struct Engine {
     I.pstat = a_pstat[a];
     I.same = a_same[a] != 0;
     I.pa = 0; I.plo = 0; I.phi = 0; I.pwb = nullptr;
-    I.pmlo = I.pmhi = 0;
     if (I.pstat == PS_INE) {
       I.pa = a_par[a];
       I.plo = a_lo[2 * I.pa + r]; I.phi = a_hi[2 * I.pa + r]; I.pwb = wbase(a_pslot[a], r);
-      // A live parent's prob values of the last MIR_DEPTH timesteps are in its shared-memory mirror (a child whose last
-      // base differs from the parent's reads prob; the others read gap, which only the window holds).  The parent may
-      // write up to te - 1 during this sweep, which recycles the ring slots of the timesteps below te - MIR_DEPTH; a
-      // parent that has just taken its slot (che < 0) has no mirror yet.
-      if (POB_MIRROR_PARENT && mir_off() >= 0 && !I.same && a_che[2 * I.pa + r] >= 0) {
-        I.pmlo = max(max(mir_lo()[2 * I.pa + r], te - MIR_DEPTH), I.plo);
-        I.pmhi = min(mir_hi()[2 * I.pa + r], I.phi);
-      }
     } else if (I.pstat == PS_FROZEN) {
       I.plo = a_plo[2 * a + r]; I.phi = a_phi[2 * a + r]; I.pwb = wbase(a_pslot[a], r);
     }
@@ -571,7 +520,6 @@ struct Engine {
   }
 
   __device__ __forceinline__ double parent_at(const SwItem& I, int r, int t) const {
-    if (POB_MIRROR_PARENT && t - 1 >= I.pmlo && t - 1 < I.pmhi) return mir_base(I.pa, r)[t & (MIR_DEPTH - 1)];
     if (I.pstat == PS_INE || I.pstat == PS_FROZEN) return frozen_at(I.pwb, t, I.wmask, I.plo, I.phi, I.same);
     if (I.pstat == PS_ROOT) return root_prob(r, t - 1);
     return 0.0;
@@ -611,7 +559,7 @@ struct Engine {
 
   // Private recomputation of the cells [cs, lim) of one (node, read), cs < lim: every parent entry read here is
   // final.  Leaves the node's values at lim - 1 in p_prev / ng_prev / g_prev and folds the new values into maxv.
-  __device__ __forceinline__ void chain(const SwItem& I, int a, int r, int cs, int lim, bool mirror, const ChainIn& C,
+  __device__ __forceinline__ void chain(const SwItem& I, int a, int r, int cs, int lim, const ChainIn& C,
                                         double& p_prev, double& ng_prev, double& g_prev, double& maxv, int& maxt) const {
     p_prev = C.p_prev; ng_prev = C.ng_prev;
     // inputs are requested two timesteps ahead of their use
@@ -624,7 +572,6 @@ struct Engine {
       Ent* o = I.wb + ((t + 1) & I.wmask);
       st_ent(o, prob, gp, ng);
       if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) { ng_prev = ng; g_prev = gp; }
-      if (mirror) mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
       fold_max(maxv, maxt, in_band_scale(I, prob, t), t);
       p_prev = prob;
       yl = yl_n; yb = yb_n; pv = pv_n;
@@ -637,7 +584,7 @@ struct Engine {
   // list per read, so that chains of equal length share a warp), and the LAST warps of the block (which own few items
   // of their own) run one chain per lane.  Only the band maximum travels back (through a_maxp); the values at the end
   // of the chain are in the node's window.
-  __device__ __noinline__ void long_chains(int nl0, int nl1, int s0, int e0, int s1, int e1, bool mirror) {
+  __device__ __noinline__ void long_chains(int nl0, int nl1, int s0, int e0, int s1, int e1) {
     POB_VIEWS
     const int k0 = (nl0 + 31) >> 5, k1 = (nl1 + 31) >> 5;
     // worker index, counted from the end of the block; a block with fewer warps than lists' warps takes several rounds
@@ -655,7 +602,7 @@ struct Engine {
       if (ts < lim) {
         ChainIn C;
         chain_preload(I, r, ts, te, C);
-        chain(I, a, r, ts, lim, mirror, C, p_prev, ng_prev, g_prev, maxv, maxt);
+        chain(I, a, r, ts, lim, C, p_prev, ng_prev, g_prev, maxv, maxt);
       }
       a_maxp[2 * a + r] = maxv;
     }
@@ -707,11 +654,10 @@ struct Engine {
     SwItem I;
     ChainIn C;
     C.p_prev = C.ng_prev = C.yl = C.yb = C.pv = C.yl_n = C.yb_n = C.pv_n = 0.0;
-    I.lo = I.hi = I.plo = I.phi = I.pa = I.wmask = I.cmask = I.last = I.kref = I.pmlo = I.pmhi = 0; I.pstat = PS_DEAD; I.same = I.mixed = false;
+    I.lo = I.hi = I.plo = I.phi = I.pa = I.wmask = I.cmask = I.last = I.kref = 0; I.pstat = PS_DEAD; I.same = I.mixed = false;
     I.wb = nullptr; I.pwb = nullptr; I.cb = nullptr;
     PCLK(12);
     deferred_finalize();
-    const bool mirror = POB_USE_MIRROR && mir_off() >= 0;
     PCLK(13);
     if (on && te > ts) {
       load_item(a, r, ts, te, I);
@@ -805,11 +751,11 @@ struct Engine {
 #ifndef POB_HOIST
       chain_preload(I, r, cs, te, C);
 #endif
-      if (!longi) chain(I, a, r, cs, limA, mirror, C, p_prev, ng_prev, g_prev, maxv, maxt);
+      if (!longi) chain(I, a, r, cs, limA, C, p_prev, ng_prev, g_prev, maxv, maxt);
     }
 #ifdef POB_LONGQ
     if (nl0 + nl1 > 0) {
-      if ((int)blockDim.x - 1 - tid < 32 * (((nl0 + 31) >> 5) + ((nl1 + 31) >> 5))) long_chains(nl0, nl1, s0, e0, s1, e1, mirror);
+      if ((int)blockDim.x - 1 - tid < 32 * (((nl0 + 31) >> 5) + ((nl1 + 31) >> 5))) long_chains(nl0, nl1, s0, e0, s1, e1);
       __syncthreads();
       if (longi) maxv = a_maxp[2 * a + r];
     }
@@ -891,7 +837,6 @@ struct Engine {
             st_ent(o, prob, gp, ng);
             if constexpr (MODEL == POB_MODEL_CTC_MERGE_REPEATS) ng_prev = ng;
             pb.x = prob; pb.y = gp;
-            if (mirror) mir_base(a, r)[(t + 1) & (MIR_DEPTH - 1)] = prob;
             fold_max(maxv, maxt, in_band_scale(I, prob, t), t);
             p_prev = prob;
           } else {
@@ -920,13 +865,6 @@ struct Engine {
         if (hi - lo > g_es.cap[r]) lo = hi - g_es.cap[r];
         a_lo[2 * a + r] = lo; a_hi[2 * a + r] = hi;
         a_che[2 * a + r] = te;
-        if (mirror) {
-          // this sweep wrote [cs, te): joined with what the mirror held when the two ranges touch
-          const int mlo = mir_lo()[2 * a + r], mhi = mir_hi()[2 * a + r];
-          int nlo = cs;
-          if (!was_fresh && mhi > mlo && cs >= mlo && cs <= mhi) nlo = mlo;
-          mir_lo()[2 * a + r] = max(nlo, te - MIR_DEPTH); mir_hi()[2 * a + r] = te;
-        }
         a_maxp[2 * a + r] = maxv;  // reset + max over the band
         a_maxk[2 * a + r] = kmax;
         a_maxt[2 * a + r] = maxt;
@@ -1396,7 +1334,6 @@ __device__ void Engine<MODEL, EM_CT, W_CT, MODE_CT>::run_item(const BeamParams& 
     g_es.W = G.W; g_es.NP = G.NP; g_es.RQ = G.RQ; g_es.EMAX = G.EMAX; g_es.mode = G.mode;
     g_es.noreclaim = G.dbg_noreclaim; g_es.inspect_every = G.inspect_every; g_es.longq = G.dbg_long;
     g_es.nbase = G.r[0].n_states - 1;
-    g_es.mir_off = G.mir_off; g_es.mdepth = G.mir_depth; g_es.mdmask = G.mir_depth - 1;
     g_es.cap[0] = G.CAP0; g_es.cap[1] = G.CAP1; g_es.mask[0] = G.CAP0 - 1; g_es.mask[1] = G.CAP1 - 1;
     g_es.rv[0] = make_view(G.r[0], item);
     if (G.mode != MODE_1D) g_es.rv[1] = make_view(G.r[1], item); else { g_es.rv[1] = g_es.rv[0]; g_es.rv[1].T = 0; }
@@ -1812,15 +1749,6 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   size_t smem = smem_bytes(W, P.NP, P.EMAX);
   int max_cta_sm = 0;  // 0 = as many as fit (three CTAs of 256 / 288 threads per SM)
   if (const char* e = getenv("POB_DEBUG_CTA_PER_SM")) max_cta_sm = atoi(e);
-  // prob mirror: 2 * EMAX rows of (depth + 1) doubles + two int bounds per (slot, read); the deepest that fits
-  P.mir_off = -1; P.mir_depth = 8;
-  if (mode != MODE_1D) {
-    const size_t budget_cta = (max_cta_sm == 2 ? 227 * 1024 / 2 : max_cta_sm == 1 ? 200 * 1024 : 227 * 1024 / 3) - 1024;
-    const size_t mir = (size_t)P.EMAX * 2 * (MIR_DEPTH + 1) * 8 + (size_t)P.EMAX * 2 * 2 * 4;
-    bool on = POB_USE_MIRROR && smem + mir <= budget_cta;
-    if (const char* e = getenv("POB_DEBUG_MIRROR")) on = on && atoi(e) != 0;
-    if (on) { P.mir_off = (int)smem; P.mir_depth = MIR_DEPTH; smem = pob_align_up(smem + mir, 16); }
-  }
   // column records (64 B per timestep of the band ring) in shared memory when they fit next to the rest
   P.col_off = -1;
   {
@@ -1838,7 +1766,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   if (threads <= 64) {
     threads = 64;
     kern = ctc ? beam_kernel<M0, 64, 12> : beam_kernel<M1, 64, 12>;
-    if (W == 5 && P.EMAX == 32 && (!POB_USE_MIRROR || P.mir_off == (int)smem_bytes(5, 0, 32)) && r1.n_states == 5 && !getenv("POB_DEBUG_NO_CT")) {
+    if (W == 5 && P.EMAX == 32 && r1.n_states == 5 && !getenv("POB_DEBUG_NO_CT")) {
       kern = ctc ? beam_kernel<M0, 64, 12, 32, 5> : beam_kernel<M1, 64, 12, 32, 5>;
       if (mode == MODE_ROWCOL && !P.dbg_noreuse)
         kern = ctc ? beam_kernel<M0, 64, 12, 32, 5, MODE_ROWCOL> : beam_kernel<M1, 64, 12, 32, 5, MODE_ROWCOL>;
@@ -1847,7 +1775,7 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   else if (threads <= 128) { kern = ctc ? beam_kernel<M0, 128, 6> : beam_kernel<M1, 128, 6>; }
   else if (threads <= 256) {
     kern = ctc ? beam_kernel<M0, 256, 3> : beam_kernel<M1, 256, 3>;
-    if (W == 25 && P.EMAX == 128 && (!POB_USE_MIRROR || P.mir_off == (int)smem_bytes(25, 0, 128)) && r1.n_states == 5 && !getenv("POB_DEBUG_NO_CT")) {
+    if (W == 25 && P.EMAX == 128 && r1.n_states == 5 && !getenv("POB_DEBUG_NO_CT")) {
       kern = ctc ? beam_kernel<M0, 256, 3, 128, 25> : beam_kernel<M1, 256, 3, 128, 25>;
       if (mode == MODE_ROWCOL && !P.dbg_noreuse && !getenv("POB_DEBUG_NO_CTMODE"))
         kern = ctc ? beam_kernel<M0, 256, 3, 128, 25, MODE_ROWCOL> : beam_kernel<M1, 256, 3, 128, 25, MODE_ROWCOL>;
@@ -1928,8 +1856,8 @@ int pob_beam_launch(pob_ctx* ctx, const pob_reads& r1, const pob_reads* r2, cons
   P.counters = ctx->d_counters;
   P.trace = trace; P.trace_off = trace_off; P.out_top = top; P.out_score = out_score;
   if (getenv("POB_DEBUG_VERBOSE"))
-    fprintf(stderr, "[pob] beam launch: items %d W %d mode %d NP %d CAP %d/%d span %d/%d threads %d grid %d (%d/SM) smem %zu mirror %d ws/CTA %.1f MB\n",
-            n_items, W, mode, P.NP, P.CAP0, P.CAP1, max_span0, max_span1, threads, grid, per_sm, smem, P.mir_off >= 0 ? P.mir_depth : 0,
+    fprintf(stderr, "[pob] beam launch: items %d W %d mode %d NP %d CAP %d/%d span %d/%d threads %d grid %d (%d/SM) smem %zu ws/CTA %.1f MB\n",
+            n_items, W, mode, P.NP, P.CAP0, P.CAP1, max_span0, max_span1, threads, grid, per_sm, smem,
             stride / 1048576.0);
   if (n_items > 0) {
     pob_prof_scope ps(ctx, mode == MODE_1D ? POB_K_BEAM_1D : POB_K_BEAM_2D);
