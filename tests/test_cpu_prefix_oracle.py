@@ -51,3 +51,53 @@ def test_oracle_on_the_reference_tests_own_toy_tables():
             lab, p = PO.prefix_search(np.log(y), 2, "numpy")
         want, wp = brute(y)
         assert lab == want and abs(p - wp) < 1e-9
+
+
+def test_prefix_host_logic_window_cuts_and_alphabet_checks(monkeypatch):
+    """decode --algorithm prefix cuts a read into windows exactly as decode.py:181-188 does and joins the labels; the
+    module rejects alphabets it cannot map onto the kernels.  The GPU call is replaced by the oracle here (host logic
+    only: no CUDA in the CPU suite)."""
+    from collections import OrderedDict
+
+    import pytest
+
+    from poreover_b200 import batch
+    from poreover_b200.decoding import decode, prefix_search, transducer
+
+    calls = []
+
+    def fake(arrays, flavour=1, device=None):
+        calls.append([len(a) for a in arrays])
+        labs = [np.array(PO.prefix_search(a, a.shape[1] - 1, "cy" if flavour == 1 else "numpy")[0], dtype=np.uint8)
+                for a in arrays]
+        return labs, np.zeros(len(arrays)), np.zeros(len(arrays), np.int32)
+
+    monkeypatch.setattr(batch, "prefix_search_batch", fake)
+    rng = np.random.default_rng(4)
+
+    def table(T):
+        x = rng.random((T, 5)) ** 5
+        x /= x.sum(axis=1, keepdims=True)
+        return np.log(x)
+
+    reads = [table(T) for T in (7, 20, 21, 40)]
+    models = [transducer.poreover(r) for r in reads]
+    seqs = decode.decode_models(models, "prefix", window=10)
+    assert calls == [[7, 10, 10, 10, 10, 1, 10, 10, 10, 10]]  # T = 20: a window and then the empty-free tail (i + window < T)
+    for r, s in zip(reads, seqs):
+        want, i = "", 0
+        while i + 10 < len(r):
+            want += "".join("ACGT"[c] for c in PO.prefix_search(r[i:i + 10], 4, "cy")[0])
+            i += 10
+        want += "".join("ACGT"[c] for c in PO.prefix_search(r[i:], 4, "cy")[0])
+        assert s == want
+    assert prefix_search.prefix_search_windows(reads[2], 10) == seqs[2]
+    y = table(6)
+    with pytest.raises(NotImplementedError):
+        prefix_search.prefix_search_log(y, alphabet=OrderedDict([("C", 1), ("A", 0), ("G", 2), ("T", 3)]))
+    with pytest.raises(ValueError):
+        prefix_search.prefix_search_log(y, alphabet=OrderedDict([("A", 0), ("B", 1)]))  # 5 columns, 2 letters
+    with pytest.raises(NotImplementedError):
+        prefix_search.prefix_search_log(y, return_forward=True)
+    assert prefix_search.remove_gaps("A-C--G") == "ACG"
+    assert prefix_search.greedy_search(np.log(np.array([[.7, .1, .1, .05, .05], [.1, .1, .1, .1, .6], [.1, .6, .1, .1, .1]]))) == "AC"
