@@ -272,7 +272,6 @@ extern __shared__ __align__(128) char pob_smem[];
   const int E4 = (EMAX + 3) & ~3;                                                                   \
   uint32_t* const k32 = (uint32_t*)(a_needed + eb_);                                                \
   int32_t* const a_maxt = (int32_t*)(k32 + E4);   /* [2] timestep that holds a_maxp, -1 = unknown */ \
-  int16_t* const lst = (int16_t*)tmpb;   /* [2][EMAX] work lists of long_chains() */                                  \
   NodeHdr* const hdr = g_es.hdr;                                                                    \
   int32_t* const freelist = g_es.freelist;                                                          \
   int2* const retq = g_es.retq;                                                                     \
@@ -484,7 +483,7 @@ struct Engine {
 
   // Everything a thread needs to recompute cells of one (active slot, read): views of the node's window, of its
   // parent's window and of the read's column records.  Filled from the shared-memory arrays, so that any thread can
-  // take over any item (see long_chains).
+  // take over any item.
   struct SwItem {
     Ent* wb;
     const Ent* pwb;
@@ -579,35 +578,6 @@ struct Engine {
     }
   }
 
-  // Whole-band recomputations (nodes that entered the expanded beam in this step) are dependent chains over the band,
-  // and the threads that own them are scattered over all warps.  With POB_DEBUG_LONG=1 their owners queue them (one
-  // list per read, so that chains of equal length share a warp), and the LAST warps of the block (which own few items
-  // of their own) run one chain per lane.  Only the band maximum travels back (through a_maxp); the values at the end
-  // of the chain are in the node's window.
-  __device__ __noinline__ void long_chains(int nl0, int nl1, int s0, int e0, int s1, int e1) {
-    POB_VIEWS
-    const int k0 = (nl0 + 31) >> 5, k1 = (nl1 + 31) >> 5;
-    // worker index, counted from the end of the block; a block with fewer warps than lists' warps takes several rounds
-    for (int w = (int)blockDim.x - 1 - (int)threadIdx.x; w < 32 * (k0 + k1); w += (int)blockDim.x) {
-      int r = 0, idx = w;
-      if (w >= 32 * k0) { r = 1; idx = w - 32 * k0; }
-      if (idx >= (r ? nl1 : nl0)) continue;
-      const int a = lst[r * EMAX + idx];
-      const int ts = r ? s1 : s0, te = r ? e1 : e0;
-      const int lim = min(te, sh[SH_TB0 + r]);
-      SwItem I;
-      load_item(a, r, ts, te, I);
-      double p_prev, ng_prev, g_prev = 0.0, maxv = 0.0;
-      int maxt = -1;
-      if (ts < lim) {
-        ChainIn C;
-        chain_preload(I, r, ts, te, C);
-        chain(I, a, r, ts, lim, C, p_prev, ng_prev, g_prev, maxv, maxt);
-      }
-      a_maxp[2 * a + r] = maxv;
-    }
-  }
-
   // ---- band sweep over the expanded beam (BeamSearch.h:361-375, :146-156), incremental ----------------
   // reads_mask bit r: read r swept over [s_r, e_r).  Thread (2a + r) owns (active slot a, read r).
   //
@@ -643,7 +613,6 @@ struct Engine {
     const bool used = a < EMAX && a_slot[a] >= 0;
     const bool on = used && ((reads_mask >> r) & 1);
     int cs = 0;
-    bool was_fresh = true, longi = false;
     double p_prev = 0.0, ng_prev = 0.0, g_prev = 0.0, maxv = 0.0;
     int maxt = -1;  // timestep of maxv
 #ifdef POB_COUNT_RESCAN
@@ -662,26 +631,17 @@ struct Engine {
     if (on && te > ts) {
       load_item(a, r, ts, te, I);
       const int che = a_che[2 * a + r];
-      was_fresh = che < 0;
       cs = full ? ts : min(max(che, ts), te);
       if (I.pstat == PS_INE) {
         const int pche = a_che[2 * I.pa + r];
         const int pcs = full ? ts : min(max(pche, ts), te);
         atomicMin(&sh[SH_TB0 + r], pcs + 1);
       }
-      // a node that entered the expanded beam in this step recomputes its whole band: optionally queued for long_chains()
-#ifdef POB_LONGQ
-      longi = g_es.longq && !full && was_fresh && te - ts >= 2;
-      if (longi) lst[r * EMAX + atomicAdd(&sh[SH_NL0 + r], 1)] = (int16_t)a;
-#endif
-#ifdef POB_HOIST
-      if (cs < te && !longi) {
-        chain_preload(I, r, cs, te, C);
-        // a long private chain (new node: whole band): pull the rest of the parent's entries into L1 (four to a line)
-        if (te - cs > 2 && I.pwb != nullptr)
-          for (int q = cs + 2; q < te; q += 4) prefetch_l1(I.pwb + (q & I.wmask));
-      }
-#endif
+      // (a node that entered the expanded beam in this step recomputes its whole band in phase A, as one dependent
+      // chain on its own thread.  Queueing those chains for the last warps of the block, one chain per lane, lowered
+      // the instruction count and raised the latency of the step -- 4.2 k against 5.9 k pairs/s, its noinline call
+      // cost more registers than it saved -- and loading the chain's first inputs before the barrier below was +2 % at
+      // two CTAs per SM and -4 % at three: both are gone from the source.)
       PCLK(14);
       // Clean part of the band, [c0, c1): its entries are final and only their maximum is needed.  The band maximum of
       // the node's previous sweep (a_maxp, in the scale a_maxk, found at timestep a_maxt) is that maximum whenever its
@@ -739,27 +699,15 @@ struct Engine {
     __syncthreads();
     PCLK(1);
     const int Tb0 = sh[SH_TB0], Tb1 = sh[SH_TB1];
-#ifdef POB_LONGQ
-    const int nl0 = sh[SH_NL0], nl1 = sh[SH_NL1];
-#endif
     const int Tb = r ? Tb1 : Tb0;  // first timestep of this read that needs the synchronised loop
     bool computing = false;        // p_prev / ng_prev hold the node's values at the previous timestep
     const int limA = min(te, Tb);
     // ---- phase A: private work [cs, min(te, Tb))
     if (on && te > ts && cs < limA) {
       computing = true;
-#ifndef POB_HOIST
       chain_preload(I, r, cs, te, C);
-#endif
-      if (!longi) chain(I, a, r, cs, limA, C, p_prev, ng_prev, g_prev, maxv, maxt);
+      chain(I, a, r, cs, limA, C, p_prev, ng_prev, g_prev, maxv, maxt);
     }
-#ifdef POB_LONGQ
-    if (nl0 + nl1 > 0) {
-      if ((int)blockDim.x - 1 - tid < 32 * (((nl0 + 31) >> 5) + ((nl1 + 31) >> 5))) long_chains(nl0, nl1, s0, e0, s1, e1);
-      __syncthreads();
-      if (longi) maxv = a_maxp[2 * a + r];
-    }
-#endif
     PCLK(2);
     // ---- phase B: synchronised time-major loop over [Tb, te)
     const int iters = max(max((reads_mask & 1) ? e0 - Tb0 : 0, (reads_mask & 2) ? e1 - Tb1 : 0), 0);
@@ -768,12 +716,6 @@ struct Engine {
       const bool inB = on && te > ts && Tb < te;
       double ylast = 0, yblank = 0;
       if (inB) {
-        if (longi && computing) {
-          // the chain ran on another thread: its last values are in the window
-          const Ent* se = I.wb + (Tb & I.wmask);
-          const EV v = ld_ent(se);
-          p_prev = v.prob; g_prev = v.gap; ng_prev = v.nogap;
-        }
         // publish the node's value at Tb-1: computed in phase A, or a stored clean entry
         double2 pb; pb.x = 0.0; pb.y = 0.0;
         const int tp = Tb - 1;
